@@ -1,0 +1,119 @@
+/* piper_b200 — C ABI of the B200-native VITS inference engine.
+ *
+ * Drop-in boundary: these entry points replace what piper's C++ host obtains from onnxruntime
+ * for the phoneme-ids -> waveform path.  Each one names the reference interface it stands in for
+ * (paths relative to the rhasspy/piper tree, commit 73c04d8):
+ *
+ *   pb200_voice_load        <- loadModel(): Ort::Env + Ort::SessionOptions + Ort::Session(modelPath)
+ *                              src/cpp/piper.cpp:262-306 (called from loadVoice, :309-334)
+ *   pb200_voice_free        <- ~ModelSession (Ort::Session release), src/cpp/piper.hpp:78-85
+ *   pb200_synthesize        <- inside synthesize(): CreateTensor x3(4) + session.onnx.Run(...)
+ *                              + GetTensorData/GetShape, src/cpp/piper.cpp:342-400
+ *   pb200_release           <- Ort::detail::OrtRelease(outputTensors[i].release()), piper.cpp:434-440
+ *   pb200_synthesize_int16  <- the same Run plus the host loops that peak-normalise to int16,
+ *                              src/cpp/piper.cpp:411-431 (python twin: src/python_run/piper/util.py:5-12)
+ *   pb200_synthesize_batch  <- the graph's dynamic batch axis (export_onnx.py:96-100); no reference
+ *                              caller uses B > 1 (piper.cpp:352), semantics are B independent utterances
+ *   pb200_vocode            <- the decoder half of the reference's streaming export
+ *                              (src/python/piper_train/export_onnx_streaming.py:61-69)
+ *   pb200_last_error        <- the std::runtime_error / Ort::Exception messages thrown up to main
+ *                              (e.g. piper.cpp:391-393); the C ABI returns codes, the C++ shim rethrows.
+ *
+ * Plain C types only: no torch / CUDA types cross this boundary.  All calls are blocking and may be
+ * issued repeatedly from one thread per voice handle (the reference's threading contract).
+ * There is NO CPU fallback: without a usable sm_100 device pb200_voice_load fails.
+ */
+#ifndef PIPER_B200_H_
+#define PIPER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_OK 0
+#define PB200_ERROR 1
+
+typedef struct pb200_voice pb200_voice;
+
+/* Inferred from the .onnx initializer shapes (hyper-parameters are not in the voice JSON). */
+typedef struct pb200_voice_info {
+  int32_t n_vocab, hidden, inter, filter, n_heads, n_layers, window;
+  int32_t resblock;        /* 1 (high) or 2 (x-low / low / medium) */
+  int32_t n_upsamples;
+  int32_t hop;             /* samples per frame = prod(upsample_rates) */
+  int32_t up_initial;
+  int32_t device;
+  int64_t n_params;        /* fp32 parameters read from the file */
+  int64_t weight_bytes;    /* packed blob resident in HBM */
+} pb200_voice_info;
+
+/* Noise for the graph's two RandomNormalLike nodes (unseeded in the reference export).
+ * eps_dp : item-major, for item b a [2][len_b] block          (models.py:111)   or NULL
+ * eps_z  : [B][inter][z_stride], only the first y_len_b columns are read (models.py:718) or NULL
+ * NULL pointers draw N(0,1) on the device from a Philox stream keyed by `seed`. */
+typedef struct pb200_noise {
+  const float* eps_dp;
+  const float* eps_z;
+  int64_t z_stride;
+  uint64_t seed;
+} pb200_noise;
+
+/* Parse `onnx_path`, pack the weights and upload them to CUDA device `device`. */
+int pb200_voice_load(const char* onnx_path, int device, pb200_voice** out);
+void pb200_voice_free(pb200_voice* v);
+int pb200_voice_get_info(const pb200_voice* v, pb200_voice_info* info);
+
+/* Host-only (no GPU needed): parse + pack and describe the result as JSON into buf (NUL-terminated,
+ * truncated to cap).  Returns PB200_OK or PB200_ERROR. */
+int pb200_voice_describe(const char* onnx_path, char* buf, int64_t cap);
+/* Host-only: copy the packed weight blob (for loader tests).  *n_floats in: capacity, out: size. */
+int pb200_voice_pack(const char* onnx_path, float* blob, int64_t* n_floats);
+
+/* One utterance.  ids: int64 [n_ids]; scales = {noise_scale, length_scale, noise_w};
+ * sid must be NULL (single-speaker voices).  On success *audio points at fp32 samples owned by the
+ * engine (pinned host memory), valid until the next call on this voice or pb200_release(). */
+int pb200_synthesize(pb200_voice* v, const int64_t* ids, int64_t n_ids, const float scales[3], const int64_t* sid,
+                     const pb200_noise* noise, const float** audio, int64_t* n_samples, double* infer_seconds);
+
+/* B utterances (ragged): ids_concat int64 [sum lens], lens int64 [B].  Audio is the concatenation of the
+ * items' valid samples; n_samples[b] = y_len_b * hop.  w_ceil_override (int32, ids_concat layout) replaces
+ * the predicted per-id frame counts when non-NULL (benchmark / test control of T'). */
+int pb200_synthesize_batch(pb200_voice* v, const int64_t* ids_concat, const int64_t* lens, int32_t B,
+                           const float scales[3], const pb200_noise* noise, const int32_t* w_ceil_override,
+                           const float** audio, int64_t* n_samples, double* infer_seconds);
+
+/* As above with the int16 peak-normalisation of piper.cpp:411-431 fused on the GPU (per utterance). */
+int pb200_synthesize_int16(pb200_voice* v, const int64_t* ids_concat, const int64_t* lens, int32_t B,
+                           const float scales[3], const pb200_noise* noise, const int16_t** audio,
+                           int64_t* n_samples, double* infer_seconds);
+
+/* Generator only: z fp32 [B][inter][frames] (host) -> audio [B][frames*hop]. */
+int pb200_vocode(pb200_voice* v, const float* z, int32_t B, int64_t frames, const float** audio,
+                 double* infer_seconds);
+
+/* Device-resident timing: stage inputs in HBM once, then run the kernels (no host<->device traffic except
+ * the B-int output-length read-back the graph's data-dependent shape requires). */
+int pb200_stage(pb200_voice* v, const int64_t* ids_concat, const int64_t* lens, int32_t B, const float scales[3],
+                const pb200_noise* noise, const int32_t* w_ceil_override);
+int pb200_run_staged(pb200_voice* v, int64_t* total_samples, float* device_ms);
+/* enc, duration predictor, host length round-trip, expand+flow, generator — CUDA-event ms of the last run */
+int pb200_stage_times(const pb200_voice* v, float ms[5]);
+
+void pb200_release(pb200_voice* v, const void* audio);
+
+/* Test taps: when debug is on, intermediate tensors of the last call are kept on the host.
+ * names: x, stats, logw, cum, z_p, z, up<i>, stage<i>, audio.  Copies item b as [C][len] into buf. */
+int pb200_set_debug(pb200_voice* v, int32_t on);
+int pb200_tap_shape(const pb200_voice* v, const char* name, int32_t b, int32_t* channels, int32_t* len);
+int pb200_tap_read(const pb200_voice* v, const char* name, int32_t b, float* buf, int64_t cap_floats);
+
+uint64_t pb200_launch_count(void);
+const char* pb200_last_error(void);
+const char* pb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIPER_B200_H_ */

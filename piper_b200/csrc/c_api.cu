@@ -1,0 +1,195 @@
+// C ABI of the engine (declared in include/piper_b200.h).
+#include "../../include/piper_b200.h"
+
+#include <cstring>
+#include <algorithm>
+#include <exception>
+#include <stdexcept>
+#include <string>
+
+#include "engine.h"
+
+struct pb200_voice {
+  pb200::Engine engine;
+  pb200_voice(const char* path, int device) : engine(path, device) {}
+};
+
+namespace {
+thread_local std::string g_error;
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return PB200_OK;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+  } catch (...) {
+    g_error = "unknown error";
+  }
+  return PB200_ERROR;
+}
+
+pb200::NoiseSpec to_spec(const pb200_noise* n) {
+  pb200::NoiseSpec s;
+  if (n) {
+    s.eps_dp = n->eps_dp;
+    s.eps_z = n->eps_z;
+    s.z_stride = n->z_stride;
+    s.seed = n->seed;
+  }
+  return s;
+}
+}  // namespace
+
+extern "C" {
+
+int pb200_voice_load(const char* onnx_path, int device, pb200_voice** out) {
+  return guarded([&] {
+    if (!onnx_path || !out) throw std::runtime_error("pb200_voice_load: null argument");
+    *out = new pb200_voice(onnx_path, device);
+  });
+}
+
+void pb200_voice_free(pb200_voice* v) { delete v; }
+
+int pb200_voice_get_info(const pb200_voice* v, pb200_voice_info* info) {
+  return guarded([&] {
+    if (!v || !info) throw std::runtime_error("pb200_voice_get_info: null argument");
+    const pb200::VoiceSpec& s = v->engine.spec();
+    info->n_vocab = s.n_vocab; info->hidden = s.hidden; info->inter = s.inter; info->filter = s.filter;
+    info->n_heads = s.n_heads; info->n_layers = s.n_layers; info->window = s.window; info->resblock = s.resblock;
+    info->n_upsamples = int32_t(s.up_rates.size()); info->hop = s.hop; info->up_initial = s.up_initial;
+    info->device = v->engine.device();
+    info->n_params = v->engine.voice().n_params;
+    info->weight_bytes = v->engine.weight_bytes();
+  });
+}
+
+int pb200_voice_describe(const char* onnx_path, char* buf, int64_t cap) {
+  return guarded([&] {
+    if (!onnx_path || !buf || cap <= 0) throw std::runtime_error("pb200_voice_describe: bad argument");
+    pb200::PackedVoice pv;
+    pb200::load_voice_file(onnx_path, pv);
+    const std::string s = pb200::describe_voice(pv);
+    const size_t n = std::min<size_t>(s.size(), size_t(cap - 1));
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  });
+}
+
+int pb200_voice_pack(const char* onnx_path, float* blob, int64_t* n_floats) {
+  return guarded([&] {
+    if (!onnx_path || !n_floats) throw std::runtime_error("pb200_voice_pack: null argument");
+    pb200::PackedVoice pv;
+    pb200::load_voice_file(onnx_path, pv);
+    const int64_t need = int64_t(pv.blob.size());
+    if (blob) {
+      if (*n_floats < need) throw std::runtime_error("pb200_voice_pack: buffer too small");
+      std::memcpy(blob, pv.blob.data(), size_t(need) * 4);
+    }
+    *n_floats = need;
+  });
+}
+
+int pb200_synthesize(pb200_voice* v, const int64_t* ids, int64_t n_ids, const float scales[3], const int64_t* sid,
+                     const pb200_noise* noise, const float** audio, int64_t* n_samples, double* infer_seconds) {
+  return guarded([&] {
+    if (!v || !ids || !scales || !audio || !n_samples) throw std::runtime_error("pb200_synthesize: null argument");
+    if (sid) throw std::runtime_error("speaker id given but this build supports single-speaker voices only");
+    int64_t lens[1] = {n_ids};
+    *audio = v->engine.synthesize(ids, lens, 1, scales, to_spec(noise), nullptr, n_samples, infer_seconds);
+  });
+}
+
+int pb200_synthesize_batch(pb200_voice* v, const int64_t* ids_concat, const int64_t* lens, int32_t B,
+                           const float scales[3], const pb200_noise* noise, const int32_t* w_ceil_override,
+                           const float** audio, int64_t* n_samples, double* infer_seconds) {
+  return guarded([&] {
+    if (!v || !ids_concat || !lens || !scales || !audio || !n_samples)
+      throw std::runtime_error("pb200_synthesize_batch: null argument");
+    *audio = v->engine.synthesize(ids_concat, lens, B, scales, to_spec(noise), w_ceil_override, n_samples, infer_seconds);
+  });
+}
+
+int pb200_synthesize_int16(pb200_voice* v, const int64_t* ids_concat, const int64_t* lens, int32_t B,
+                           const float scales[3], const pb200_noise* noise, const int16_t** audio,
+                           int64_t* n_samples, double* infer_seconds) {
+  return guarded([&] {
+    if (!v || !ids_concat || !lens || !scales || !audio || !n_samples)
+      throw std::runtime_error("pb200_synthesize_int16: null argument");
+    *audio = v->engine.synthesize_int16(ids_concat, lens, B, scales, to_spec(noise), n_samples, infer_seconds);
+  });
+}
+
+int pb200_vocode(pb200_voice* v, const float* z, int32_t B, int64_t frames, const float** audio,
+                 double* infer_seconds) {
+  return guarded([&] {
+    if (!v || !z || !audio) throw std::runtime_error("pb200_vocode: null argument");
+    *audio = v->engine.vocode(z, B, frames, infer_seconds);
+  });
+}
+
+int pb200_stage(pb200_voice* v, const int64_t* ids_concat, const int64_t* lens, int32_t B, const float scales[3],
+                const pb200_noise* noise, const int32_t* w_ceil_override) {
+  return guarded([&] {
+    if (!v || !ids_concat || !lens || !scales) throw std::runtime_error("pb200_stage: null argument");
+    v->engine.stage(ids_concat, lens, B, scales, to_spec(noise), w_ceil_override);
+  });
+}
+
+int pb200_run_staged(pb200_voice* v, int64_t* total_samples, float* device_ms) {
+  return guarded([&] {
+    if (!v) throw std::runtime_error("pb200_run_staged: null argument");
+    const int64_t n = v->engine.run_staged(device_ms);
+    if (total_samples) *total_samples = n;
+  });
+}
+
+int pb200_stage_times(const pb200_voice* v, float ms[5]) {
+  return guarded([&] {
+    if (!v || !ms) throw std::runtime_error("pb200_stage_times: null argument");
+    v->engine.stage_times(ms);
+  });
+}
+
+void pb200_release(pb200_voice*, const void*) {
+  // Output buffers are engine-owned pinned staging areas reused by the next call; nothing to free.
+}
+
+int pb200_set_debug(pb200_voice* v, int32_t on) {
+  return guarded([&] {
+    if (!v) throw std::runtime_error("pb200_set_debug: null argument");
+    v->engine.set_debug(on != 0);
+  });
+}
+
+int pb200_tap_shape(const pb200_voice* v, const char* name, int32_t b, int32_t* channels, int32_t* len) {
+  return guarded([&] {
+    if (!v || !name) throw std::runtime_error("pb200_tap_shape: null argument");
+    const pb200::HostTap* t = v->engine.tap(name);
+    if (!t) throw std::runtime_error(std::string("no tap named '") + name + "' (debug off, or stage not run)");
+    if (b < 0 || b >= t->B) throw std::runtime_error("tap: item index out of range");
+    if (channels) *channels = t->C;
+    if (len) *len = t->len[b];
+  });
+}
+
+int pb200_tap_read(const pb200_voice* v, const char* name, int32_t b, float* buf, int64_t cap_floats) {
+  return guarded([&] {
+    if (!v || !name || !buf) throw std::runtime_error("pb200_tap_read: null argument");
+    const pb200::HostTap* t = v->engine.tap(name);
+    if (!t) throw std::runtime_error(std::string("no tap named '") + name + "'");
+    if (b < 0 || b >= t->B) throw std::runtime_error("tap: item index out of range");
+    const int L = t->len[b];
+    if (int64_t(t->C) * L > cap_floats) throw std::runtime_error("tap: buffer too small");
+    for (int c = 0; c < t->C; ++c)
+      std::memcpy(buf + size_t(c) * L, t->data.data() + (size_t(b) * t->C + c) * t->pitch, size_t(L) * 4);
+  });
+}
+
+uint64_t pb200_launch_count(void) { return pb200::launch_count(); }
+const char* pb200_last_error(void) { return g_error.c_str(); }
+const char* pb200_version(void) { return "piper_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

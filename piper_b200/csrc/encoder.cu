@@ -1,0 +1,247 @@
+// Text-encoder kernels: embedding gather, relative-position multi-head attention, channel LayerNorm.
+//
+// Reference: TextEncoder.forward (models.py:198-209), Encoder.forward (attentions.py:60-74),
+// MultiHeadAttention.attention (attentions.py:225-272) with the banded closed form of the
+// relative-position terms (validated there to 1.8e-7):
+//     S[i,j]  = (q_i/sqrt(dk)) . k_j  +  [|j-i| <= w] (q_i/sqrt(dk)) . emb_rel_k[j-i+w]
+//     O_i     = sum_j P[i,j] v_j      +  sum_{|j-i|<=w} P[i,j] emb_rel_v[j-i+w]
+// and modules.LayerNorm (modules.py:23-26): LayerNorm over the CHANNEL axis, eps 1e-5.
+#include "kernels.cuh"
+
+#include <stdexcept>
+
+namespace pb200 {
+void count_launch();
+
+namespace {
+
+__global__ void embed_kernel(const int* __restrict__ ids, int ids_pitch, const float* __restrict__ emb, int H,
+                             float scale, View x, const int* __restrict__ len, int Tmax) {
+  const int b = blockIdx.z;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= len[b]) return;
+  const int id = ids[(long long)b * ids_pitch + t];
+  const float* e = emb + (long long)id * H;
+  float* xb = x.p + (long long)b * x.bs;
+  for (int c = blockIdx.y; c < H; c += gridDim.y) xb[(long long)c * x.cs + t] = __ldg(e + c) * scale;
+}
+
+// One warp per query row, 8 query rows per CTA, keys/values streamed through shared memory in
+// chunks of 32 with an online softmax.  dk <= 128 (lane owns channels d = lane + 32*r, r < 4).
+constexpr int ATT_Q = 8;
+constexpr int ATT_MAXR = 4;
+
+__global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, const float* __restrict__ rel_k,
+                                                            const float* __restrict__ rel_v, int H, int dk, int window,
+                                                            const int* __restrict__ len) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int T = len[b];
+  const int i0 = blockIdx.x * ATT_Q;
+  if (i0 >= T) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrel = 2 * window + 1;
+  float* Ks = sm;                       // [dk][33]
+  float* Vs = Ks + dk * 33;             // [dk][33]
+  float* Qs = Vs + dk * 33;             // [ATT_Q][dk]
+  float* Rl = Qs + ATT_Q * dk;          // [ATT_Q][nrel]   relative-key logits per query
+  float* Ev = Rl + ATT_Q * nrel;        // [nrel][dk]      emb_rel_v
+
+  const float* base = qkv.p + (long long)b * qkv.bs;
+  const float* qg = base + (long long)(h * dk) * qkv.cs;
+  const float* kg = base + (long long)(H + h * dk) * qkv.cs;
+  const float* vg = base + (long long)(2 * H + h * dk) * qkv.cs;
+
+  for (int idx = threadIdx.x; idx < ATT_Q * dk; idx += 256) {
+    const int qi = idx / dk, d = idx - qi * dk;
+    const int i = i0 + qi;
+    Qs[idx] = i < T ? qg[(long long)d * qkv.cs + i] / sqrtf((float)dk) : 0.f;   // query / sqrt(k_channels), attentions.py:232
+  }
+  for (int idx = threadIdx.x; idx < nrel * dk; idx += 256) Ev[idx] = rel_v[idx];
+  __syncthreads();
+  // relative-key logits: Rl[qi][r] = q_i . emb_rel_k[r]
+  for (int r = 0; r < nrel; ++r) {
+    float p = 0.f;
+    for (int d = lane; d < dk; d += 32) p += Qs[warp * dk + d] * __ldg(rel_k + r * dk + d);
+    for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if (lane == 0) Rl[warp * nrel + r] = p;
+  }
+  __syncwarp();
+
+  const int i = i0 + warp;
+  float m_run = -INFINITY, l_run = 0.f;
+  float acc[ATT_MAXR] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int j0 = 0; j0 < T; j0 += 32) {
+    __syncthreads();  // previous chunk fully consumed
+    for (int idx = threadIdx.x; idx < dk * 32; idx += 256) {
+      const int d = idx >> 5, jj = idx & 31;
+      const int j = j0 + jj;
+      float kv = 0.f, vv = 0.f;
+      if (j < T) {
+        kv = kg[(long long)d * qkv.cs + j];
+        vv = vg[(long long)d * qkv.cs + j];
+      }
+      Ks[d * 33 + jj] = kv;
+      Vs[d * 33 + jj] = vv;
+    }
+    __syncthreads();
+    if (i < T) {
+      const int j = j0 + lane;
+      float s = 0.f;
+      const float* q = Qs + warp * dk;
+      for (int d = 0; d < dk; ++d) s = fmaf(q[d], Ks[d * 33 + lane], s);
+      const int rel = j - i + window;
+      if (rel >= 0 && rel < nrel) s += Rl[warp * nrel + rel];
+      if (j >= T) s = -INFINITY;   // keys past the utterance: masked_fill(-1e4) -> exp underflows to exactly 0
+      float cmax = s;
+      for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      const float m_new = fmaxf(m_run, cmax);
+      const float corr = expf(m_run - m_new);
+      const float p = expf(s - m_new);
+      float psum = p;
+      for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      l_run = l_run * corr + psum;
+#pragma unroll
+      for (int r = 0; r < ATT_MAXR; ++r) acc[r] *= corr;
+      const int jn = min(32, T - j0);
+      for (int jj = 0; jj < jn; ++jj) {
+        const float pj = __shfl_sync(0xffffffffu, p, jj);
+        const int relj = j0 + jj - i + window;
+        const bool band = relj >= 0 && relj < nrel;
+#pragma unroll
+        for (int r = 0; r < ATT_MAXR; ++r) {
+          const int d = lane + 32 * r;
+          if (d < dk) {
+            float v = Vs[d * 33 + jj];
+            if (band) v += Ev[relj * dk + d];
+            acc[r] = fmaf(pj, v, acc[r]);
+          }
+        }
+      }
+      m_run = m_new;
+    }
+  }
+  if (i < T) {
+    float* ob = out.p + (long long)b * out.bs + (long long)(h * dk) * out.cs;
+#pragma unroll
+    for (int r = 0; r < ATT_MAXR; ++r) {
+      const int d = lane + 32 * r;
+      if (d < dk) ob[(long long)d * out.cs + i] = acc[r] / l_run;
+    }
+  }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// LayerNorm over channels for a tile of 32 time steps; 8 warps split the channel axis.
+// Values are staged in shared memory [C][33] so the (optional) depthwise conv is evaluated once.
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+  extern __shared__ float sm[];
+  __shared__ float red[8][32];
+  const int b = blockIdx.z;
+  const int T = a.len[b];
+  const int t0 = blockIdx.x * 32;
+  if (t0 >= T) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = t0 + lane;
+  const bool live = t < T;
+  const int C = a.C;
+  const float* ab = a.a.p + (long long)b * a.a.bs;
+
+  for (int c = warp; c < C; c += 8) {
+    float v = 0.f;
+    if (live) {
+      const float* ar = ab + (long long)c * a.a.cs;
+      if (a.mode == LN_DW_GELU) {
+        v = __ldg(a.dw_b + c);
+        const int half = (a.dw_k - 1) / 2;
+        for (int j = 0; j < a.dw_k; ++j) {
+          const int tt = t + (j - half) * a.dw_dil;
+          if (tt >= 0 && tt < T) v = fmaf(__ldg(a.dw_w + c * a.dw_k + j), ar[tt], v);
+        }
+      } else {
+        v = ar[t];
+        if (a.mode == LN_ADD) v += a.b.p[(long long)b * a.b.bs + (long long)c * a.b.cs + t];
+      }
+    }
+    sm[c * 33 + lane] = v;
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int c = warp; c < C; c += 8) s += sm[c * 33 + lane];
+  red[warp][lane] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mean += red[w][lane];
+  mean /= (float)C;
+  __syncthreads();
+  float q = 0.f;
+  for (int c = warp; c < C; c += 8) {
+    const float d = sm[c * 33 + lane] - mean;
+    q = fmaf(d, d, q);
+  }
+  red[warp][lane] = q;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) var += red[w][lane];
+  var /= (float)C;
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  if (!live) return;
+  float* yb = a.y.p + (long long)b * a.y.bs;
+  for (int c = warp; c < C; c += 8) {
+    float v = (sm[c * 33 + lane] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
+    if (a.mode == LN_GELU_RES || a.mode == LN_DW_GELU) v = gelu_erf(v);
+    if (a.mode == LN_GELU_RES) v += a.r.p[(long long)b * a.r.bs + (long long)c * a.r.cs + t];
+    yb[(long long)c * a.y.cs + t] = v;
+  }
+}
+
+}  // namespace
+
+void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float scale, View x, const int* len, int B,
+                  int Tmax, cudaStream_t st) {
+  if (B <= 0 || Tmax <= 0) return;
+  dim3 grid((Tmax + 127) / 128, 8, B);
+  embed_kernel<<<grid, 128, 0, st>>>(ids, ids_pitch, emb, H, scale, x, len, Tmax);
+  count_launch();
+}
+
+void launch_rel_attention(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
+                          const int* len, int B, int Tmax, cudaStream_t st) {
+  if (B <= 0 || Tmax <= 0) return;
+  const int dk = H / n_heads;
+  if (dk > 32 * ATT_MAXR) throw std::runtime_error("attention: head width > 128 is not supported");
+  const int nrel = 2 * window + 1;
+  const size_t smem = size_t(2 * dk * 33 + ATT_Q * dk + ATT_Q * nrel + nrel * dk) * sizeof(float);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaFuncSetAttribute(rel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set[dev & 63] = true;
+  }
+  dim3 grid((Tmax + ATT_Q - 1) / ATT_Q, n_heads, B);
+  rel_attention_kernel<<<grid, 256, smem, st>>>(qkv, out, rel_k, rel_v, H, dk, window, len);
+  count_launch();
+}
+
+void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st) {
+  if (B <= 0 || Tmax <= 0) return;
+  const size_t smem = size_t(a.C) * 33 * sizeof(float);
+  if (smem > 96 * 1024) throw std::runtime_error("layernorm: channel count too large");
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaFuncSetAttribute(layernorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set[dev & 63] = true;
+  }
+  dim3 grid((Tmax + 31) / 32, 1, B);
+  layernorm_kernel<<<grid, 256, smem, st>>>(a);
+  count_launch();
+}
+
+}  // namespace pb200

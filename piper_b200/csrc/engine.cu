@@ -1,0 +1,576 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace pb200 {
+
+#define CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
+  } while (0)
+
+void DeviceBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return;
+  release();
+  size_t want = bytes + bytes / 4 + 256;   // headroom: data-dependent lengths vary call to call
+  CUDA_CHECK(cudaMalloc(&p, want));
+  cap = want;
+}
+void DeviceBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+void PinnedBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return;
+  release();
+  size_t want = bytes + bytes / 4 + 256;
+  CUDA_CHECK(cudaMallocHost(&p, want));
+  cap = want;
+}
+void PinnedBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  cap = 0;
+}
+
+static int round4(int v) { return (v + 3) & ~3; }
+
+Engine::Engine(const std::string& onnx_path, int device) : device_(device) {
+  load_voice_file(onnx_path, voice_);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    throw std::runtime_error(std::string("piper_b200 needs a CUDA device (no CPU fallback): ") +
+                             (e != cudaSuccess ? cudaGetErrorString(e) : "no devices"));
+  if (device < 0 || device >= n_dev) throw std::runtime_error("device index out of range");
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    throw std::runtime_error(std::string("piper_b200 kernels are built for sm_100a only; device is sm_") +
+                             std::to_string(prop.major) + std::to_string(prop.minor));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  for (auto& ev : ev_) CUDA_CHECK(cudaEventCreate(&ev));
+  weights_.ensure(voice_.blob.size() * sizeof(float));
+  CUDA_CHECK(cudaMemcpy(weights_.p, voice_.blob.data(), voice_.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  DeviceBuf* dbs[] = {&weights_, &ids_d_, &len_d_, &ylen_d_, &cum_d_, &logw_d_, &override_d_, &epsdp_d_, &epsoff_d_,
+                      &off_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
+                      &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_};
+  for (auto* d : dbs) d->release();
+  PinnedBuf* pbs[] = {&ids_pin_, &misc_pin_, &audio_pin_, &audio16_pin_, &eps_pin_};
+  for (auto* p : pbs) p->release();
+  for (auto& ev : ev_)
+    if (ev) cudaEventDestroy(ev);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+ConvArgs Engine::conv_args(const ConvW& c, View x, const int* len, int len_scale) const {
+  ConvArgs a;
+  a.x = x;
+  a.w = W(c.w);
+  a.bias = W(c.b);
+  a.len = len;
+  a.len_scale = len_scale;
+  a.ci = c.ci; a.rows = c.rows; a.rows_p = c.rows_p; a.k = c.k; a.dil = c.dil; a.pad = c.pad;
+  a.up = c.up; a.up_pad = c.up_pad;
+  return a;
+}
+
+void Engine::ensure_front(int B, int Tmax) {
+  const VoiceSpec& s = voice_.spec;
+  const int Tp = round4(Tmax);
+  const size_t n = size_t(B) * Tp;
+  ids_d_.ensure(n * 4); len_d_.ensure(size_t(B) * 4); ylen_d_.ensure(size_t(B) * 4);
+  cum_d_.ensure(n * 4); logw_d_.ensure(n * 4); off_d_.ensure(size_t(B) * 8); epsoff_d_.ensure(size_t(B) * 8);
+  x_.ensure(n * s.hidden * 4); t1_.ensure(n * s.hidden * 4); qkv_.ensure(n * 3 * s.hidden * 4);
+  att_.ensure(n * s.hidden * 4); ffn_.ensure(n * s.filter * 4); stats_.ensure(n * 2 * s.inter * 4);
+  g_.ensure(n * s.hidden * 4); h_.ensure(n * s.hidden * 4); u_.ensure(n * s.hidden * 4); v_.ensure(n * s.hidden * 4);
+  pr_.ensure(n * 32 * 4 * ((3 * s.spline_bins - 1 + 31) / 32)); z2_.ensure(n * 2 * 4);
+  peak_d_.ensure(size_t(B) * 4);
+}
+
+void Engine::ensure_back(int B, int Fmax) {
+  const VoiceSpec& s = voice_.spec;
+  const int Fp = round4(Fmax);
+  const size_t n = size_t(B) * Fp;
+  z_.ensure(n * s.inter * 4); fh_.ensure(n * s.hidden * 4); facts_.ensure(n * s.hidden * 4); fout_.ensure(n * s.hidden * 4);
+  size_t per_frame = size_t(s.up_initial);
+  int ch = s.up_initial, rate = 1;
+  for (int u : s.up_rates) {
+    ch /= 2;
+    rate *= u;
+    per_frame = std::max(per_frame, size_t(ch) * rate);
+  }
+  const size_t g = n * per_frame * 4;
+  ga_.ensure(g); gp_.ensure(g); gq_.ensure(g); gs_.ensure(g);
+  audio_d_.ensure(n * s.hop * 4);
+}
+
+void Engine::upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3],
+                           const NoiseSpec& noise, const int32_t* w_ceil_override) {
+  const VoiceSpec& s = voice_.spec;
+  if (B <= 0) throw std::runtime_error("batch size must be positive");
+  if (!ids_concat || !lens) throw std::runtime_error("null input pointer");
+  CUDA_CHECK(cudaSetDevice(device_));
+  int Tmax = 0;
+  int64_t total = 0;
+  for (int b = 0; b < B; ++b) {
+    if (lens[b] <= 0) throw std::runtime_error("empty phoneme-id sequence (input_lengths must be >= 1)");
+    if (lens[b] > (1 << 20)) throw std::runtime_error("phoneme-id sequence too long");
+    Tmax = std::max<int>(Tmax, int(lens[b]));
+    total += lens[b];
+  }
+  B_ = B; Tmax_ = Tmax; Tp_ = round4(Tmax);
+  for (int i = 0; i < 3; ++i) scales_[i] = scales[i];
+  seed_ = noise.seed;
+  ensure_front(B, Tmax);
+  len_h_.assign(B, 0);
+  // ids: int64 host -> int32 [B][Tp] (validated: an out-of-range id would index past the embedding table)
+  ids_pin_.ensure(size_t(B) * Tp_ * 4);
+  int* ip = ids_pin_.as<int>();
+  std::memset(ip, 0, size_t(B) * Tp_ * 4);
+  int64_t pos = 0;
+  for (int b = 0; b < B; ++b) {
+    len_h_[b] = int(lens[b]);
+    for (int t = 0; t < len_h_[b]; ++t) {
+      const int64_t id = ids_concat[pos + t];
+      if (id < 0 || id >= s.n_vocab)
+        throw std::runtime_error("phoneme id " + std::to_string(id) + " outside the voice's symbol table [0," +
+                                 std::to_string(s.n_vocab) + ")");
+      ip[size_t(b) * Tp_ + t] = int(id);
+    }
+    pos += lens[b];
+  }
+  misc_pin_.ensure(size_t(B) * 32);
+  int* lp = misc_pin_.as<int>();
+  for (int b = 0; b < B; ++b) lp[b] = len_h_[b];
+  CUDA_CHECK(cudaMemcpyAsync(ids_d_.p, ip, size_t(B) * Tp_ * 4, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(len_d_.p, lp, size_t(B) * 4, cudaMemcpyHostToDevice, stream_));
+
+  have_eps_dp_ = noise.eps_dp != nullptr;
+  have_eps_z_ = noise.eps_z != nullptr;
+  z_stride_ = noise.z_stride;
+  if (have_eps_dp_) {
+    epsdp_d_.ensure(size_t(total) * 2 * 4);
+    CUDA_CHECK(cudaMemcpyAsync(epsdp_d_.p, noise.eps_dp, size_t(total) * 2 * 4, cudaMemcpyHostToDevice, stream_));
+    long long* op = reinterpret_cast<long long*>(lp + B + (B & 1));
+    long long o = 0;
+    for (int b = 0; b < B; ++b) { op[b] = o; o += 2LL * len_h_[b]; }
+    CUDA_CHECK(cudaMemcpyAsync(epsoff_d_.p, op, size_t(B) * 8, cudaMemcpyHostToDevice, stream_));
+  }
+  if (have_eps_z_) {
+    if (z_stride_ <= 0) throw std::runtime_error("eps_z given without z_stride");
+    const size_t n = size_t(B) * s.inter * size_t(z_stride_);
+    epsz_d_.ensure(n * 4);
+    CUDA_CHECK(cudaMemcpyAsync(epsz_d_.p, noise.eps_z, n * 4, cudaMemcpyHostToDevice, stream_));
+  }
+  have_override_ = w_ceil_override != nullptr;
+  if (have_override_) {
+    override_d_.ensure(size_t(total) * 4 + size_t(B) * Tp_ * 4);
+    // ragged host array -> padded [B][Tp]
+    std::vector<int> tmp(size_t(B) * Tp_, 0);
+    int64_t p2 = 0;
+    for (int b = 0; b < B; ++b) {
+      for (int t = 0; t < len_h_[b]; ++t) {
+        const int v = w_ceil_override[p2 + t];
+        if (v < 0) throw std::runtime_error("negative duration override");
+        tmp[size_t(b) * Tp_ + t] = v;
+      }
+      p2 += len_h_[b];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(override_d_.p, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));   // tmp goes out of scope
+  }
+  // pinned scratch is reused by the next call: make sure the copies have left it
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void Engine::dds(const DDSW& d, View h, View u, View v, int C) {
+  const int* len = len_d_.as<int>();
+  for (const DDSLayerW& l : d.layers) {
+    LnArgs a;
+    a.a = h; a.y = u; a.gamma = W(l.n1.gamma); a.beta = W(l.n1.beta);
+    a.dw_w = W(l.sep_w); a.dw_b = W(l.sep_b); a.dw_k = l.k; a.dw_dil = l.dil;
+    a.C = C; a.mode = LN_DW_GELU; a.len = len;
+    launch_layernorm(a, B_, Tmax_, stream_);
+    ConvArgs c = conv_args(l.pw, u, len, 1);
+    c.y = v; c.epi = EPI_BIAS;
+    launch_conv1d(c, B_, Tmax_, stream_);
+    LnArgs b;
+    b.a = v; b.r = h; b.y = h; b.gamma = W(l.n2.gamma); b.beta = W(l.n2.beta);
+    b.C = C; b.mode = LN_GELU_RES; b.len = len;
+    launch_layernorm(b, B_, Tmax_, stream_);
+  }
+}
+
+void Engine::save_tap(const std::string& name, View v, int C, const int* len_host, int scale) {
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  HostTap t;
+  t.B = B_; t.C = C; t.pitch = v.cs;
+  t.len.resize(B_);
+  for (int b = 0; b < B_; ++b) t.len[b] = len_host[b] * scale;
+  t.data.resize(size_t(B_) * C * v.cs);
+  for (int b = 0; b < B_; ++b)
+    CUDA_CHECK(cudaMemcpy(t.data.data() + size_t(b) * C * v.cs, v.p + (long long)b * v.bs, size_t(C) * v.cs * 4,
+                          cudaMemcpyDeviceToHost));
+  taps_[name] = std::move(t);
+}
+
+const HostTap* Engine::tap(const std::string& name) const {
+  auto it = taps_.find(name);
+  return it == taps_.end() ? nullptr : &it->second;
+}
+
+void Engine::run_front() {
+  const VoiceSpec& s = voice_.spec;
+  const int H = s.hidden, I = s.inter, Tp = Tp_, B = B_, T = Tmax_;
+  const int* len = len_d_.as<int>();
+  if (debug_) taps_.clear();
+  View x = view(x_.as<float>(), H, Tp), t1 = view(t1_.as<float>(), H, Tp), qkv = view(qkv_.as<float>(), 3 * H, Tp),
+       att = view(att_.as<float>(), H, Tp), ffn = view(ffn_.as<float>(), s.filter, Tp),
+       stats = view(stats_.as<float>(), 2 * I, Tp);
+  CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
+  // ---- text encoder (models.py:198-209)
+  launch_embed(ids_d_.as<int>(), Tp, W(voice_.emb), H, std::sqrt(float(H)), x, len, B, T, stream_);
+  for (const EncLayerW& e : voice_.enc) {
+    ConvArgs c = conv_args(e.qkv, x, len, 1);
+    c.y = qkv;
+    launch_conv1d(c, B, T, stream_);
+    launch_rel_attention(qkv, att, W(e.rel_k), W(e.rel_v), H, s.n_heads, s.window, len, B, T, stream_);
+    c = conv_args(e.o, att, len, 1);
+    c.y = t1; c.r = x; c.epi = EPI_RES;
+    launch_conv1d(c, B, T, stream_);
+    LnArgs l;
+    l.a = t1; l.y = x; l.gamma = W(e.ln1.gamma); l.beta = W(e.ln1.beta); l.C = H; l.mode = LN_PLAIN; l.len = len;
+    launch_layernorm(l, B, T, stream_);
+    c = conv_args(e.ffn1, x, len, 1);
+    c.y = ffn; c.epi = EPI_RELU;
+    launch_conv1d(c, B, T, stream_);
+    c = conv_args(e.ffn2, ffn, len, 1);
+    c.y = t1; c.r = x; c.epi = EPI_RES;
+    launch_conv1d(c, B, T, stream_);
+    l.gamma = W(e.ln2.gamma); l.beta = W(e.ln2.beta);
+    launch_layernorm(l, B, T, stream_);
+  }
+  {
+    ConvArgs c = conv_args(voice_.enc_proj, x, len, 1);
+    c.y = stats;
+    launch_conv1d(c, B, T, stream_);
+  }
+  CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
+  if (debug_) {
+    save_tap("x", x, H, len_h_.data(), 1);
+    save_tap("stats", stats, 2 * I, len_h_.data(), 1);
+  }
+  // ---- stochastic duration predictor, reverse (models.py:63-70,108-117)
+  View g = view(g_.as<float>(), H, Tp), h = view(h_.as<float>(), H, Tp), u = view(u_.as<float>(), H, Tp),
+       v = view(v_.as<float>(), H, Tp), z2 = view(z2_.as<float>(), 2, Tp);
+  const int pr_rows = 3 * s.spline_bins - 1;
+  View pr = view(pr_.as<float>(), pr_rows, Tp);
+  {
+    ConvArgs c = conv_args(voice_.dp_pre, x, len, 1);
+    c.y = h;
+    launch_conv1d(c, B, T, stream_);
+    dds(voice_.dp_dds, h, u, v, H);
+    c = conv_args(voice_.dp_proj, h, len, 1);
+    c.y = g;
+    launch_conv1d(c, B, T, stream_);
+  }
+  launch_dp_noise(z2, have_eps_dp_ ? epsdp_d_.as<float>() : nullptr, epsoff_d_.as<long long>(), seed_, scales_[2], len, B,
+                  T, stream_);
+  bool flipped = false;
+  for (const ConvFlowW& cf : voice_.dp_flows) {
+    flipped = !flipped;                       // Flip precedes every ConvFlow in the reversed list
+    const int x0 = flipped ? 1 : 0, x1 = 1 - x0;
+    launch_cf_pre(z2, x0, W(cf.pre_w), W(cf.pre_b), g, h, H, len, B, T, stream_);
+    dds(cf.dds, h, u, v, H);
+    ConvArgs c = conv_args(cf.proj, h, len, 1);
+    c.y = pr;
+    launch_conv1d(c, B, T, stream_);
+    launch_spline_inverse(z2, x1, pr, s.spline_bins, 1.f / std::sqrt(float(H)), 5.0f, len, B, T, stream_);
+  }
+  flipped = !flipped;                         // the Flip before ElementwiseAffine
+  const int lw_ch = flipped ? 1 : 0;
+  launch_durations(z2.offset_channels(lw_ch), voice_.ea_m[0], voice_.ea_scale[0], scales_[1],
+                   have_override_ ? override_d_.as<int>() : nullptr, Tp, cum_d_.as<int>(), Tp, ylen_d_.as<int>(),
+                   logw_d_.as<float>(), len, B, T, stream_);
+  CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
+  // ---- the one data-dependent host round trip: output lengths size everything downstream
+  misc_pin_.ensure(size_t(B) * 32);
+  int* yl = misc_pin_.as<int>();
+  CUDA_CHECK(cudaMemcpyAsync(yl, ylen_d_.p, size_t(B) * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  ylen_h_.assign(yl, yl + B);
+  if (debug_) {
+    HostTap t;
+    t.B = B; t.C = 1; t.pitch = Tp; t.len = len_h_;
+    t.data.resize(size_t(B) * Tp);
+    CUDA_CHECK(cudaMemcpy(t.data.data(), logw_d_.p, size_t(B) * Tp * 4, cudaMemcpyDeviceToHost));
+    taps_["logw"] = t;
+    std::vector<int> cum(size_t(B) * Tp);
+    CUDA_CHECK(cudaMemcpy(cum.data(), cum_d_.p, cum.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < cum.size(); ++i) t.data[i] = float(cum[i]);
+    taps_["cum"] = t;
+  }
+}
+
+void Engine::plan_back() {
+  const VoiceSpec& s = voice_.spec;
+  int Fmax = 0;
+  off_h_.assign(B_, 0);
+  long long off = 0;
+  for (int b = 0; b < B_; ++b) {
+    if (ylen_h_[b] < 1) throw std::runtime_error("internal: non-positive output length");
+    if (ylen_h_[b] > max_frames_)
+      throw std::runtime_error("predicted utterance length " + std::to_string(ylen_h_[b]) + " frames exceeds the limit " +
+                               std::to_string(max_frames_));
+    if (have_eps_z_ && ylen_h_[b] > z_stride_)
+      throw std::runtime_error("eps_z has " + std::to_string(z_stride_) + " columns but the utterance needs " +
+                               std::to_string(ylen_h_[b]));
+    Fmax = std::max(Fmax, ylen_h_[b]);
+    off_h_[b] = off;
+    off += (long long)ylen_h_[b] * s.hop;
+  }
+  total_samples_ = off;
+  Fmax_ = Fmax;
+  Fp_ = round4(Fmax);
+  ensure_back(B_, Fmax);
+  // tight audio layout: item b starts at off[b]
+  audio_d_.ensure(size_t(std::max<long long>(off, 1)) * 4);
+  long long* op = reinterpret_cast<long long*>(misc_pin_.as<int>() + B_ + (B_ & 1));
+  for (int b = 0; b < B_; ++b) op[b] = off_h_[b];
+  CUDA_CHECK(cudaMemcpyAsync(off_d_.p, op, size_t(B_) * 8, cudaMemcpyHostToDevice, stream_));
+}
+
+void Engine::run_generator() {
+  const VoiceSpec& s = voice_.spec;
+  const int B = B_, Fp = Fp_, F = Fmax_;
+  const int* ylen = ylen_d_.as<int>();
+  View z = view(z_.as<float>(), s.inter, Fp);
+  int ch = s.up_initial;
+  View S = view(gs_.as<float>(), ch, Fp);
+  {
+    ConvArgs c = conv_args(voice_.dec_pre, z, ylen, 1);
+    c.y = S;
+    launch_conv1d(c, B, F, stream_);
+  }
+  int rate = 1;
+  const int nk = int(voice_.resblocks.at(0).size());
+  // EPI_MRF mode 2 expects an accumulator initialised by an earlier resblock; every piper preset has 3 kernels
+  if (nk < 2) throw std::runtime_error("generators with a single resblock kernel are not supported");
+  for (size_t st = 0; st < voice_.ups.size(); ++st) {
+    const ConvW& up = voice_.ups[st];
+    const int co = up.rows / up.up;
+    const int Lp_out = Fp * rate * up.up;
+    View A = view(ga_.as<float>(), co, Lp_out);
+    {
+      ConvArgs c = conv_args(up, S, ylen, rate);
+      c.pre = PRE_LRELU; c.slope = 0.1f;           // F.leaky_relu(x, LRELU_SLOPE) before every upsample (models.py:354)
+      c.y = A; c.epi = EPI_UPSAMPLE; c.q_extra = up.k - 1;
+      launch_conv1d(c, B, F * rate + c.q_extra, stream_);
+    }
+    rate *= up.up;
+    ch = co;
+    const int L = F * rate;
+    View P = view(gp_.as<float>(), ch, Lp_out), Q = view(gq_.as<float>(), ch, Lp_out);
+    S = view(gs_.as<float>(), ch, Lp_out);
+    if (debug_) save_tap("up" + std::to_string(st), A, ch, ylen_h_.data(), rate);
+    for (int j = 0; j < nk; ++j) {
+      const ResBlockW& rb = voice_.resblocks[st][j];
+      const int mrf = nk == 1 ? 2 : (j == 0 ? 0 : (j == nk - 1 ? 2 : 1));
+      const int n = int(rb.c1.size());
+      View y = A;
+      for (int c = 0; c < n; ++c) {
+        const bool last = c == n - 1;
+        if (s.resblock == 1) {
+          ConvArgs a1 = conv_args(rb.c1[c], y, ylen, rate);
+          a1.pre = PRE_LRELU; a1.slope = 0.1f; a1.y = P; a1.epi = EPI_BIAS;
+          launch_conv1d(a1, B, L, stream_);
+          ConvArgs a2 = conv_args(rb.c2[c], P, ylen, rate);
+          a2.pre = PRE_LRELU; a2.slope = 0.1f; a2.r = y;
+          if (last) { a2.epi = EPI_MRF; a2.y2 = S; a2.mrf = mrf; a2.mrf_n = nk; }
+          else { a2.epi = EPI_RES; a2.y = Q; }
+          launch_conv1d(a2, B, L, stream_);
+          y = Q;
+        } else {
+          ConvArgs a1 = conv_args(rb.c1[c], y, ylen, rate);
+          a1.pre = PRE_LRELU; a1.slope = 0.1f; a1.r = y;
+          View dst = (c & 1) ? Q : P;
+          if (last) { a1.epi = EPI_MRF; a1.y2 = S; a1.mrf = mrf; a1.mrf_n = nk; }
+          else { a1.epi = EPI_RES; a1.y = dst; }
+          launch_conv1d(a1, B, L, stream_);
+          y = dst;
+        }
+      }
+    }
+    if (debug_) save_tap("stage" + std::to_string(st), S, ch, ylen_h_.data(), rate);
+  }
+  launch_conv_post(S, W(voice_.post_w), voice_.post_c, voice_.post_k, 0.01f, audio_d_.as<float>(),
+                   off_d_.as<long long>(), ylen, rate, B, F * rate, stream_);
+}
+
+void Engine::run_back() {
+  const VoiceSpec& s = voice_.spec;
+  const int B = B_, H = s.hidden, I = s.inter, Fp = Fp_, F = Fmax_;
+  const int* ylen = ylen_d_.as<int>();
+  const int* len = len_d_.as<int>();
+  CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
+  View stats = view(stats_.as<float>(), 2 * I, Tp_);
+  View z = view(z_.as<float>(), I, Fp);
+  launch_expand(stats, I, cum_d_.as<int>(), Tp_, len, ylen, z, have_eps_z_ ? epsz_d_.as<float>() : nullptr,
+                (long long)I * z_stride_, int(z_stride_), seed_, scales_[0], B, F, stream_);
+  if (debug_) save_tap("z_p", z, I, ylen_h_.data(), 1);
+  // ---- flow, reverse (models.py:251-253; modules.py:447-466,184-209)
+  View fh = view(fh_.as<float>(), H, Fp), acts = view(facts_.as<float>(), H, Fp), out = view(fout_.as<float>(), H, Fp);
+  const int half = I / 2;
+  for (const CouplingW& cw : voice_.flow) {
+    View x0 = cw.flipped ? z.offset_channels(half) : z;
+    View x1 = cw.flipped ? z : z.offset_channels(half);
+    ConvArgs c = conv_args(cw.pre, x0, ylen, 1);
+    c.y = fh;
+    launch_conv1d(c, B, F, stream_);
+    const int nl = int(cw.in_layers.size());
+    for (int i = 0; i < nl; ++i) {
+      ConvArgs a = conv_args(cw.in_layers[i], fh, ylen, 1);
+      a.y = acts; a.epi = EPI_GATE;
+      launch_conv1d(a, B, F, stream_);
+      ConvArgs r = conv_args(cw.res_skip[i], acts, ylen, 1);
+      r.epi = EPI_WN; r.y = fh; r.r = fh; r.y2 = out; r.first = i == 0;
+      r.split = i < nl - 1 ? H : 0;
+      launch_conv1d(r, B, F, stream_);
+    }
+    ConvArgs p = conv_args(cw.post, out, ylen, 1);
+    p.epi = EPI_SUBFROM; p.y = x1; p.r = x1;
+    launch_conv1d(p, B, F, stream_);
+  }
+  if (debug_) save_tap("z", z, I, ylen_h_.data(), 1);
+  CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
+  run_generator();
+  CUDA_CHECK(cudaEventRecord(ev_[5], stream_));
+}
+
+void Engine::stage(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3], const NoiseSpec& noise,
+                   const int32_t* w_ceil_override) {
+  upload_inputs(ids_concat, lens, B, scales, noise, w_ceil_override);
+}
+
+int64_t Engine::run_staged(float* device_ms) {
+  if (B_ <= 0) throw std::runtime_error("run_staged: nothing staged");
+  CUDA_CHECK(cudaSetDevice(device_));
+  run_front();
+  plan_back();
+  run_back();
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  collect_stage_times();
+  if (device_ms) {
+    float tot = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&tot, ev_[0], ev_[5]));
+    *device_ms = tot;
+  }
+  return total_samples_;
+}
+
+void Engine::collect_stage_times() {
+  for (int i = 0; i < 5; ++i) CUDA_CHECK(cudaEventElapsedTime(&stage_ms_[i], ev_[i], ev_[i + 1]));
+}
+
+void Engine::stage_times(float out_ms[5]) const {
+  for (int i = 0; i < 5; ++i) out_ms[i] = stage_ms_[i];
+}
+
+const float* Engine::synthesize(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3],
+                                const NoiseSpec& noise, const int32_t* w_ceil_override, int64_t* n_samples,
+                                double* infer_seconds) {
+  const auto t0 = std::chrono::steady_clock::now();
+  upload_inputs(ids_concat, lens, B, scales, noise, w_ceil_override);
+  run_front();
+  plan_back();
+  run_back();
+  audio_pin_.ensure(size_t(std::max<int64_t>(total_samples_, 1)) * 4);
+  CUDA_CHECK(cudaMemcpyAsync(audio_pin_.p, audio_d_.p, size_t(total_samples_) * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  collect_stage_times();
+  if (debug_) {
+    HostTap t;
+    t.B = 1; t.C = 1; t.pitch = int(total_samples_); t.len = {int(total_samples_)};
+    t.data.assign(audio_pin_.as<float>(), audio_pin_.as<float>() + total_samples_);
+    taps_["audio"] = std::move(t);
+  }
+  for (int b = 0; b < B; ++b)
+    if (n_samples) n_samples[b] = int64_t(ylen_h_[b]) * voice_.spec.hop;
+  if (infer_seconds)
+    *infer_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return audio_pin_.as<float>();
+}
+
+const int16_t* Engine::synthesize_int16(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3],
+                                        const NoiseSpec& noise, int64_t* n_samples, double* infer_seconds) {
+  const auto t0 = std::chrono::steady_clock::now();
+  upload_inputs(ids_concat, lens, B, scales, noise, nullptr);
+  run_front();
+  plan_back();
+  run_back();
+  const int hop = voice_.spec.hop;
+  audio16_d_.ensure(size_t(std::max<int64_t>(total_samples_, 1)) * 2);
+  CUDA_CHECK(cudaMemsetAsync(peak_d_.p, 0, size_t(B) * 4, stream_));
+  launch_peak(audio_d_.as<float>(), off_d_.as<long long>(), ylen_d_.as<int>(), hop, peak_d_.as<unsigned int>(), B,
+              Fmax_ * hop, stream_);
+  launch_to_int16(audio_d_.as<float>(), off_d_.as<long long>(), ylen_d_.as<int>(), hop, peak_d_.as<unsigned int>(),
+                  audio16_d_.as<int16_t>(), B, Fmax_ * hop, stream_);
+  audio16_pin_.ensure(size_t(std::max<int64_t>(total_samples_, 1)) * 2);
+  CUDA_CHECK(cudaMemcpyAsync(audio16_pin_.p, audio16_d_.p, size_t(total_samples_) * 2, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  collect_stage_times();
+  for (int b = 0; b < B; ++b)
+    if (n_samples) n_samples[b] = int64_t(ylen_h_[b]) * hop;
+  if (infer_seconds)
+    *infer_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return audio16_pin_.as<int16_t>();
+}
+
+const float* Engine::vocode(const float* z, int B, int64_t frames, double* infer_seconds) {
+  const VoiceSpec& s = voice_.spec;
+  if (B <= 0 || frames <= 0 || !z) throw std::runtime_error("vocode: bad arguments");
+  if (frames > max_frames_) throw std::runtime_error("vocode: too many frames");
+  const auto t0 = std::chrono::steady_clock::now();
+  CUDA_CHECK(cudaSetDevice(device_));
+  B_ = B; Tmax_ = 1; Tp_ = 4;
+  ensure_front(B, 1);
+  ylen_h_.assign(B, int(frames));
+  len_h_.assign(B, 1);
+  misc_pin_.ensure(size_t(B) * 32);
+  int* yl = misc_pin_.as<int>();
+  for (int b = 0; b < B; ++b) yl[b] = int(frames);
+  CUDA_CHECK(cudaMemcpyAsync(ylen_d_.p, yl, size_t(B) * 4, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  have_eps_z_ = false;
+  plan_back();
+  if (debug_) taps_.clear();
+  // z host [B][inter][frames] -> device [B][inter][Fp]
+  CUDA_CHECK(cudaMemcpy2DAsync(z_.p, size_t(Fp_) * 4, z, size_t(frames) * 4, size_t(frames) * 4, size_t(B) * s.inter,
+                               cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
+  run_generator();
+  CUDA_CHECK(cudaEventRecord(ev_[5], stream_));
+  audio_pin_.ensure(size_t(total_samples_) * 4);
+  CUDA_CHECK(cudaMemcpyAsync(audio_pin_.p, audio_d_.p, size_t(total_samples_) * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  CUDA_CHECK(cudaEventElapsedTime(&stage_ms_[4], ev_[4], ev_[5]));
+  if (infer_seconds)
+    *infer_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return audio_pin_.as<float>();
+}
+
+}  // namespace pb200

@@ -1,0 +1,133 @@
+// Host-side engine: owns one voice's packed weights in HBM, a grow-only activation workspace, one
+// CUDA stream, and runs the VITS inference graph (SynthesizerTrn.infer, models.py:681-722) as a
+// sequence of hand-written sm_100a kernels.  This is what stands behind `Ort::Session::Run` at
+// /root/reference/src/cpp/piper.cpp:386-388.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "voice.h"
+
+namespace pb200 {
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes);
+  void release();
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes);
+  void release();
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct NoiseSpec {
+  const float* eps_dp = nullptr;  // host, item-major [sum_b 2*len_b]; null => Philox(seed)
+  const float* eps_z = nullptr;   // host, [B][inter][z_stride]; null => Philox(seed)
+  int64_t z_stride = 0;
+  uint64_t seed = 0;
+};
+
+struct HostTap {
+  int B = 0, C = 0;
+  std::vector<int> len;           // valid length per item
+  int pitch = 0;
+  std::vector<float> data;        // [B][C][pitch]
+};
+
+class Engine {
+ public:
+  Engine(const std::string& onnx_path, int device);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  const VoiceSpec& spec() const { return voice_.spec; }
+  const PackedVoice& voice() const { return voice_; }
+  int device() const { return device_; }
+  int64_t weight_bytes() const { return int64_t(voice_.blob.size()) * 4; }
+
+  // ---- whole pipeline, host buffers in / host buffer out (the reference-facing call)
+  // ids_concat: int64 [sum lens]; returns pointer to pinned fp32 audio (valid until the next call),
+  // n_samples[b] = y_len[b] * hop, items concatenated in order.
+  const float* synthesize(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3],
+                          const NoiseSpec& noise, const int32_t* w_ceil_override, int64_t* n_samples,
+                          double* infer_seconds);
+  // Same, with the int16 peak-normalisation epilogue of piper.cpp:411-431 fused on the GPU.
+  const int16_t* synthesize_int16(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3],
+                                  const NoiseSpec& noise, int64_t* n_samples, double* infer_seconds);
+  // Generator only: z host [B][inter][frames] -> audio [B][frames*hop]
+  const float* vocode(const float* z, int B, int64_t frames, double* infer_seconds);
+
+  // ---- staged execution for device-resident timing (bench.py `value`)
+  void stage(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3], const NoiseSpec& noise,
+             const int32_t* w_ceil_override);
+  // runs the kernels on the already-staged inputs; audio stays in HBM. Returns total valid samples and the
+  // device time (CUDA events on the engine's stream) in ms.
+  int64_t run_staged(float* device_ms);
+  // per-stage device times of the last run_staged/synthesize: enc, dp, sync, flow(expand+flow), dec
+  void stage_times(float out_ms[5]) const;
+
+  void set_debug(bool on) { debug_ = on; }
+  const HostTap* tap(const std::string& name) const;
+  void set_max_frames(int64_t f) { max_frames_ = f; }
+
+ private:
+  void upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3],
+                     const NoiseSpec& noise, const int32_t* w_ceil_override);
+  void run_front();              // encoder + duration predictor, ends with the y_len D2H + sync
+  void plan_back();              // host: sizes, offsets, workspace growth
+  void run_back();               // expand + flow + generator -> audio_d_
+  void run_generator();
+  void ensure_front(int B, int Tmax);
+  void ensure_back(int B, int Fmax);
+  void collect_stage_times();
+  void save_tap(const std::string& name, View v, int C, const int* len_host, int scale);
+
+  View view(float* p, int C, int pitch) const { return View{p, (long long)C * pitch, pitch}; }
+  const float* W(int64_t off) const { return off >= 0 ? weights_.as<float>() + off : nullptr; }
+  ConvArgs conv_args(const ConvW& c, View x, const int* len, int len_scale) const;
+  void dds(const DDSW& d, View h, View u, View v, int C);
+
+  PackedVoice voice_;
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[8] = {};
+  DeviceBuf weights_;
+
+  // request state
+  int B_ = 0, Tmax_ = 0, Tp_ = 0, Fmax_ = 0, Fp_ = 0;
+  float scales_[3] = {0.667f, 1.f, 0.8f};
+  uint64_t seed_ = 0;
+  bool have_eps_dp_ = false, have_eps_z_ = false, have_override_ = false;
+  int64_t z_stride_ = 0;
+  std::vector<int> len_h_, ylen_h_;
+  std::vector<long long> off_h_;
+  int64_t total_samples_ = 0;
+  int64_t max_frames_ = 1 << 17;
+
+  // phoneme-rate workspace
+  DeviceBuf ids_d_, len_d_, ylen_d_, cum_d_, logw_d_, override_d_, epsdp_d_, epsoff_d_, off_d_;
+  DeviceBuf x_, t1_, qkv_, att_, ffn_, stats_, g_, h_, u_, v_, pr_, z2_;
+  // frame-rate workspace
+  DeviceBuf z_, fh_, facts_, fout_, epsz_d_;
+  // sample-rate workspace
+  DeviceBuf ga_, gp_, gq_, gs_, audio_d_, audio16_d_, peak_d_;
+  PinnedBuf ids_pin_, misc_pin_, audio_pin_, audio16_pin_, eps_pin_;
+
+  bool debug_ = false;
+  std::map<std::string, HostTap> taps_;
+  float stage_ms_[5] = {0, 0, 0, 0, 0};
+};
+
+}  // namespace pb200

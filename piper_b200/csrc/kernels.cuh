@@ -1,0 +1,111 @@
+// Kernel launch interface of the sm_100a VITS engine (device code in *.cu next to this file).
+//
+// Layout convention everywhere: activations are fp32 [B][C][Lp], time contiguous (the reference's
+// [B,C,T] channel-major layout, models.py / modules.py), Lp = padded row pitch (multiple of 4 floats
+// so rows are 16-byte aligned).  Batches are RAGGED: item b is valid on [0, len[b]*len_scale); every
+// kernel zero-fills reads outside that range and never stores outside it, which gives each utterance
+// its own zero padding (parity is per utterance against the B = 1 reference).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace pb200 {
+
+struct View {        // a [B][C][L] activation view
+  float* p = nullptr;
+  long long bs = 0;  // batch stride (floats)
+  int cs = 0;        // channel stride (floats)
+  __host__ __device__ View offset_channels(int c) const { return View{p + (long long)c * cs, bs, cs}; }
+};
+
+enum PreAct { PRE_NONE = 0, PRE_LRELU = 1 };
+
+enum Epilogue {
+  EPI_BIAS = 0,      // y = v
+  EPI_RELU = 1,      // y = max(v, 0)
+  EPI_RES = 2,       // y = v + r
+  EPI_GATE = 3,      // rows interleaved (a_i, b_i): y[row/2] = tanh(a) * sigmoid(b)      (commons.py:99-106)
+  EPI_WN = 4,        // row < split: y = r + v (residual stream, in place); row >= split: y2 (+)= v (skip sum)
+  EPI_SUBFROM = 5,   // y = r - v                                                          (modules.py:464)
+  EPI_UPSAMPLE = 6,  // ConvTranspose pixel-shuffle store: y[row/up][q*up + row%up - up_pad] = v
+  EPI_MRF = 7,       // v' = v + r; mrf 0: y2 = v'; 1: y2 += v'; 2: y2 = (y2 + v') / mrf_n   (models.py:356-363)
+};
+
+struct ConvArgs {
+  View x, y, y2, r;
+  const float* w = nullptr;     // [ci][k][rows_p]
+  const float* bias = nullptr;  // [rows] or null
+  const int* len = nullptr;     // per item
+  int len_scale = 1;            // valid input length = len[b] * len_scale
+  int ci = 0, rows = 0, rows_p = 0, k = 1, dil = 1, pad = 0;
+  int q_extra = 0;              // output positions computed past the input length (ConvTranspose tail)
+  int pre = PRE_NONE;
+  float slope = 0.f;
+  int epi = EPI_BIAS;
+  int split = 0, first = 0;     // EPI_WN
+  int up = 1, up_pad = 0;       // EPI_UPSAMPLE
+  int mrf = 0, mrf_n = 1;       // EPI_MRF
+  int cic = 16;                 // input-channel chunk staged in shared memory (set by the launcher)
+};
+
+// max_len = max over the batch of (len[b]*len_scale + q_extra): sizes the grid.
+void launch_conv1d(ConvArgs a, int B, int max_len, cudaStream_t st);
+
+// ---- text encoder -----------------------------------------------------------------------------
+void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float scale, View x, const int* len, int B,
+                  int Tmax, cudaStream_t st);
+// qkv: [B][3H][Lp] (q | k | v rows), out: [B][H][Lp]
+void launch_rel_attention(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
+                          const int* len, int B, int Tmax, cudaStream_t st);
+
+enum LnMode {
+  LN_ADD = 0,          // y = LN(a + b)
+  LN_GELU_RES = 1,     // y = r + gelu(LN(a))
+  LN_DW_GELU = 2,      // y = gelu(LN(dwconv_k(a)))      (modules.py:117-129, first half of a DDSConv layer)
+  LN_PLAIN = 3,        // y = LN(a)
+};
+struct LnArgs {
+  View a, b, r, y;
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  const float* dw_w = nullptr;  // [C][k]
+  const float* dw_b = nullptr;  // [C]
+  int dw_k = 3, dw_dil = 1;
+  int C = 0, mode = LN_ADD;
+  const int* len = nullptr;
+};
+void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st);
+
+// ---- stochastic duration predictor ------------------------------------------------------------
+// z[b][ch][t] = eps * noise_w  (eps explicit [sum_b 2*len_b] item-major, or Philox(seed) when eps == null)
+void launch_dp_noise(View z, const float* eps, const long long* eps_off, unsigned long long seed, float noise_w,
+                     const int* len, int B, int Tmax, cudaStream_t st);
+// h[c][t] = w[c] * z[x0_ch][t] + b[c] + g[c][t]
+void launch_cf_pre(View z, int x0_ch, const float* w, const float* b, View g, View h, int C, const int* len, int B,
+                   int Tmax, cudaStream_t st);
+// inverse rational-quadratic spline on z[x1_ch] with parameters h [B][3*bins-1][Lp]   (transforms.py:50-191)
+void launch_spline_inverse(View z, int x1_ch, View h, int bins, float inv_sqrt_c, float bound, const int* len, int B,
+                           int Tmax, cudaStream_t st);
+// logw = (z0 - m)*s ; w = exp(logw)*length_scale ; w_ceil = ceil(w) ; cum = inclusive scan ; y_len = max(sum, 1)
+void launch_durations(View z, float ea_m, float ea_scale, float length_scale, const int* w_override,
+                      int w_override_pitch, int* cum, int cum_pitch, int* y_len, float* logw_out, const int* len,
+                      int B, int Tmax, cudaStream_t st);
+// z_p[c][j] = m_p[c][i(j)] + eps * exp(logs_p[c][i(j)]) * noise_scale   for j < y_len  (models.py:705-718)
+void launch_expand(View stats, int inter, const int* cum, int cum_pitch, const int* len, const int* y_len, View zp,
+                   const float* eps, long long eps_bs, int eps_cs, unsigned long long seed, float noise_scale, int B,
+                   int Fmax, cudaStream_t st);
+
+// ---- generator tail / audio epilogue ------------------------------------------------------------
+// out[off[b] + t] = tanh( sum_c sum_j w[c][j] * lrelu_0.01(x[c][t + j - k/2]) )      (models.py:364-366)
+void launch_conv_post(View x, const float* w, int C, int k, float slope, float* out, const long long* out_off,
+                      const int* len, int len_scale, int B, int max_len, cudaStream_t st);
+// peak[b] = max |x| over the item (as float bits, non-negative floats order like ints)
+void launch_peak(const float* audio, const long long* off, const int* len, int len_scale, unsigned int* peak, int B,
+                 int max_len, cudaStream_t st);
+// int16 = clamp(x * 32767 / max(0.01, peak), -32768, 32767) truncated      (piper.cpp:411-431)
+void launch_to_int16(const float* audio, const long long* off, const int* len, int len_scale, const unsigned int* peak,
+                     int16_t* out, int B, int max_len, cudaStream_t st);
+
+unsigned long long launch_count();  // kernels launched by this library since load (bench.py's gpu_launches)
+
+}  // namespace pb200

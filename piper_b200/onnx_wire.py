@@ -49,6 +49,8 @@ def _fields(buf: memoryview) -> Iterator[Tuple[int, int, object]]:
             pos += 8
         elif wt == 2:
             n, pos = _varint(buf, pos)
+            if pos + n > end:
+                raise ValueError("truncated length-delimited protobuf field")
             yield fno, wt, buf[pos:pos + n]
             pos += n
         elif wt == 5:

@@ -1,0 +1,97 @@
+"""CPU tests that pin the oracle: against the reference's own PyTorch source (build container) and
+against the golden fixtures minted from it (everywhere)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, real_fixture_lines, real_voice_path
+from piper_b200 import voicegen
+
+
+def _oracle_for(tag):
+    from oracle.voice_loader import load_voice
+    from oracle.vits_oracle import Oracle
+    if tag.startswith("real:"):
+        path = real_voice_path()
+        if path is None:
+            pytest.skip("reference test voice not staged")
+    else:
+        _, arch, seed = tag.split(":")
+        path = voicegen.cached_voice(arch, int(seed))
+    spec, w, attrs = load_voice(path)
+    return Oracle(spec, w, attrs), w
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))))
+def test_oracle_matches_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    orc, w = _oracle_for(str(g["voice"]))
+    from oracle.make_golden import weights_digest
+    assert weights_digest(w) == str(g["weights_sha256"]), "voice weights differ from the ones the golden was minted on"
+    dump = {}
+    o = orc.infer(g["ids"], g["scales"], g["eps_dp"] if "eps_dp" in g else None,
+                  g["eps_z"] if "eps_z" in g else None, dump=dump)
+    assert np.array_equal(dump["w_ceil"].numpy().astype(np.int32), g["w_ceil"])   # durations: exact
+    assert o.shape == g["audio"].shape
+    assert np.abs(dump["z"].numpy() - g["z"]).max() <= 1e-3
+    assert np.abs(o - g["audio"]).max() <= 1e-3       # north_star tolerance, fp32 waveform
+
+
+def test_oracle_matches_survey_anchors():
+    """Frame counts / waveform statistics of all 7 en-us fixtures on the real voice."""
+    lines = real_fixture_lines()
+    if lines is None:
+        pytest.skip("reference fixtures not staged")
+    orc, _ = _oracle_for("real:test_voice")
+    anchors = json.load(open(os.path.join(GOLDEN, "real_enus_anchors.json")))
+    for a in anchors[1:4]:
+        dump = {}
+        o = orc.infer(lines[a["index"]]["phoneme_ids"], (0.0, 1.0, 0.0), dump=dump)
+        assert len(o) == a["frames"] * 256
+        assert dump["w_ceil"].numpy().astype(int).tolist() == a["w_ceil"]
+        assert abs(float(np.abs(o).max()) - a["max_abs"]) < 1e-3
+        assert abs(float(np.abs(o).mean()) - a["mean_abs"]) < 1e-4
+        assert np.abs(o[:3] - np.asarray(a["first3"], np.float32)).max() < 1e-3
+
+
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("tag,n_ph,scales", [("real:test_voice", 0, (0.667, 1.0, 0.8)),
+                                             ("synthetic:tiny:1234", 40, (0.667, 1.3, 0.8)),
+                                             ("synthetic:tiny-high:1234", 12, (0.3, 0.8, 1.0))])
+def test_oracle_matches_reference_source(tag, n_ph, scales):
+    from oracle import ref_bridge
+    if not ref_bridge.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    orc, w = _oracle_for(tag)
+    net = ref_bridge.build_reference_model(orc.s, w)
+    if tag.startswith("real:"):
+        ids = real_fixture_lines()[3]["phoneme_ids"]
+    else:
+        ids = voicegen.benchmark_ids(n_ph, seed=17)
+    rng = np.random.default_rng(11)
+    eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
+    eps_z = rng.standard_normal((orc.s.inter, 6 * len(ids))).astype(np.float32)
+    dump = {}
+    o = orc.infer(ids, scales, eps_dp, eps_z, dump=dump)
+    r = ref_bridge.reference_infer(net, ids, scales, eps_dp, eps_z)
+    assert np.array_equal(dump["w_ceil"].numpy(), r["w_ceil"])
+    assert np.abs(dump["z_p"].numpy() - r["z_p"]).max() < 1e-4
+    assert np.abs(dump["z"].numpy() - r["z"]).max() < 1e-3
+    assert np.abs(o - r["o"]).max() < 1e-3
+
+
+def test_oracle_edge_cases():
+    """Shortest legal input (BOS, PAD, EOS), single id, and a duration override."""
+    orc, _ = _oracle_for("synthetic:tiny:1234")
+    o = orc.infer([1, 0, 2], (0.667, 1.0, 0.8))
+    assert len(o) % 256 == 0 and len(o) >= 256 and np.isfinite(o).all()
+    o1 = orc.infer([5], (0.0, 1.0, 0.0))
+    assert len(o1) >= 256
+    o2 = orc.infer([1, 0, 7, 0, 2], (0.0, 1.0, 0.0), w_ceil_override=[1, 2, 3, 0, 1])
+    assert len(o2) == 7 * 256
+    # all-zero durations: clamp_min(sum, 1) gives exactly one frame (models.py:704)
+    o3 = orc.infer([1, 0, 2], (0.0, 1.0, 0.0), w_ceil_override=[0, 0, 0])
+    assert len(o3) == 256
