@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: phoneme ids -> fp32 waveform (VITS inference behind piper::synthesize).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over one batch of synthetic input.  Workload (BASELINE.json
+configs[2], the configuration the samples/sec metric is quoted on): the medium-quality VITS architecture
+(en_US-lessac-medium layout, seeded synthetic weights - the real file is not available offline),
+32 utterances x 128 phonemes (259 ids each) per GPU, noise drawn on the device, default scales.
+Weak scaling: every rank synthesises its own 32 utterances; no data-path collective.
+
+The JSON line (rank 0) follows the driver contract; see DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "audio_samples_per_sec_22050Hz"
+ARCH = "medium"
+N_PHONEMES = 128
+BATCH = 32
+SCALES = (0.667, 1.0, 0.8)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def workload_ids(rank: int):
+    from piper_b200 import voicegen
+    return [voicegen.benchmark_ids(N_PHONEMES, seed=1234 + rank * BATCH + b) for b in range(BATCH)]
+
+
+def pick_threads(orc, ids) -> int:
+    """The torch CPU port does not scale to every core of a 128-thread host (tiny convs oversubscribe):
+    give the CPU arm its best thread count, found on a short utterance."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    best, best_t = 1, float("inf")
+    cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+    short = ids[:65]
+    for c in cands:
+        torch.set_num_threads(c)
+        orc.infer(short, SCALES)
+        t = time.perf_counter()
+        orc.infer(short, SCALES)
+        dt = time.perf_counter() - t
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def time_oracle(orc, ids_list, budget_s: float, min_runs: int = 3):
+    """Per-utterance infer() timing like src/benchmark/benchmark_onnx.py:98-112 (warm-up 1, then timed runs)."""
+    rng = np.random.default_rng(1235)
+    def one(ids):
+        eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
+        eps_z = rng.standard_normal((orc.s.inter, 6 * len(ids))).astype(np.float32)
+        t = time.perf_counter()
+        o = orc.infer(ids, SCALES, eps_dp, eps_z)
+        return time.perf_counter() - t, len(o)
+    one(ids_list[0])
+    samples, secs, n = 0, 0.0, 0
+    t_start = time.perf_counter()
+    while n < min_runs or (time.perf_counter() - t_start < budget_s and n < len(ids_list)):
+        dt, ns = one(ids_list[n % len(ids_list)])
+        secs += dt; samples += ns; n += 1
+    return samples / secs, n, secs
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path.  onnxruntime is not in this
+    image and the reference's PyTorch source cannot travel to the GPU box, so this is the oracle port
+    (oracle/vits_oracle.py, validated against that source) on all host threads."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import torch
+    from oracle.voice_loader import load_voice
+    from oracle.vits_oracle import Oracle
+    from piper_b200 import voicegen
+    spec, w, attrs = load_voice(voicegen.cached_voice(ARCH))
+    orc = Oracle(spec, w, attrs)
+    ids_list = workload_ids(0)
+    pick_threads(orc, ids_list[0])
+    per_step = 2                                   # bounded sample: 2 of the 32 utterances per step
+    rng = np.random.default_rng(1235)
+    def step(k):
+        n = 0
+        for b in range(per_step):
+            ids = ids_list[(k * per_step + b) % BATCH]
+            eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
+            eps_z = rng.standard_normal((spec.inter, 6 * len(ids))).astype(np.float32)
+            n += len(orc.infer(ids, SCALES, eps_dp, eps_z))
+        return n
+    for k in range(args.warmup):
+        step(k)
+    t0 = time.perf_counter()
+    total = sum(step(k) for k in range(args.steps))
+    dt = time.perf_counter() - t0
+    v = total / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{ARCH} VITS (en_US-lessac-medium architecture, seeded synthetic weights), "
+                               f"{BATCH} x {N_PHONEMES}-phoneme utterances (259 ids) per GPU, scales {SCALES}",
+                   "sample": f"{per_step} of the {BATCH} utterances per step, B=1 calls (the only mode a reference caller uses)"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "host_cpus": os.cpu_count(), "sample": f"{per_step} utterances (259 ids) per step x {args.steps} steps, torch CPU fp32 oracle port"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_engine(args):
+    import torch
+    rank, world, local = dist_env()
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the engine arm)")
+    torch.cuda.set_device(local)
+    from piper_b200 import engine, voicegen
+
+    if rank == 0:
+        path = voicegen.cached_voice(ARCH)       # rank 0 writes the synthetic voice; others read it after the barrier
+    if use_dist:
+        dist.barrier()
+    path = voicegen.cached_voice(ARCH)
+    voice = engine.Voice(path, local)
+    ids_list = workload_ids(rank)
+    hop = voice.hop
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if not use_dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- device-resident leg (`value`): inputs staged in HBM once, kernels only
+    voice.stage(ids_list, SCALES, seed=4242)
+    for _ in range(max(args.warmup, 3)):
+        voice.run_staged()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = engine.launch_count()
+    dev_ms, samples = 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n, ms = voice.run_staged()
+        dev_ms += ms; samples += n
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = (engine.launch_count() - launches0) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = voice.stage_times()
+    dev_ms_max = max_over_ranks(dev_ms)
+    total_samples = sum_over_ranks(float(samples))
+    value = total_samples / (dev_ms_max * 1e-3)
+
+    # ---------------- end-to-end leg: the public call with HOST buffers, H2D + D2H inside the timed region
+    for _ in range(3):
+        voice.synthesize_batch(ids_list, SCALES, seed=4242, copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_samples = 0
+    for _ in range(args.steps):
+        flat, counts, _ = voice.synthesize_batch(ids_list, SCALES, seed=4242, copy=False)
+        e2e_samples += int(counts.sum())
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_total = sum_over_ranks(float(e2e_samples))
+    e2e_value = e2e_total / e2e_s
+    tp = (259 + 3) // 4 * 4
+    h2d = BATCH * tp * 4 + BATCH * 4 + BATCH * 8            # ids (int32, padded pitch) + lengths + output offsets
+    d2h = e2e_samples // args.steps * 4 + BATCH * 4         # fp32 audio + the per-item output lengths
+
+    # ---------------- roofline of the dominant kernel family (conv1d), CUDA events around every launch
+    voice.set_profile(True)
+    prof_steps = 2
+    agg = {}
+    for _ in range(prof_steps):
+        voice.run_staged()
+        for k, v in voice.profile().items():
+            a = agg.setdefault(k, dict(launches=0, ms=0.0, bytes=0.0, flops=0.0))
+            for f in a:
+                a[f] += v[f]
+    voice.set_profile(False)
+    peaks = measured_peaks()
+    dom = max(agg, key=lambda k: agg[k]["ms"])
+    d = agg[dom]
+    gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+    tflops = d["flops"] / (d["ms"] * 1e-3) / 1e12
+    roofline = {"kernel": f"conv1d_kernel ({dom})", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["source"], "avg_launch_us": d["ms"] / d["launches"] * 1e3,
+                "launches_per_step": d["launches"] / prof_steps,
+                "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
+                "fp32_tflops": tflops,
+                "share_of_conv_time": d["ms"] / sum(v["ms"] for v in agg.values()),
+                "stages": {k: {"ms_per_step": v["ms"] / prof_steps, "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+                               "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} for k, v in agg.items()}}
+
+    # ---------------- batch = 1 latency / real-time factor (BASELINE.json configs[1])
+    one = [ids_list[0]]
+    for _ in range(3):
+        voice.synthesize_batch(one, SCALES, seed=1, copy=False)
+    lat, n1 = [], 0
+    for _ in range(10):
+        t = time.perf_counter()
+        flat, counts, _ = voice.synthesize_batch(one, SCALES, seed=1, copy=False)
+        lat.append(time.perf_counter() - t); n1 = int(counts.sum())
+    lat_s = statistics.median(lat)
+    rtf = lat_s / (n1 / 22050.0)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.voice_loader import load_voice
+        from oracle.vits_oracle import Oracle
+        spec, w, attrs = load_voice(path)
+        orc = Oracle(spec, w, attrs)
+        pick_threads(orc, ids_list[0])
+        v, n, secs = time_oracle(orc, ids_list, budget_s=15.0)
+        cpu_baseline = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "host_cpus": os.cpu_count(),
+                        "sample": f"{n} utterances of the batch (259 ids each), B=1 calls, {secs:.1f} s of CPU work, best of 4..ncpu threads; "
+                                  "torch CPU fp32 oracle port of the reference graph (onnxruntime absent)"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{ARCH} VITS (en_US-lessac-medium architecture, seeded synthetic weights), "
+                                   f"{BATCH} x {N_PHONEMES}-phoneme utterances (259 ids) per GPU, scales {SCALES}, device Philox noise",
+                       "batch_per_gpu": BATCH, "ids_per_utterance": 259, "samples_per_step": total_samples / args.steps,
+                       "l2": "working set (4 x ~0.5 GB generator buffers per step) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world} (utterances sharded, no data-path collective)"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "stage_ms": dict(zip(["text_encoder", "duration_predictor", "host_length_roundtrip", "expand_flow", "generator"], stage_ms)),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "batch1": {"latency_ms": lat_s * 1e3, "rtf": rtf, "samples": n1, "samples_per_s": n1 / lat_s},
+        }), flush=True)
+    voice.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,11 @@ int pb200_run_staged(pb200_voice* v, int64_t* total_samples, float* device_ms);
 /* enc, duration predictor, host length round-trip, expand+flow, generator — CUDA-event ms of the last run */
 int pb200_stage_times(const pb200_voice* v, float ms[5]);
 
+/* Per-launch CUDA-event timing of the convolution kernels of the last run, aggregated by pipeline stage,
+ * as JSON {"stage": {"launches", "ms", "bytes", "flops"}} with the algorithmic bytes/flops of SURVEY §8d. */
+int pb200_set_profile(pb200_voice* v, int32_t on);
+int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap);
+
 void pb200_release(pb200_voice* v, const void* audio);
 
 /* Test taps: when debug is on, intermediate tensors of the last call are kept on the host.

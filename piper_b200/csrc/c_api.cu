@@ -153,6 +153,23 @@ int pb200_stage_times(const pb200_voice* v, float ms[5]) {
   });
 }
 
+int pb200_set_profile(pb200_voice* v, int32_t on) {
+  return guarded([&] {
+    if (!v) throw std::runtime_error("pb200_set_profile: null argument");
+    v->engine.set_profile(on != 0);
+  });
+}
+
+int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap) {
+  return guarded([&] {
+    if (!v || !buf || cap <= 0) throw std::runtime_error("pb200_profile_read: bad argument");
+    const std::string s = v->engine.profile_json();
+    const size_t n = std::min<size_t>(s.size(), size_t(cap - 1));
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  });
+}
+
 void pb200_release(pb200_voice*, const void*) {
   // Output buffers are engine-owned pinned staging areas reused by the next call; nothing to free.
 }

@@ -32,6 +32,17 @@ namespace {
 
 __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.f / (1.f + expf(-v)); }
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Two-stage cp.async pipeline: while chunk k is in the FMA loop, chunk k+1 (input tile with its dilated
+// halo + weight slab) streams global -> shared with 16-byte LDGSTS; out-of-range bytes are zero-filled by
+// the copy itself (src-size < 16), which is what gives every utterance its own zero padding.
 template <int CPT, int WR, int TPT>
 __global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs a) {
   constexpr int WT = 8 / WR;
@@ -48,10 +59,16 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = warp % WR, wt = warp / WR;
 
-  const int span = TT + (a.k - 1) * a.dil;
+  // the tile starts at the 16-byte boundary below t0 - pad so every row copy is a run of aligned float4
+  const int tbase = t0 - a.pad;
+  const int t_al = tbase & ~3;                 // floor to a multiple of 4 (two's complement: also for negatives)
+  const int off = tbase - t_al;                // 0..3
+  const int span4 = (TT + (a.k - 1) * a.dil + off + 3) >> 2;   // float4 per row
+  const int span = span4 << 2;
   const int cic = a.cic;
-  float* xs = smem;                                  // [cic][span]
-  float* ws = smem + ((cic * span + 3) & ~3);        // [cic][k][ROWS]
+  const int xs_floats = cic * span;
+  const int ws_floats = cic * a.k * ROWS;
+  const int stage_floats = xs_floats + ws_floats;               // both multiples of 4
 
   float acc[CPT][TPT];
 #pragma unroll
@@ -60,42 +77,65 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs a) {
     for (int i = 0; i < TPT; ++i) acc[r][i] = 0.f;
 
   const float* xb = a.x.p + (long long)b * a.x.bs;
-  const int tbase = t0 - a.pad;
+  const int n_chunks = (a.ci + cic - 1) / cic;
+  const int x4_total = cic * span4;
+  const int w4_total = cic * a.k * (ROWS / 4);
 
-  for (int ci0 = 0; ci0 < a.ci; ci0 += cic) {
-    // ---- stage the input tile (zero outside [0, L), pre-activation applied once)
-    for (int c = 0; c < cic; ++c) {
+  auto prefetch = [&](int chunk, float* stage) {
+    const int ci0 = chunk * cic;
+    float* xs = stage;
+    float* ws = stage + xs_floats;
+    for (int idx = tid; idx < x4_total; idx += 256) {
+      const int c = idx / span4, u4 = idx - c * span4;
       const int ci = ci0 + c;
-      const float* xr = xb + (long long)ci * a.x.cs;
-      float* dst = xs + c * span;
-      for (int u = tid; u < span; u += 256) {
-        const int t = tbase + u;
-        float v = 0.f;
-        if (ci < a.ci && t >= 0 && t < L) v = __ldg(xr + t);
-        if (a.pre == PRE_LRELU) v = v > 0.f ? v : v * a.slope;
-        dst[u] = v;
-      }
+      const int t = t_al + (u4 << 2);
+      int valid = 0;                                   // bytes of this float4 inside [0, L)
+      if (ci < a.ci && t >= 0 && t < L) valid = min(4, L - t) * 4;
+      const float* src = valid ? xb + (long long)ci * a.x.cs + t : xb;
+      cp_async16(xs + c * span + (u4 << 2), src, valid);
     }
-    // ---- stage the weight slab [cic][k][ROWS] (rows contiguous in global: 16B vector loads)
-    {
-      const int n4 = cic * a.k * (ROWS / 4);
-      for (int idx = tid; idx < n4; idx += 256) {
-        const int r4 = idx % (ROWS / 4);
-        const int cj = idx / (ROWS / 4);
-        const int c = cj / a.k, j = cj - c * a.k;
-        const int ci = ci0 + c;
-        const int row = row0 + r4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ci < a.ci && row < a.rows_p)
-          v = __ldg(reinterpret_cast<const float4*>(a.w + ((long long)ci * a.k + j) * a.rows_p + row));
-        reinterpret_cast<float4*>(ws)[idx] = v;
+    for (int idx = tid; idx < w4_total; idx += 256) {
+      const int r4 = idx % (ROWS / 4);
+      const int cj = idx / (ROWS / 4);
+      const int c = cj / a.k, j = cj - c * a.k;
+      const int ci = ci0 + c;
+      const int row = row0 + r4 * 4;
+      const bool ok = ci < a.ci && row < a.rows_p;
+      const float* src = ok ? a.w + ((long long)ci * a.k + j) * a.rows_p + row : a.w;
+      cp_async16(ws + (idx << 2), src, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  prefetch(0, smem);
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    float* stage = smem + (chunk & 1) * stage_floats;
+    if (chunk + 1 < n_chunks) {
+      prefetch(chunk + 1, smem + ((chunk + 1) & 1) * stage_floats);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    float* xs = stage;
+    const float* ws = stage + xs_floats;
+    if (a.pre == PRE_LRELU) {
+      // each thread activates exactly the float4s it copied itself (visible to it after wait_group)
+      for (int idx = tid; idx < x4_total; idx += 256) {
+        const int c = idx / span4, u4 = idx - c * span4;
+        float4* p = reinterpret_cast<float4*>(xs + c * span + (u4 << 2));
+        float4 v = *p;
+        v.x = v.x > 0.f ? v.x : v.x * a.slope;
+        v.y = v.y > 0.f ? v.y : v.y * a.slope;
+        v.z = v.z > 0.f ? v.z : v.z * a.slope;
+        v.w = v.w > 0.f ? v.w : v.w * a.slope;
+        *p = v;
       }
     }
     __syncthreads();
 
     // ---- FMA
     for (int c = 0; c < cic; ++c) {
-      const float* xrow = xs + c * span + wt * (32 * TPT) + lane;
+      const float* xrow = xs + c * span + off + wt * (32 * TPT) + lane;
       const float* wrow = ws + c * a.k * ROWS + wr * CPT;
       for (int j = 0; j < a.k; ++j) {
         float wv[CPT];
@@ -113,7 +153,7 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs a) {
           for (int i = 0; i < TPT; ++i) acc[r][i] = fmaf(wv[r], xv[i], acc[r][i]);
       }
     }
-    __syncthreads();
+    __syncthreads();   // everyone is done with this stage before the next prefetch overwrites it
   }
 
   // ---- epilogue
@@ -182,21 +222,23 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs a) {
 template <int CPT, int WR, int TPT>
 void launch_cfg(ConvArgs& a, int B, int max_len, cudaStream_t st) {
   constexpr int WT = 8 / WR, ROWS = CPT * WR, TT = WT * 32 * TPT;
-  const int span = TT + (a.k - 1) * a.dil;
-  int cic = 16;
-  while (cic > a.ci) cic >>= 1;
-  auto bytes = [&](int c) { return size_t(((c * span + 3) & ~3) + c * a.k * ROWS) * sizeof(float); };
-  while (cic > 2 && bytes(cic) > 64 * 1024) cic >>= 1;
+  const int span = ((TT + (a.k - 1) * a.dil + 3 + 3) >> 2) << 2;   // worst-case alignment offset of 3
+  // input-channel chunk: as deep as two pipeline stages allow (fewer barriers per FLOP), at most 64
+  auto bytes = [&](int c) { return size_t(2) * size_t(c * span + c * a.k * ROWS) * sizeof(float); };
+  int cic = a.ci < 64 ? a.ci : 64;
+  while (cic > 2 && bytes(cic) > 100 * 1024) --cic;
+  const int n_chunks = (a.ci + cic - 1) / cic;
+  cic = (a.ci + n_chunks - 1) / n_chunks;              // even split: no mostly-empty last chunk
   a.cic = cic;
   const size_t smem = bytes(cic);
+  if (smem > 200 * 1024) throw std::runtime_error("conv1d: tile does not fit shared memory (k*dil too large)");
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(conv1d_kernel<CPT, WR, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(conv1d_kernel<CPT, WR, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set[dev & 63] = true;
   }
-  if (smem > 96 * 1024) throw std::runtime_error("conv1d: tile does not fit shared memory (k*dil too large)");
   dim3 grid((max_len + TT - 1) / TT, (a.rows + ROWS - 1) / ROWS, B);
   conv1d_kernel<CPT, WR, TPT><<<grid, 256, smem, st>>>(a);
   count_launch();

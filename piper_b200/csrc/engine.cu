@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 
@@ -88,6 +89,57 @@ ConvArgs Engine::conv_args(const ConvW& c, View x, const int* len, int len_scale
   return a;
 }
 
+void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
+  if (!profile_) {
+    launch_conv1d(a, B_, max_len, stream_);
+    return;
+  }
+  if (ev_used_ + 2 > ev_pool_.size()) {
+    const size_t old = ev_pool_.size();
+    ev_pool_.resize(old + 256);
+    for (size_t i = old; i < ev_pool_.size(); ++i) CUDA_CHECK(cudaEventCreate(&ev_pool_[i]));
+  }
+  ProfRec r;
+  r.tag = tag;
+  r.e0 = ev_pool_[ev_used_++];
+  r.e1 = ev_pool_[ev_used_++];
+  // algorithmic work of this launch: fp32 in + out + weights once; elementwise ops free
+  const double co = double(a.rows) / a.up, lin = len_sum, lout = len_sum * a.up;
+  r.bytes = 4.0 * (lin * a.ci + lout * (a.epi == EPI_GATE ? co / 2 : co) + double(a.ci) * a.rows * a.k + a.rows);
+  r.flops = 2.0 * lout * a.ci * co * a.k;
+  CUDA_CHECK(cudaEventRecord(r.e0, stream_));
+  launch_conv1d(a, B_, max_len, stream_);
+  CUDA_CHECK(cudaEventRecord(r.e1, stream_));
+  recs_.push_back(r);
+}
+
+void Engine::profile_begin() {
+  recs_.clear();
+  ev_used_ = 0;
+}
+
+std::string Engine::profile_json() {
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  struct Agg { long n = 0; double ms = 0, bytes = 0, flops = 0; };
+  std::map<std::string, Agg> agg;
+  for (const ProfRec& r : recs_) {
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    Agg& a = agg[r.tag];
+    a.n++; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
+  }
+  std::string out = "{";
+  bool first = true;
+  for (const auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\":{\"launches\":%ld,\"ms\":%.6f,\"bytes\":%.0f,\"flops\":%.0f}", first ? "" : ",",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
+    out += buf;
+    first = false;
+  }
+  return out + "}";
+}
+
 void Engine::ensure_front(int B, int Tmax) {
   const VoiceSpec& s = voice_.spec;
   const int Tp = round4(Tmax);
@@ -133,6 +185,7 @@ void Engine::upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B
     total += lens[b];
   }
   B_ = B; Tmax_ = Tmax; Tp_ = round4(Tmax);
+  sum_T_ = double(total);
   for (int i = 0; i < 3; ++i) scales_[i] = scales[i];
   seed_ = noise.seed;
   ensure_front(B, Tmax);
@@ -207,7 +260,7 @@ void Engine::dds(const DDSW& d, View h, View u, View v, int C) {
     launch_layernorm(a, B_, Tmax_, stream_);
     ConvArgs c = conv_args(l.pw, u, len, 1);
     c.y = v; c.epi = EPI_BIAS;
-    launch_conv1d(c, B_, Tmax_, stream_);
+    conv("dp", c, Tmax_, sum_T_);
     LnArgs b;
     b.a = v; b.r = h; b.y = h; b.gamma = W(l.n2.gamma); b.beta = W(l.n2.beta);
     b.C = C; b.mode = LN_GELU_RES; b.len = len;
@@ -238,6 +291,7 @@ void Engine::run_front() {
   const int H = s.hidden, I = s.inter, Tp = Tp_, B = B_, T = Tmax_;
   const int* len = len_d_.as<int>();
   if (debug_) taps_.clear();
+  if (profile_) profile_begin();
   View x = view(x_.as<float>(), H, Tp), t1 = view(t1_.as<float>(), H, Tp), qkv = view(qkv_.as<float>(), 3 * H, Tp),
        att = view(att_.as<float>(), H, Tp), ffn = view(ffn_.as<float>(), s.filter, Tp),
        stats = view(stats_.as<float>(), 2 * I, Tp);
@@ -247,27 +301,27 @@ void Engine::run_front() {
   for (const EncLayerW& e : voice_.enc) {
     ConvArgs c = conv_args(e.qkv, x, len, 1);
     c.y = qkv;
-    launch_conv1d(c, B, T, stream_);
+    conv("enc", c, T, sum_T_);
     launch_rel_attention(qkv, att, W(e.rel_k), W(e.rel_v), H, s.n_heads, s.window, len, B, T, stream_);
     c = conv_args(e.o, att, len, 1);
     c.y = t1; c.r = x; c.epi = EPI_RES;
-    launch_conv1d(c, B, T, stream_);
+    conv("enc", c, T, sum_T_);
     LnArgs l;
     l.a = t1; l.y = x; l.gamma = W(e.ln1.gamma); l.beta = W(e.ln1.beta); l.C = H; l.mode = LN_PLAIN; l.len = len;
     launch_layernorm(l, B, T, stream_);
     c = conv_args(e.ffn1, x, len, 1);
     c.y = ffn; c.epi = EPI_RELU;
-    launch_conv1d(c, B, T, stream_);
+    conv("enc", c, T, sum_T_);
     c = conv_args(e.ffn2, ffn, len, 1);
     c.y = t1; c.r = x; c.epi = EPI_RES;
-    launch_conv1d(c, B, T, stream_);
+    conv("enc", c, T, sum_T_);
     l.gamma = W(e.ln2.gamma); l.beta = W(e.ln2.beta);
     launch_layernorm(l, B, T, stream_);
   }
   {
     ConvArgs c = conv_args(voice_.enc_proj, x, len, 1);
     c.y = stats;
-    launch_conv1d(c, B, T, stream_);
+    conv("enc", c, T, sum_T_);
   }
   CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
   if (debug_) {
@@ -282,11 +336,11 @@ void Engine::run_front() {
   {
     ConvArgs c = conv_args(voice_.dp_pre, x, len, 1);
     c.y = h;
-    launch_conv1d(c, B, T, stream_);
+    conv("dp", c, T, sum_T_);
     dds(voice_.dp_dds, h, u, v, H);
     c = conv_args(voice_.dp_proj, h, len, 1);
     c.y = g;
-    launch_conv1d(c, B, T, stream_);
+    conv("dp", c, T, sum_T_);
   }
   launch_dp_noise(z2, have_eps_dp_ ? epsdp_d_.as<float>() : nullptr, epsoff_d_.as<long long>(), seed_, scales_[2], len, B,
                   T, stream_);
@@ -298,7 +352,7 @@ void Engine::run_front() {
     dds(cf.dds, h, u, v, H);
     ConvArgs c = conv_args(cf.proj, h, len, 1);
     c.y = pr;
-    launch_conv1d(c, B, T, stream_);
+    conv("dp", c, T, sum_T_);
     launch_spline_inverse(z2, x1, pr, s.spline_bins, 1.f / std::sqrt(float(H)), 5.0f, len, B, T, stream_);
   }
   flipped = !flipped;                         // the Flip before ElementwiseAffine
@@ -344,6 +398,7 @@ void Engine::plan_back() {
     off += (long long)ylen_h_[b] * s.hop;
   }
   total_samples_ = off;
+  sum_F_ = double(off) / s.hop;
   Fmax_ = Fmax;
   Fp_ = round4(Fmax);
   ensure_back(B_, Fmax);
@@ -364,7 +419,7 @@ void Engine::run_generator() {
   {
     ConvArgs c = conv_args(voice_.dec_pre, z, ylen, 1);
     c.y = S;
-    launch_conv1d(c, B, F, stream_);
+    conv("dec.pre", c, F, sum_F_);
   }
   int rate = 1;
   const int nk = int(voice_.resblocks.at(0).size());
@@ -379,7 +434,7 @@ void Engine::run_generator() {
       ConvArgs c = conv_args(up, S, ylen, rate);
       c.pre = PRE_LRELU; c.slope = 0.1f;           // F.leaky_relu(x, LRELU_SLOPE) before every upsample (models.py:354)
       c.y = A; c.epi = EPI_UPSAMPLE; c.q_extra = up.k - 1;
-      launch_conv1d(c, B, F * rate + c.q_extra, stream_);
+      conv("dec.up", c, F * rate + c.q_extra, sum_F_ * rate);
     }
     rate *= up.up;
     ch = co;
@@ -397,12 +452,12 @@ void Engine::run_generator() {
         if (s.resblock == 1) {
           ConvArgs a1 = conv_args(rb.c1[c], y, ylen, rate);
           a1.pre = PRE_LRELU; a1.slope = 0.1f; a1.y = P; a1.epi = EPI_BIAS;
-          launch_conv1d(a1, B, L, stream_);
+          conv("dec.rb", a1, L, sum_F_ * rate);
           ConvArgs a2 = conv_args(rb.c2[c], P, ylen, rate);
           a2.pre = PRE_LRELU; a2.slope = 0.1f; a2.r = y;
           if (last) { a2.epi = EPI_MRF; a2.y2 = S; a2.mrf = mrf; a2.mrf_n = nk; }
           else { a2.epi = EPI_RES; a2.y = Q; }
-          launch_conv1d(a2, B, L, stream_);
+          conv("dec.rb", a2, L, sum_F_ * rate);
           y = Q;
         } else {
           ConvArgs a1 = conv_args(rb.c1[c], y, ylen, rate);
@@ -410,7 +465,7 @@ void Engine::run_generator() {
           View dst = (c & 1) ? Q : P;
           if (last) { a1.epi = EPI_MRF; a1.y2 = S; a1.mrf = mrf; a1.mrf_n = nk; }
           else { a1.epi = EPI_RES; a1.y = dst; }
-          launch_conv1d(a1, B, L, stream_);
+          conv("dec.rb", a1, L, sum_F_ * rate);
           y = dst;
         }
       }
@@ -440,20 +495,20 @@ void Engine::run_back() {
     View x1 = cw.flipped ? z : z.offset_channels(half);
     ConvArgs c = conv_args(cw.pre, x0, ylen, 1);
     c.y = fh;
-    launch_conv1d(c, B, F, stream_);
+    conv("flow", c, F, sum_F_);
     const int nl = int(cw.in_layers.size());
     for (int i = 0; i < nl; ++i) {
       ConvArgs a = conv_args(cw.in_layers[i], fh, ylen, 1);
       a.y = acts; a.epi = EPI_GATE;
-      launch_conv1d(a, B, F, stream_);
+      conv("flow", a, F, sum_F_);
       ConvArgs r = conv_args(cw.res_skip[i], acts, ylen, 1);
       r.epi = EPI_WN; r.y = fh; r.r = fh; r.y2 = out; r.first = i == 0;
       r.split = i < nl - 1 ? H : 0;
-      launch_conv1d(r, B, F, stream_);
+      conv("flow", r, F, sum_F_);
     }
     ConvArgs p = conv_args(cw.post, out, ylen, 1);
     p.epi = EPI_SUBFROM; p.y = x1; p.r = x1;
-    launch_conv1d(p, B, F, stream_);
+    conv("flow", p, F, sum_F_);
   }
   if (debug_) save_tap("z", z, I, ylen_h_.data(), 1);
   CUDA_CHECK(cudaEventRecord(ev_[4], stream_));

@@ -78,6 +78,9 @@ class Engine {
   // per-stage device times of the last run_staged/synthesize: enc, dp, sync, flow(expand+flow), dec
   void stage_times(float out_ms[5]) const;
 
+  // per-launch CUDA-event timing of the conv kernel family, aggregated by pipeline stage (bench.py roofline)
+  void set_profile(bool on) { profile_ = on; }
+  std::string profile_json();
   void set_debug(bool on) { debug_ = on; }
   const HostTap* tap(const std::string& name) const;
   void set_max_frames(int64_t f) { max_frames_ = f; }
@@ -92,6 +95,8 @@ class Engine {
   void ensure_front(int B, int Tmax);
   void ensure_back(int B, int Fmax);
   void collect_stage_times();
+  void conv(const char* tag, ConvArgs& a, int max_len, double len_sum);
+  void profile_begin();
   void save_tap(const std::string& name, View v, int C, const int* len_host, int scale);
 
   View view(float* p, int C, int pitch) const { return View{p, (long long)C * pitch, pitch}; }
@@ -125,6 +130,12 @@ class Engine {
   DeviceBuf ga_, gp_, gq_, gs_, audio_d_, audio16_d_, peak_d_;
   PinnedBuf ids_pin_, misc_pin_, audio_pin_, audio16_pin_, eps_pin_;
 
+  struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; };
+  bool profile_ = false;
+  std::vector<cudaEvent_t> ev_pool_;
+  size_t ev_used_ = 0;
+  std::vector<ProfRec> recs_;
+  double sum_T_ = 0, sum_F_ = 0;
   bool debug_ = false;
   std::map<std::string, HostTap> taps_;
   float stage_ms_[5] = {0, 0, 0, 0, 0};

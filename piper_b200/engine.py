@@ -173,6 +173,14 @@ class Voice:
         check(self._lib.pb200_stage_times(self._h, ms))
         return list(ms)
 
+    def set_profile(self, on: bool):
+        check(self._lib.pb200_set_profile(self._h, 1 if on else 0))
+
+    def profile(self) -> dict:
+        buf = C.create_string_buffer(1 << 14)
+        check(self._lib.pb200_profile_read(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def set_debug(self, on: bool):
         check(self._lib.pb200_set_debug(self._h, 1 if on else 0))
 
