@@ -106,6 +106,16 @@ int pb200_stage_times(const pb200_voice* v, float ms[5]);
 int pb200_set_profile(pb200_voice* v, int32_t on);
 int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap);
 
+/* Select the convolution back end of the generator resblocks: 1 = tcgen05 tensor cores with bf16x3 split
+ * precision (default), 0 = fp32 CUDA cores.  Env PIPER_B200_MMA=0/1 sets the default at load. */
+int pb200_set_mma(pb200_voice* v, int32_t on);
+/* Kernel-level test hook: one Conv1d (same-padded, pad = dil*(k-1)/2) on host arrays through the chosen
+ * back end (0 = CUDA-core kernel, 1 = tensor-core kernel).  x [B][ci][L], w [co][ci][k], bias [co] or NULL,
+ * pre_slope != 0 applies leaky-relu to the input, resid [B][co][L] or NULL is added, y [B][co][L]. */
+int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, int32_t L, const float* w,
+                       const float* bias, int32_t co, int32_t k, int32_t dil, float pre_slope, const float* resid,
+                       float* y);
+
 void pb200_release(pb200_voice* v, const void* audio);
 
 /* Test taps: when debug is on, intermediate tensors of the last call are kept on the host.

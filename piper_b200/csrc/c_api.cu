@@ -170,6 +170,77 @@ int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap) {
   });
 }
 
+int pb200_set_mma(pb200_voice* v, int32_t on) {
+  return guarded([&] {
+    if (!v) throw std::runtime_error("pb200_set_mma: null argument");
+    v->engine.set_mma(on != 0);
+  });
+}
+
+#define CK(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, int32_t L, const float* w,
+                       const float* bias, int32_t co, int32_t k, int32_t dil, float pre_slope, const float* resid,
+                       float* y) {
+  return guarded([&] {
+    using namespace pb200;
+    if (!x || !w || !y || B <= 0 || L <= 0) throw std::runtime_error("pb200_debug_conv1d: bad argument");
+    const int Lp = (L + 3) & ~3, pad = dil * (k - 1) / 2, rows_p = (co + 3) & ~3;
+    float *dx = nullptr, *dy = nullptr, *dr = nullptr, *dw = nullptr, *db = nullptr;
+    int* dlen = nullptr;
+    uint16_t* dw16 = nullptr;
+    CK(cudaMalloc(&dx, size_t(B) * ci * Lp * 4));
+    CK(cudaMalloc(&dy, size_t(B) * co * Lp * 4));
+    CK(cudaMemset(dy, 0, size_t(B) * co * Lp * 4));
+    CK(cudaMemcpy2D(dx, size_t(Lp) * 4, x, size_t(L) * 4, size_t(L) * 4, size_t(B) * ci, cudaMemcpyHostToDevice));
+    if (resid) {
+      CK(cudaMalloc(&dr, size_t(B) * co * Lp * 4));
+      CK(cudaMemcpy2D(dr, size_t(Lp) * 4, resid, size_t(L) * 4, size_t(L) * 4, size_t(B) * co, cudaMemcpyHostToDevice));
+    }
+    if (bias) {
+      CK(cudaMalloc(&db, size_t(co) * 4));
+      CK(cudaMemcpy(db, bias, size_t(co) * 4, cudaMemcpyHostToDevice));
+    }
+    std::vector<int> lens(B, L);
+    CK(cudaMalloc(&dlen, size_t(B) * 4));
+    CK(cudaMemcpy(dlen, lens.data(), size_t(B) * 4, cudaMemcpyHostToDevice));
+    View vx{dx, (long long)ci * Lp, Lp}, vy{dy, (long long)co * Lp, Lp}, vr{dr, (long long)co * Lp, Lp};
+    if (backend == 0) {
+      std::vector<float> pk(size_t(ci) * k * rows_p, 0.f);
+      for (int i = 0; i < ci; ++i)
+        for (int j = 0; j < k; ++j)
+          for (int o = 0; o < co; ++o) pk[(size_t(i) * k + j) * rows_p + o] = w[(size_t(o) * ci + i) * k + j];
+      CK(cudaMalloc(&dw, pk.size() * 4));
+      CK(cudaMemcpy(dw, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+      ConvArgs a;
+      a.x = vx; a.y = vy; a.r = vr; a.w = dw; a.bias = db; a.len = dlen; a.len_scale = 1;
+      a.ci = ci; a.rows = co; a.rows_p = rows_p; a.k = k; a.dil = dil; a.pad = pad;
+      a.pre = pre_slope != 0.f ? PRE_LRELU : PRE_NONE; a.slope = pre_slope;
+      a.epi = resid ? EPI_RES : EPI_BIAS;
+      launch_conv1d(a, B, L, nullptr);
+    } else {
+      if (!mma_conv_supported(ci, co, k, dil)) throw std::runtime_error("shape not supported by the tensor-core conv");
+      std::vector<uint16_t> pk;
+      pack_conv_mma(w, co, ci, k, mma_conv_chunk(ci, co, k, dil), pk);
+      CK(cudaMalloc(&dw16, pk.size() * 2));
+      CK(cudaMemcpy(dw16, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      MmaConvArgs m;
+      m.x = vx; m.y = vy; m.r = vr; m.w = dw16; m.bias = db; m.len = dlen; m.len_scale = 1;
+      m.ci = ci; m.co = co; m.k = k; m.dil = dil; m.pad = pad;
+      m.pre = pre_slope != 0.f ? PRE_LRELU : PRE_NONE; m.slope = pre_slope;
+      m.epi = resid ? EPI_RES : EPI_BIAS;
+      launch_conv_mma(m, B, L, nullptr);
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy2D(y, size_t(L) * 4, dy, size_t(Lp) * 4, size_t(L) * 4, size_t(B) * co, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(dr); cudaFree(dw); cudaFree(db); cudaFree(dlen); cudaFree(dw16);
+  });
+}
+
 void pb200_release(pb200_voice*, const void*) {
   // Output buffers are engine-owned pinned staging areas reused by the next call; nothing to free.
 }

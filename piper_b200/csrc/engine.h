@@ -81,6 +81,8 @@ class Engine {
   // per-launch CUDA-event timing of the conv kernel family, aggregated by pipeline stage (bench.py roofline)
   void set_profile(bool on) { profile_ = on; }
   std::string profile_json();
+  void set_mma(bool on) { use_mma_ = on; }
+  bool mma() const { return use_mma_; }
   void set_debug(bool on) { debug_ = on; }
   const HostTap* tap(const std::string& name) const;
   void set_max_frames(int64_t f) { max_frames_ = f; }
@@ -96,6 +98,8 @@ class Engine {
   void ensure_back(int B, int Fmax);
   void collect_stage_times();
   void conv(const char* tag, ConvArgs& a, int max_len, double len_sum);
+  // resblock conv: tensor-core path when the layer has a bf16 split copy and the path is enabled
+  void rb_conv(const ConvW& w, ConvArgs& a, int max_len, double len_sum);
   void profile_begin();
   void save_tap(const std::string& name, View v, int C, const int* len_host, int scale);
 
@@ -108,7 +112,8 @@ class Engine {
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[8] = {};
-  DeviceBuf weights_;
+  DeviceBuf weights_, weights16_;
+  bool use_mma_ = true;
 
   // request state
   int B_ = 0, Tmax_ = 0, Tp_ = 0, Fmax_ = 0, Fp_ = 0;

@@ -8,6 +8,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
+#include <vector>
 
 namespace pb200 {
 
@@ -50,6 +52,25 @@ struct ConvArgs {
 
 // max_len = max over the batch of (len[b]*len_scale + q_extra): sizes the grid.
 void launch_conv1d(ConvArgs a, int B, int max_len, cudaStream_t st);
+
+// ---- tensor-core (tcgen05, bf16x3 split precision) Conv1d for the generator's resblocks ------------------
+struct MmaConvArgs {
+  View x, y, y2, r;
+  const uint16_t* w = nullptr;   // packed by pack_conv_mma
+  const float* bias = nullptr;
+  const int* len = nullptr;
+  int len_scale = 1;
+  int ci = 0, co = 0, k = 1, dil = 1, pad = 0;
+  int pre = PRE_NONE;
+  float slope = 0.f;
+  int epi = EPI_BIAS;            // EPI_BIAS | EPI_RES | EPI_MRF
+  int mrf = 0, mrf_n = 1;
+  int kc = 0, rows = 0, tmem_cols = 0;   // filled by the launcher
+};
+bool mma_conv_supported(int ci, int co, int k, int dil);
+int mma_conv_chunk(int ci, int co, int k, int dil);
+void pack_conv_mma(const float* w /*[co][ci][k]*/, int co, int ci, int k, int kc, std::vector<uint16_t>& out);
+void launch_conv_mma(MmaConvArgs a, int B, int max_len, cudaStream_t st);
 
 // ---- text encoder -----------------------------------------------------------------------------
 void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float scale, View x, const int* len, int B,

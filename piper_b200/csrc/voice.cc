@@ -196,6 +196,20 @@ struct Packer {
     return r;
   }
 
+  // split-precision bf16 copy for the tcgen05 path (resblock convs only)
+  void add_mma(const std::string& prefix, ConvW& c) {
+    const OnnxTensor& w = get(prefix + ".weight", 3);
+    const int co = int(w.dims[0]), ci = int(w.dims[1]), k = int(w.dims[2]);
+    if (!mma_conv_supported(ci, co, k, c.dil)) return;
+    std::vector<uint16_t> packed;
+    c.mma_kc = mma_conv_chunk(ci, co, k, c.dil);
+    pack_conv_mma(w.f32(), co, ci, k, c.mma_kc, packed);
+    const size_t off = (v.blob16.size() + 63) / 64 * 64;   // 128-byte aligned units
+    v.blob16.resize(off + packed.size(), 0);
+    std::memcpy(&v.blob16[off], packed.data(), packed.size() * 2);
+    c.mma = int64_t(off);
+  }
+
   LayerNormW ln(const std::string& prefix, int c_expected) {
     LayerNormW r;
     const OnnxTensor& g = get(prefix + ".gamma", 1);
@@ -399,10 +413,12 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
         if (c1.pad * 2 != c1.dil * (c1.k - 1)) fail("'" + r + "': resblock conv is not same-padded");
         rb.k = c1.k;
         dils.push_back(c1.dil);
+        P.add_mma(r + first + std::to_string(id), c1);
         rb.c1.push_back(c1);
         if (s.resblock == 1) {
           ConvW c2 = P.conv(r + ".convs2." + std::to_string(id), Packer::kPlain, ch, ch);
           if (c2.pad * 2 != c2.dil * (c2.k - 1)) fail("'" + r + "': resblock conv is not same-padded");
+          P.add_mma(r + ".convs2." + std::to_string(id), c2);
           rb.c2.push_back(c2);
         }
       }

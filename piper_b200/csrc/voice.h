@@ -21,6 +21,9 @@ struct ConvW {
   int ci = 0, rows = 0, rows_p = 0, k = 1, dil = 1, pad = 0;
   // ConvTranspose lowering: rows = Co * up, output t = q*up + (row % up) - up_pad
   int up = 1, up_pad = 0;
+  // tensor-core copy (bf16 hi/lo units, see conv_mma.cu): offset in uint16 units into blob16, -1 if none
+  int64_t mma = -1;
+  int mma_kc = 0;
 };
 
 struct LayerNormW {
@@ -71,6 +74,7 @@ struct VoiceSpec {
 struct PackedVoice {
   VoiceSpec spec;
   std::vector<float> blob;
+  std::vector<uint16_t> blob16;   // split-precision bf16 weights of the generator resblock convs
   int64_t emb = -1;
   std::vector<EncLayerW> enc;
   ConvW enc_proj;
@@ -93,5 +97,10 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& out);
 
 // Human/test-readable description (JSON) of the inferred spec and packed layout.
 std::string describe_voice(const PackedVoice& v);
+
+// defined in conv_mma.cu (declared here so the host-only loader can call them)
+bool mma_conv_supported(int ci, int co, int k, int dil);
+int mma_conv_chunk(int ci, int co, int k, int dil);
+void pack_conv_mma(const float* w, int co, int ci, int k, int kc, std::vector<uint16_t>& out);
 
 }  // namespace pb200

@@ -173,6 +173,9 @@ class Voice:
         check(self._lib.pb200_stage_times(self._h, ms))
         return list(ms)
 
+    def set_mma(self, on: bool):
+        check(self._lib.pb200_set_mma(self._h, 1 if on else 0))
+
     def set_profile(self, on: bool):
         check(self._lib.pb200_set_profile(self._h, 1 if on else 0))
 
@@ -190,6 +193,21 @@ class Voice:
         buf = np.empty((ch.value, ln.value), np.float32)
         check(self._lib.pb200_tap_read(self._h, name.encode(), b, _fptr(buf), buf.size))
         return buf
+
+
+def debug_conv1d(backend: int, x, w, bias=None, dil: int = 1, pre_slope: float = 0.0, resid=None) -> np.ndarray:
+    """One same-padded Conv1d through the CUDA-core (0) or tensor-core (1) kernel (unit-test hook)."""
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    B, ci, L = x.shape
+    co, ci2, k = w.shape
+    assert ci == ci2
+    y = np.empty((B, co, L), np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    r = None if resid is None else np.ascontiguousarray(resid, np.float32)
+    check(_lib.load().pb200_debug_conv1d(backend, _fptr(x), B, ci, L, _fptr(w), _fptr(b), co, k, dil, pre_slope,
+                                         _fptr(r), _fptr(y)))
+    return y
 
 
 def launch_count() -> int:
