@@ -106,11 +106,15 @@ int pb200_stage_times(const pb200_voice* v, float ms[5]);
 int pb200_set_profile(pb200_voice* v, int32_t on);
 int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap);
 
-/* Select the convolution back end of the generator resblocks: 1 = tcgen05 tensor cores with bf16x3 split
- * precision (default), 0 = fp32 CUDA cores.  Env PIPER_B200_MMA=0/1 sets the default at load. */
-int pb200_set_mma(pb200_voice* v, int32_t on);
+/* Select which layer families run on the tcgen05 tensor cores (split precision): bit 0 = generator (bf16x3),
+ * bit 1 = flow (tf32x3), bit 2 = text encoder (tf32x3); cleared bits use the fp32 CUDA-core kernel.
+ * Default 7.  The tensor core truncates (RZ) when adding into its fp32 accumulator; the tf32x3 layers therefore split
+ * K into 3 chains plus a separate accumulator for the correction terms and combine them in fp32 RN in the epilogue,
+ * which restores fp32-grade accuracy on the ill-conditioned real test voice.
+ * Env PIPER_B200_MMA=<mask> sets the default at load. */
+int pb200_set_mma(pb200_voice* v, int32_t mask);
 /* Kernel-level test hook: one Conv1d (same-padded, pad = dil*(k-1)/2) on host arrays through the chosen
- * back end (0 = CUDA-core kernel, 1 = tensor-core kernel).  x [B][ci][L], w [co][ci][k], bias [co] or NULL,
+ * back end (0 = CUDA-core kernel, 1 = tensor cores bf16x3, 2 = tensor cores tf32x3).  x [B][ci][L], w [co][ci][k], bias [co] or NULL,
  * pre_slope != 0 applies leaky-relu to the input, resid [B][co][L] or NULL is added, y [B][co][L]. */
 int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, int32_t L, const float* w,
                        const float* bias, int32_t co, int32_t k, int32_t dil, float pre_slope, const float* resid,

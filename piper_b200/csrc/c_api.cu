@@ -173,7 +173,7 @@ int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap) {
 int pb200_set_mma(pb200_voice* v, int32_t on) {
   return guarded([&] {
     if (!v) throw std::runtime_error("pb200_set_mma: null argument");
-    v->engine.set_mma(on != 0);
+    v->engine.set_mma(on);
   });
 }
 
@@ -192,7 +192,7 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
     const int Lp = (L + 3) & ~3, pad = dil * (k - 1) / 2, rows_p = (co + 3) & ~3;
     float *dx = nullptr, *dy = nullptr, *dr = nullptr, *dw = nullptr, *db = nullptr;
     int* dlen = nullptr;
-    uint16_t* dw16 = nullptr;
+    uint8_t* dw16 = nullptr;
     CK(cudaMalloc(&dx, size_t(B) * ci * Lp * 4));
     CK(cudaMalloc(&dy, size_t(B) * co * Lp * 4));
     CK(cudaMemset(dy, 0, size_t(B) * co * Lp * 4));
@@ -223,17 +223,22 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
       a.epi = resid ? EPI_RES : EPI_BIAS;
       launch_conv1d(a, B, L, nullptr);
     } else {
-      if (!mma_conv_supported(ci, co, k, dil)) throw std::runtime_error("shape not supported by the tensor-core conv");
-      std::vector<uint16_t> pk;
-      pack_conv_mma(w, co, ci, k, mma_conv_chunk(ci, co, k, dil), pk);
-      CK(cudaMalloc(&dw16, pk.size() * 2));
-      CK(cudaMemcpy(dw16, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+      MmaPlan plan;
+      if (!mma_plan(ci, co, k, dil, backend == 2, plan)) throw std::runtime_error("shape not supported by the tensor-core conv");
+      std::vector<float> pk(size_t(ci) * k * rows_p, 0.f);
+      for (int i = 0; i < ci; ++i)
+        for (int j = 0; j < k; ++j)
+          for (int o = 0; o < co; ++o) pk[(size_t(i) * k + j) * rows_p + o] = w[(size_t(o) * ci + i) * k + j];
+      std::vector<uint8_t> pm;
+      pack_conv_mma(pk.data(), ci, k, co, rows_p, plan, pm);
+      CK(cudaMalloc(&dw16, pm.size()));
+      CK(cudaMemcpy(dw16, pm.data(), pm.size(), cudaMemcpyHostToDevice));
       MmaConvArgs m;
       m.x = vx; m.y = vy; m.r = vr; m.w = dw16; m.bias = db; m.len = dlen; m.len_scale = 1;
-      m.ci = ci; m.co = co; m.k = k; m.dil = dil; m.pad = pad;
+      m.ci = ci; m.rows = co; m.k = k; m.dil = dil; m.pad = pad;
       m.pre = pre_slope != 0.f ? PRE_LRELU : PRE_NONE; m.slope = pre_slope;
       m.epi = resid ? EPI_RES : EPI_BIAS;
-      launch_conv_mma(m, B, L, nullptr);
+      launch_conv_mma(m, plan, B, L, nullptr);
     }
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy2D(y, size_t(L) * 4, dy, size_t(Lp) * 4, size_t(L) * 4, size_t(B) * co, cudaMemcpyDeviceToHost));

@@ -1,46 +1,56 @@
-// Conv1d on the 5th-generation tensor cores: tcgen05.mma (kind::f16, BF16 operands, FP32 accumulators in
-// TMEM) with error-compensated split precision ("bf16x3").
+// Conv1d / ConvTranspose1d on the 5th-generation tensor cores: tcgen05.mma with FP32 accumulators in TMEM and
+// error-compensated split precision.
 //
-//   x = x_hi + x_lo,  w = w_hi + w_lo   (hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits kept)
-//   y = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi          (three MMAs, products exact in fp32, fp32 accumulate)
+//   x = x_hi + x_lo,  w = w_hi + w_lo,   y = x_hi*w_hi + x_hi*w_lo + x_lo*w_hi   (three MMAs per k-step)
 //
-// Single-pass BF16/TF32 misses the 1e-3 waveform bar (SURVEY.md finding 7); the 3-term split measured on the
-// CPU emulation gives 6.5e-5 on the generator of the real voice.
+//   * kind::f16  / BF16 operands ("bf16x3", 16 mantissa bits kept): HiFi-GAN generator layers
+//   * kind::tf32 / TF32 operands ("tf32x3", 21 mantissa bits kept): flow (WaveNet) and text-encoder layers,
+//     whose outputs feed exp()/ceil() and need fp32-grade accuracy (DESIGN.md §Precision has the measurements;
+//     single-pass BF16/TF32 misses the 1e-3 waveform bar, SURVEY.md finding 7).
 //
-// GEMM view of a stride-1 Conv1d layer (C_in -> C_out, K taps, dilation d), one CTA per 128 output positions:
-//   D[128 t][C_out] += A_j[128 t][KC ci] * W_j[C_out][KC ci]^T        for every tap j and channel chunk
-// A_j is NOT materialised per tap: the activation tile (with its halo) is staged once per channel chunk in
-// the canonical no-swizzle K-major layout  [ci/8][row][8 ci]  where consecutive rows (time steps) are 16 bytes
-// apart, so tap j is the same buffer with the descriptor start address advanced by j*d*16 bytes.
-// The fp32 -> (leaky-relu) -> bf16 hi/lo conversion happens while staging; weights are pre-split and
-// pre-laid-out at load time and stream through a two-deep cp.async ring; the epilogue reads the
-// accumulators with tcgen05.ld (lane = output position -> coalesced stores along time) and applies
-// bias / residual / MRF-average exactly like the CUDA-core kernel in conv1d.cu.
+// GEMM view of one layer (C_in -> rows, K taps, dilation d); one CTA owns MT (128 or 256) output positions x
+// one tile of up to 256 output rows:
+//     D[MT t][N] += A_j[MT t][KC ci] * W_j[N][KC ci]^T      for every tap j and every channel chunk
+// A_j is never materialised per tap: the activation chunk (with its halo) is staged once in the canonical
+// no-swizzle K-major layout [ci/E][row][E] (E = 16 bytes of elements) where consecutive rows (time steps) are
+// 16 bytes apart, so tap j is the same buffer with the descriptor start address advanced by j*d*16 bytes.
 //
-// Reference ops: ResBlock1/ResBlock2 convolutions of the HiFi-GAN generator (modules.py:301-314,355-364).
+// Warp roles (320 threads):
+//   warps 0-7  producers: global fp32 -> (leaky-relu) -> hi/lo split -> shared, double-buffered per channel chunk;
+//              then the epilogue: tcgen05.ld (lane = output position -> coalesced stores along time), bias and
+//              the same fused epilogues as conv1d.cu (residual, MRF average, WaveNet gate, WN residual/skip,
+//              coupling subtract, relu, ConvTranspose pixel-shuffle)
+//   warp  8    owns the TMEM allocation; its lane 0 issues every tcgen05.mma and the tcgen05.commit that
+//              releases ring slots (mbarrier arrive when the MMAs that read the slot have retired)
+//   warp  9    lane 0 feeds the weight ring with cp.async.bulk (TMA 1-D) + mbarrier complete_tx
+//
+// Reference ops: modules.py:184-209 (WN), 301-314 / 355-364 (ResBlock1/2), models.py:348-368 (Generator),
+// attentions.py:215-223,386-407 (1x1 projections, FFN), all lowered by voice.cc.
 #include "kernels.cuh"
 
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstring>
-#include <vector>
-
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace pb200 {
 void count_launch();
 
 namespace {
 
-constexpr int MMA_M = 128;          // output positions per CTA == TMEM lanes
-constexpr int MMA_THREADS = 256;
+constexpr int PROD_THREADS = 256;                 // 8 producer / epilogue warps
+constexpr int MMA_THREADS = PROD_THREADS + 64;    // + warp 8 (MMA issuer, TMEM owner) + warp 9 (weight TMA)
+constexpr int MAX_A_SLOTS = 2;
+constexpr int MAX_W_SLOTS = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Shared-memory matrix descriptor, SWIZZLE_NONE, K-major "interleave" canonical layout:
-//   element (row, k) at  start + (row % 8) * 16 + (row / 8) * SBO + (k / 8) * LBO + (k % 8) * 2   bytes
-// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)).
+// Shared-memory matrix descriptor, SWIZZLE_NONE, K-major canonical ("interleave") layout:
+//   element (row, k) at  start + (row % 8) * 16 + (row / 8) * SBO + (k / E) * LBO + (k % E) * elem_bytes
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64)=0)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -50,52 +60,71 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// Instruction descriptor for kind::f16: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), both K-major,
-// N>>3 at bits 17-22, M>>4 at bits 24-28  (cute::UMMA::InstrDescriptor).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (bits 4-5 = 1), A/B format at bits 7-9 / 10-12
+// (1 = BF16, 2 = TF32), both operands K-major, N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N) {
+  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
-      : "memory");
+template <bool TF32>
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+  }
 }
 
 __device__ __forceinline__ void mma_commit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
                : "memory");
 }
-
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
 }
-
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   const uint32_t a = smem_u32(mbar);
   asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
+      "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t"
-      "}\n" ::"r"(a), "r"(parity)
+      "DONE_%=:\n\t}\n" ::"r"(a),
+      "r"(parity)
       : "memory");
 }
-
-__device__ __forceinline__ void cp_async16_mma(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // .x = a (low half), .y = b
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -110,160 +139,235 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// dynamic shared memory layout (all offsets multiples of 128 bytes):
-//   A_hi [KC/8][R][8] bf16 | A_lo same | W ring: 2 x { hi [KC/8][N][8], lo [KC/8][N][8] }
+__device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
+
+struct Barriers {
+  uint64_t a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS], w_full[MAX_W_SLOTS], w_empty[MAX_W_SLOTS], d_full;
+};
+
+// dynamic shared memory: A ring  A_SLOTS x { hi [KC/E][R][16 B], lo same }  |  W ring  W_SLOTS x { hi [KC/E][N][16 B], lo }
+template <bool TF32, int MT>
 __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs a) {
+  constexpr int ES = TF32 ? 4 : 2;         // operand element bytes
+  constexpr int E = 16 / ES;               // elements per 16-byte K chunk
+  constexpr int KSTEP = 2 * E;             // K per MMA (32 bytes): 16 (bf16) / 8 (tf32)
+  constexpr int MH = MT / 128;             // accumulators (row halves) per CTA
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mbar_w[2];   // weight-ring slot consumed by the tensor core
-  __shared__ __align__(8) uint64_t mbar_a;      // activation chunk consumed
+  __shared__ __align__(8) Barriers bar;
   __shared__ uint32_t tmem_base_s;
 
   const int b = blockIdx.y;
   const int L = a.len[b] * a.len_scale;
-  const int t0 = blockIdx.x * MMA_M;
-  if (t0 >= L) return;
+  const int Lq = L + a.q_extra;
+  const int t0 = blockIdx.x * MT;
+  if (t0 >= Lq) return;
+  const int n0 = blockIdx.z * a.n_tile;                  // first output row of this CTA
+  const int N = min(a.n_tile, a.rows - n0);              // rows in this tile (multiple of 16)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = a.co, KC = a.kc;
-  const int R = a.rows;                          // staged rows: 128 + (k-1)*dil rounded up to 8
-  const int a_part_bytes = KC * R * 2;
-  const int w_part_bytes = KC * N * 2;
-  uint8_t* A_hi = smem;
-  uint8_t* A_lo = smem + a_part_bytes;
-  uint8_t* W_ring = smem + 2 * a_part_bytes;     // slot s at + s * 2 * w_part_bytes
+  const int KC = a.kc, R = a.stage_rows;
+  const int A_SLOTS = a.a_slots, W_SLOTS = a.w_slots;
+  const int a_part = KC * R * ES, w_part = KC * a.n_tile * ES;      // ring slots are sized for a full N tile
+  uint8_t* A_ring = smem;
+  uint8_t* W_ring = smem + size_t(A_SLOTS) * 2 * a_part;
   const int n_kc = a.ci / KC;
-  const int n_units = n_kc * a.k;                // weight units: (kc, tap), kc outer
-  const size_t unit_bytes = size_t(2) * w_part_bytes;
+  const int n_units = n_kc * a.k;
+  const uint32_t unit_bytes = 2u * (uint32_t)w_part;
+  const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;            // skip the second row half at the ragged end
 
-  // ---- one-time setup: TMEM allocation (warp 0), barriers (one thread)
-  if (warp == 0) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
                  "r"((uint32_t)a.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  if (tid == 32) {
-    mbar_init(&mbar_w[0], 1);
-    mbar_init(&mbar_w[1], 1);
-    mbar_init(&mbar_a, 1);
+  if (tid == 0) {
+    for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&bar.a_full[i], PROD_THREADS); mbar_init(&bar.a_empty[i], 1); }
+    for (int i = 0; i < W_SLOTS; ++i) { mbar_init(&bar.w_full[i], 1); mbar_init(&bar.w_empty[i], 1); }
+    mbar_init(&bar.d_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
-  const uint32_t idesc = make_idesc_bf16(MMA_M, N);
 
-  auto load_unit = [&](int u) {                  // cp.async one (kc, tap) weight unit into ring slot u & 1
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w) + size_t(u) * unit_bytes;
-    uint8_t* dst = W_ring + size_t(u & 1) * unit_bytes;
-    for (int i = tid * 16; i < (int)unit_bytes; i += MMA_THREADS * 16) cp_async16_mma(dst + i, src + i);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-  };
-
-  const float* xb = a.x.p + (long long)b * a.x.bs;
-  uint32_t ph_w[2] = {0, 0}, ph_a = 0;
-  bool first_mma = true;
-  load_unit(0);
-  int u = 0;
-  for (int kc = 0; kc < n_kc; ++kc) {
-    // ---- stage the activation chunk: fp32 -> leaky-relu -> bf16 hi/lo, layout [g][row][8]
-    if (kc > 0) {                                // previous chunk's MMAs must have finished reading A
-      mbar_wait(&mbar_a, ph_a);
-      ph_a ^= 1;
-    }
-    const int c0 = kc * KC;
-    const int items = (KC / 8) * R;
-    for (int idx = tid; idx < items; idx += MMA_THREADS) {
-      const int g = idx / R, r = idx - g * R;
-      const int t = t0 - a.pad + r;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (t >= 0 && t < L) {
-        const float* xr = xb + (long long)(c0 + g * 8) * a.x.cs + t;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(xr + (long long)e * a.x.cs);
+  if (warp >= 8) {
+    // =========================== control warps: weight TMA (warp 9) and MMA issue (warp 8), one lane each ===
+    if (warp == 9 && lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + size_t(blockIdx.z) * n_units * unit_bytes;
+      for (int u = 0; u < n_units; ++u) {
+        const int s = u % W_SLOTS;
+        if (u >= W_SLOTS) mbar_wait(&bar.w_empty[s], ((u / W_SLOTS) - 1) & 1);
+        mbar_expect_tx(&bar.w_full[s], unit_bytes);
+        bulk_g2s(W_ring + size_t(s) * unit_bytes, wsrc + size_t(u) * unit_bytes, unit_bytes, &bar.w_full[s]);
       }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        float p = v[e], q = v[e + 1];
-        if (a.pre == PRE_LRELU) {
-          p = p > 0.f ? p : p * a.slope;
-          q = q > 0.f ? q : q * a.slope;
-        }
-        const float ph = __bfloat162float(__float2bfloat16_rn(p)), qh = __bfloat162float(__float2bfloat16_rn(q));
-        hi[e >> 1] = pack_bf16(ph, qh);
-        lo[e >> 1] = pack_bf16(p - ph, q - qh);
-      }
-      const int off = (g * R + r) * 16;
-      *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    }
-
-    for (int j = 0; j < a.k; ++j, ++u) {
-      // prefetch the next weight unit into the other slot once the tensor core has released it
-      if (u + 1 < n_units) {
-        if (u + 1 >= 2) {
-          mbar_wait(&mbar_w[(u + 1) & 1], ph_w[(u + 1) & 1]);
-          ph_w[(u + 1) & 1] ^= 1;
-        }
-        load_unit(u + 1);
-        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-      }
-      // generic-proxy writes (st.shared / cp.async) -> visible to the tensor core's async proxy
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      __syncthreads();
-      if (tid == 0) {
+    } else if (warp == 8 && lane == 0) {
+      const uint32_t idesc = make_idesc(TF32, 128, N);
+      const uint32_t a_lbo = (uint32_t)R * 16, w_lbo = (uint32_t)a.n_tile * 16;
+      // The tensor core truncates (round-toward-zero) when it adds into the fp32 accumulator, a systematic bias
+      // that grows with the number of accumulation steps.  Where fp32-grade accuracy is needed (tf32x3 layers)
+      // the K range is cut into `chains` independent accumulators and the two small correction terms
+      // (hi*lo, lo*hi) go to an accumulator of their own; the epilogue adds them in fp32 with round-to-nearest.
+      uint32_t started = 0;                               // bit (mh * 8 + accumulator) set once it holds data
+      int u = 0;
+      for (int kc = 0; kc < n_kc; ++kc) {
+        const int as = kc % A_SLOTS;
+        mbar_wait(&bar.a_full[as], (kc / A_SLOTS) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t a_hi = smem_u32(A_hi), a_lo = smem_u32(A_lo);
-        const uint32_t w_hi = smem_u32(W_ring + size_t(u & 1) * unit_bytes), w_lo = w_hi + w_part_bytes;
-        const uint32_t a_lbo = R * 16, w_lbo = N * 16;
-        const uint32_t shift = (uint32_t)(j * a.dil) * 16;
-        for (int kb = 0; kb < KC / 16; ++kb) {
-          const uint64_t ah = make_desc(a_hi + 2 * kb * a_lbo + shift, a_lbo, 128);
-          const uint64_t al = make_desc(a_lo + 2 * kb * a_lbo + shift, a_lbo, 128);
-          const uint64_t wh = make_desc(w_hi + 2 * kb * w_lbo, w_lbo, 128);
-          const uint64_t wl = make_desc(w_lo + 2 * kb * w_lbo, w_lbo, 128);
-          mma_bf16(tmem_d, ah, wh, idesc, !first_mma);
-          first_mma = false;
-          mma_bf16(tmem_d, ah, wl, idesc, true);
-          mma_bf16(tmem_d, al, wh, idesc, true);
+        const uint32_t a_hi = smem_u32(A_ring + size_t(as) * 2 * a_part), a_lo = a_hi + a_part;
+        for (int j = 0; j < a.k; ++j, ++u) {
+          const int ws = u % W_SLOTS;
+          mbar_wait(&bar.w_full[ws], (u / W_SLOTS) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t w_hi = smem_u32(W_ring + size_t(ws) * unit_bytes), w_lo = w_hi + w_part;
+          const uint32_t shift = (uint32_t)(j * a.dil) * 16;
+          const int chain = (u * a.chains) / n_units;
+          const int corr = a.sep_corr ? a.chains : chain;
+          for (int kb = 0; kb < KC / KSTEP; ++kb) {
+            const uint64_t wh = make_desc(w_hi + 2 * kb * w_lbo, w_lbo, 128);
+            const uint64_t wl = make_desc(w_lo + 2 * kb * w_lbo, w_lbo, 128);
+            for (int mh = 0; mh < mh_live; ++mh) {
+              const uint32_t row_off = shift + (uint32_t)mh * 128 * 16;
+              const uint64_t ah = make_desc(a_hi + 2 * kb * a_lbo + row_off, a_lbo, 128);
+              const uint64_t al = make_desc(a_lo + 2 * kb * a_lbo + row_off, a_lbo, 128);
+              const uint32_t dm = tmem_d + (uint32_t)(mh * a.mh_stride + chain * a.acc_cols);
+              const uint32_t dc = tmem_d + (uint32_t)(mh * a.mh_stride + corr * a.acc_cols);
+              const uint32_t bm = 1u << (mh * 8 + chain), bc = 1u << (mh * 8 + corr);
+              mma_ss<TF32>(dm, ah, wh, idesc, (started & bm) != 0);
+              started |= bm;
+              mma_ss<TF32>(dc, ah, wl, idesc, (started & bc) != 0);
+              started |= bc;
+              mma_ss<TF32>(dc, al, wh, idesc, true);
+            }
+          }
+          mma_commit(&bar.w_empty[ws]);                 // ring slot free once these MMAs have read it
         }
-        mma_commit(&mbar_w[u & 1]);                    // ring slot free when these MMAs retire
-        if (j == a.k - 1) mma_commit(&mbar_a);         // ... and so is the activation chunk
+        mma_commit(&bar.a_empty[as]);
       }
+      mma_commit(&bar.d_full);                          // commits are cumulative: every MMA above has retired
     }
-  }
-  // ---- all MMAs of this tile issued: the last commit on mbar_a covers them (commits are cumulative)
-  mbar_wait(&mbar_a, ph_a);
-  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  } else {
+    // =========================== producers: stage activation chunks ========================================
+    const float* xb = a.x.p + (long long)b * a.x.bs;
+    for (int kc = 0; kc < n_kc; ++kc) {
+      const int as = kc % A_SLOTS;
+      if (kc >= A_SLOTS) mbar_wait(&bar.a_empty[as], ((kc / A_SLOTS) - 1) & 1);
+      uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
+      uint8_t* A_lo = A_hi + a_part;
+      const int c0 = kc * KC;
+      const int items = (KC / E) * R;
+      // two work items per thread per trip: all 2*E global loads are issued before any conversion
+      for (int base = tid; base < items; base += 2 * PROD_THREADS) {
+        float v[2][E];
+        int offs[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int idx = base + s * PROD_THREADS;
+          offs[s] = -1;
+#pragma unroll
+          for (int e = 0; e < E; ++e) v[s][e] = 0.f;
+          if (idx < items) {
+            const int g = idx / R, r = idx - g * R;
+            const int t = t0 - a.pad + r;
+            offs[s] = (g * R + r) * 16;
+            if (t >= 0 && t < L) {
+              const float* xr = xb + (long long)(c0 + g * E) * a.x.cs + t;
+#pragma unroll
+              for (int e = 0; e < E; ++e) v[s][e] = __ldg(xr + (long long)e * a.x.cs);
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (offs[s] < 0) continue;
+          if (a.pre == PRE_LRELU) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[s][e] = v[s][e] > 0.f ? v[s][e] : v[s][e] * a.slope;
+          }
+          if (TF32) {
+            float h[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h[e] = to_tf32(v[s][e]);
+            *reinterpret_cast<float4*>(A_hi + offs[s]) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(A_lo + offs[s]) =
+                make_float4(v[s][0] - h[0], v[s][1] - h[1], v[s][2] - h[2], v[s][3] - h[3]);
+          } else {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float ph = __bfloat162float(__float2bfloat16_rn(v[s][e % E])),
+                          qh = __bfloat162float(__float2bfloat16_rn(v[s][(e + 1) % E]));
+              hi[e >> 1] = pack_bf16(ph, qh);
+              lo[e >> 1] = pack_bf16(v[s][e % E] - ph, v[s][(e + 1) % E] - qh);
+            }
+            *reinterpret_cast<uint4*>(A_hi + offs[s]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(A_lo + offs[s]) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> tensor-core proxy
+      mbar_arrive(&bar.a_full[as]);
+    }
 
-  // ---- epilogue: warp w reads TMEM lanes 32*(w%4)..+31 (its sub-partition), column half w/4
-  {
+    // =========================== epilogue ====================================================================
+    mbar_wait(&bar.d_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int q = warp & 3, half = warp >> 2;
-    const int t = t0 + q * 32 + lane;
-    const int ncol = N / 2;
     float* yb = a.y.p ? a.y.p + (long long)b * a.y.bs : nullptr;
     float* y2b = a.y2.p ? a.y2.p + (long long)b * a.y2.bs : nullptr;
     const float* rb = a.r.p ? a.r.p + (long long)b * a.r.bs : nullptr;
-    for (int cb = 0; cb < ncol; cb += 16) {
-      const int col0 = half * ncol + cb;
-      float v[16];
-      tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-      if (t < L) {
+    const int n_chunks = N / 16;
+    for (int mh = 0; mh < mh_live; ++mh) {
+      const int t = t0 + mh * 128 + q * 32 + lane;
+      for (int c = half; c < n_chunks; c += 2) {
+        float v[16];
+        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * a.mh_stride + c * 16);
+        tmem_ld16(tbase, v);
+        const int n_acc = a.chains + (a.sep_corr ? 1 : 0);
+        for (int ai = 1; ai < n_acc; ++ai) {             // fp32 round-to-nearest combine of the partial sums
+          float p[16];
+          tmem_ld16(tbase + (uint32_t)(ai * a.acc_cols), p);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += p[i];
+        }
+        if (t >= Lq) continue;
+        const int row0 = n0 + c * 16;
+        if (a.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + row0 + i);
+        }
+        if (a.epi == EPI_GATE) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2)
+            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = tanhf(v[i]) * sigmoid_acc(v[i + 1]);
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int co = col0 + i;
-          float val = v[i] + (a.bias ? __ldg(a.bias + co) : 0.f);
+          const int row = row0 + i;
+          const float val = v[i];
           switch (a.epi) {
-            case EPI_BIAS: yb[(long long)co * a.y.cs + t] = val; break;
-            case EPI_RES: yb[(long long)co * a.y.cs + t] = val + rb[(long long)co * a.r.cs + t]; break;
+            case EPI_BIAS: yb[(long long)row * a.y.cs + t] = val; break;
+            case EPI_RELU: yb[(long long)row * a.y.cs + t] = fmaxf(val, 0.f); break;
+            case EPI_RES: yb[(long long)row * a.y.cs + t] = val + rb[(long long)row * a.r.cs + t]; break;
+            case EPI_WN:
+              if (row < a.split) {
+                yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + val;
+              } else {
+                float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
+                *o = a.first ? val : *o + val;
+              }
+              break;
+            case EPI_SUBFROM: yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] - val; break;
+            case EPI_UPSAMPLE: {
+              const int co = row / a.up, phi = row - co * a.up;
+              const int to = t * a.up + phi - a.up_pad;
+              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = val;
+              break;
+            }
             case EPI_MRF: {
-              const float v2 = val + rb[(long long)co * a.r.cs + t];
-              float* o = y2b + (long long)co * a.y2.cs + t;
+              const float v2 = val + rb[(long long)row * a.r.cs + t];
+              float* o = y2b + (long long)row * a.y2.cs + t;
               if (a.mrf == 0) *o = v2;
               else if (a.mrf == 1) *o = *o + v2;
               else *o = (*o + v2) / (float)a.mrf_n;
@@ -277,53 +381,96 @@ __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)a.tmem_cols)
                  : "memory");
   }
 }
 
+int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
 }  // namespace
 
-bool mma_conv_supported(int ci, int co, int k, int dil) {
-  if (ci % 16 != 0 || co % 32 != 0 || co < 32 || co > 256) return false;
-  const int rows = (MMA_M + (k - 1) * dil + 7) & ~7;
-  const int kc = mma_conv_chunk(ci, co, k, dil);
-  return kc > 0 && rows * 16 < (1 << 18);
-}
-
-// channel chunk KC (multiple of 16, divides ci) such that A (hi+lo) + 2 weight slots fit ~100 KB (2 CTAs / SM)
-int mma_conv_chunk(int ci, int co, int k, int dil) {
-  const int rows = (MMA_M + (k - 1) * dil + 7) & ~7;
-  for (int kc = ci; kc >= 16; kc -= 16) {
-    if (ci % kc) continue;
-    const size_t bytes = size_t(2) * kc * rows * 2 + size_t(2) * 2 * kc * co * 2;
-    if (bytes <= 110 * 1024) return kc;
+// Tiling of one layer for the tensor-core path.  Returns false when the shape is outside what the kernel handles.
+bool mma_plan(int ci, int rows, int k, int dil, bool tf32, MmaPlan& p) {
+  const int es = tf32 ? 4 : 2, kstep = tf32 ? 8 : 16;
+  if (ci % kstep != 0 || rows % 16 != 0 || rows < 16) return false;
+  // accumulators per row half: tf32x3 layers use 3 K-chains + 1 correction accumulator (see the MMA issuer)
+  p.chains = tf32 ? 3 : 1;
+  p.sep_corr = tf32;
+  const int n_acc = p.chains + (p.sep_corr ? 1 : 0);
+  // output-row tile: multiple of 16 dividing the rows evenly; <= 256 columns of TMEM per CTA for all its
+  // accumulators when several are needed (two CTAs per SM), <= 256 rows otherwise
+  const int max_tile = n_acc > 1 ? 256 / n_acc : 256;
+  int nt = 1;
+  while (rows / nt > max_tile || rows % nt != 0 || (rows / nt) % 16 != 0) {
+    if (++nt > 64) return false;
   }
-  return 0;
+  p.n_tile = rows / nt;
+  p.n_tiles = nt;
+  p.acc_cols = n_acc > 1 ? ((p.n_tile + 31) & ~31) : pow2_cols(p.n_tile);
+  // Occupancy first: most layers are bound by memory latency/bandwidth or by weight streaming, which several
+  // small co-resident CTAs hide better than one deeply pipelined CTA.  Try footprints of <= 56 KB (4 CTAs / SM,
+  // single activation slot), then 100 KB and 200 KB (double-buffered activations).
+  struct Try { size_t budget; int a_slots, w_slots; };
+  const Try tries[] = {{size_t(56) << 10, 1, 3}, {size_t(100) << 10, 2, 3}, {size_t(200) << 10, 2, 3}};
+  for (const Try& tr : tries)
+    for (int mt : {256, 128}) {
+      if (n_acc > 1 && mt != 128) continue;
+      if (mt / 128 * n_acc * p.acc_cols > 512) continue;
+      const int stage_rows = (mt + (k - 1) * dil + 7) & ~7;
+      if (stage_rows * 16 >= (1 << 18)) continue;
+      for (int kc = ci; kc >= kstep; kc -= kstep) {     // largest channel chunk that divides ci and fits
+        if (ci % kc) continue;
+        const size_t bytes = size_t(tr.a_slots) * 2 * kc * stage_rows * es + size_t(tr.w_slots) * 2 * kc * p.n_tile * es;
+        if (bytes <= tr.budget) {
+          p.mt = mt; p.kc = kc; p.stage_rows = stage_rows; p.smem = bytes; p.tf32 = tf32;
+          p.a_slots = tr.a_slots; p.w_slots = tr.w_slots;
+          p.mh_stride = n_acc * p.acc_cols;
+          p.tmem_cols = pow2_cols(mt / 128 * p.mh_stride);
+          return true;
+        }
+      }
+    }
+  return false;
 }
 
-void launch_conv_mma(MmaConvArgs a, int B, int max_len, cudaStream_t st) {
+void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st) {
   if (B <= 0 || max_len <= 0) return;
-  a.rows = (MMA_M + (a.k - 1) * a.dil + 7) & ~7;
-  a.kc = mma_conv_chunk(a.ci, a.co, a.k, a.dil);
-  if (a.kc <= 0) throw std::runtime_error("conv_mma: layer shape not supported by the tensor-core path");
-  a.tmem_cols = a.co <= 32 ? 32 : a.co <= 64 ? 64 : a.co <= 128 ? 128 : 256;
-  const size_t smem = size_t(2) * a.kc * a.rows * 2 + size_t(2) * 2 * a.kc * a.co * 2;
+  a.kc = p.kc; a.stage_rows = p.stage_rows; a.n_tile = p.n_tile; a.acc_cols = p.acc_cols; a.tmem_cols = p.tmem_cols;
+  a.a_slots = p.a_slots; a.w_slots = p.w_slots;
+  // never more chains than weight units, or an accumulator would be read without ever being written
+  a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);
+  a.sep_corr = p.sep_corr ? 1 : 0; a.mh_stride = p.mh_stride;
+  // small problems: 128-row tiles double the CTA count (latency regime); the plan's kc also fits MT = 128
+  int mt = p.mt;
+  if (mt == 256 && (long long)((max_len + 255) / 256) * B * p.n_tiles < 148) {
+    mt = 128;
+    a.stage_rows = (128 + (a.k - 1) * a.dil + 7) & ~7;
+    a.tmem_cols = pow2_cols(p.mh_stride);
+  }
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mma_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mma_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mma_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set[dev & 63] = true;
   }
-  dim3 grid((max_len + MMA_M - 1) / MMA_M, B);
-  conv_mma_kernel<<<grid, MMA_THREADS, smem, st>>>(a);
+  dim3 grid((max_len + mt - 1) / mt, B, p.n_tiles);
+  if (p.tf32) {
+    if (mt == 256) conv_mma_kernel<true, 256><<<grid, MMA_THREADS, p.smem, st>>>(a);
+    else conv_mma_kernel<true, 128><<<grid, MMA_THREADS, p.smem, st>>>(a);
+  } else {
+    if (mt == 256) conv_mma_kernel<false, 256><<<grid, MMA_THREADS, p.smem, st>>>(a);
+    else conv_mma_kernel<false, 128><<<grid, MMA_THREADS, p.smem, st>>>(a);
+  }
   count_launch();
 }
 
-// Host-side packing of one Conv1d weight [Co][Ci][K] (fp32) into the tensor-core layout:
-//   units (kc, tap) in issue order, each unit = { hi [KC/8][Co][8], lo [KC/8][Co][8] } bf16
+// ---- host-side packing ---------------------------------------------------------------------------------------
 static inline uint16_t f32_to_bf16_rn(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
@@ -337,24 +484,45 @@ static inline float bf16_to_f32(uint16_t h) {
   memcpy(&f, &u, 4);
   return f;
 }
+static inline float f32_to_tf32_rna(float f) {   // cvt.rna.tf32.f32: round to nearest, ties away from zero
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
 
-void pack_conv_mma(const float* w, int co, int ci, int k, int kc, std::vector<uint16_t>& out) {
-  const int n_kc = ci / kc;
-  const size_t part = size_t(kc) * co;
-  out.assign(size_t(n_kc) * k * 2 * part, 0);
-  for (int c = 0; c < n_kc; ++c)
-    for (int j = 0; j < k; ++j) {
-      uint16_t* unit = out.data() + (size_t(c) * k + j) * 2 * part;
-      for (int g = 0; g < kc / 8; ++g)
-        for (int n = 0; n < co; ++n)
-          for (int e = 0; e < 8; ++e) {
-            const float v = w[(size_t(n) * ci + (c * kc + g * 8 + e)) * k + j];
-            const uint16_t hi = f32_to_bf16_rn(v);
-            const uint16_t lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
-            unit[(size_t(g) * co + n) * 8 + e] = hi;
-            unit[part + (size_t(g) * co + n) * 8 + e] = lo;
-          }
-    }
+// Source weights in the engine's fp32 layout wsrc[ci][k][rows_p] (row fastest).  Output: per N tile, units
+// (kc, tap) in issue order, each unit = { hi [KC/E][n_tile][E], lo same }, E = 8 bf16 or 4 tf32(fp32 container).
+void pack_conv_mma(const float* wsrc, int ci, int k, int rows, int rows_p, const MmaPlan& p, std::vector<uint8_t>& out) {
+  const int es = p.tf32 ? 4 : 2, E = 16 / es;
+  const int n_kc = ci / p.kc;
+  const size_t part = size_t(p.kc) * p.n_tile * es;
+  out.assign(size_t(p.n_tiles) * n_kc * k * 2 * part, 0);
+  (void)rows;
+  for (int nt = 0; nt < p.n_tiles; ++nt)
+    for (int c = 0; c < n_kc; ++c)
+      for (int j = 0; j < k; ++j) {
+        uint8_t* unit = out.data() + ((size_t(nt) * n_kc + c) * k + j) * 2 * part;
+        for (int g = 0; g < p.kc / E; ++g)
+          for (int n = 0; n < p.n_tile; ++n)
+            for (int e = 0; e < E; ++e) {
+              const int cin = c * p.kc + g * E + e;
+              const float v = wsrc[(size_t(cin) * k + j) * rows_p + nt * p.n_tile + n];
+              const size_t pos = (size_t(g) * p.n_tile + n) * E + e;
+              if (p.tf32) {
+                const float hi = f32_to_tf32_rna(v), lo = v - hi;
+                memcpy(unit + pos * 4, &hi, 4);
+                memcpy(unit + part + pos * 4, &lo, 4);
+              } else {
+                const uint16_t hi = f32_to_bf16_rn(v);
+                const uint16_t lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
+                memcpy(unit + pos * 2, &hi, 2);
+                memcpy(unit + part + pos * 2, &lo, 2);
+              }
+            }
+      }
 }
 
 }  // namespace pb200

@@ -62,17 +62,17 @@ Engine::Engine(const std::string& onnx_path, int device) : device_(device) {
   for (auto& ev : ev_) CUDA_CHECK(cudaEventCreate(&ev));
   weights_.ensure(voice_.blob.size() * sizeof(float));
   CUDA_CHECK(cudaMemcpy(weights_.p, voice_.blob.data(), voice_.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
-  if (!voice_.blob16.empty()) {
-    weights16_.ensure(voice_.blob16.size() * 2);
-    CUDA_CHECK(cudaMemcpy(weights16_.p, voice_.blob16.data(), voice_.blob16.size() * 2, cudaMemcpyHostToDevice));
+  if (!voice_.blob_mma.empty()) {
+    weights_mma_.ensure(voice_.blob_mma.size());
+    CUDA_CHECK(cudaMemcpy(weights_mma_.p, voice_.blob_mma.data(), voice_.blob_mma.size(), cudaMemcpyHostToDevice));
   }
-  if (const char* e = std::getenv("PIPER_B200_MMA")) use_mma_ = std::atoi(e) != 0;
+  if (const char* e = std::getenv("PIPER_B200_MMA")) mma_mask_ = std::atoi(e);
 }
 
 Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
-  DeviceBuf* dbs[] = {&weights_, &weights16_, &ids_d_, &len_d_, &ylen_d_, &cum_d_, &logw_d_, &override_d_, &epsdp_d_, &epsoff_d_,
+  DeviceBuf* dbs[] = {&weights_, &weights_mma_, &ids_d_, &len_d_, &ylen_d_, &cum_d_, &logw_d_, &override_d_, &epsdp_d_, &epsoff_d_,
                       &off_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
                       &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_};
   for (auto* d : dbs) d->release();
@@ -92,12 +92,30 @@ ConvArgs Engine::conv_args(const ConvW& c, View x, const int* len, int len_scale
   a.len_scale = len_scale;
   a.ci = c.ci; a.rows = c.rows; a.rows_p = c.rows_p; a.k = c.k; a.dil = c.dil; a.pad = c.pad;
   a.up = c.up; a.up_pad = c.up_pad;
+  a.host_w = &c;
   return a;
 }
 
 void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
+  // route through the tensor cores when the layer has a split-precision copy and its family is enabled
+  const ConvW* w = a.host_w;
+  const int family = tag[0] == 'd' && tag[1] == 'e' ? 1 : tag[0] == 'f' ? 2 : tag[0] == 'e' ? 4 : 0;
+  const bool mma = w && w->mma >= 0 && (mma_mask_ & family);
+  MmaConvArgs m;
+  if (mma) {
+    m.x = a.x; m.y = a.y; m.y2 = a.y2; m.r = a.r;
+    m.w = weights_mma_.as<uint8_t>() + w->mma;
+    m.bias = a.bias; m.len = a.len; m.len_scale = a.len_scale;
+    m.ci = a.ci; m.rows = a.rows; m.k = a.k; m.dil = a.dil; m.pad = a.pad; m.q_extra = a.q_extra;
+    m.pre = a.pre; m.slope = a.slope; m.epi = a.epi; m.split = a.split; m.first = a.first;
+    m.up = a.up; m.up_pad = a.up_pad; m.mrf = a.mrf; m.mrf_n = a.mrf_n;
+  }
+  auto go = [&] {
+    if (mma) launch_conv_mma(m, w->plan, B_, max_len, stream_);
+    else launch_conv1d(a, B_, max_len, stream_);
+  };
   if (!profile_) {
-    launch_conv1d(a, B_, max_len, stream_);
+    go();
     return;
   }
   if (ev_used_ + 2 > ev_pool_.size()) {
@@ -107,6 +125,7 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   }
   ProfRec r;
   r.tag = tag;
+  r.mma = mma;
   r.e0 = ev_pool_[ev_used_++];
   r.e1 = ev_pool_[ev_used_++];
   // algorithmic work of this launch: fp32 in + out + weights once; elementwise ops free
@@ -114,40 +133,7 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   r.bytes = 4.0 * (lin * a.ci + lout * (a.epi == EPI_GATE ? co / 2 : co) + double(a.ci) * a.rows * a.k + a.rows);
   r.flops = 2.0 * lout * a.ci * co * a.k;
   CUDA_CHECK(cudaEventRecord(r.e0, stream_));
-  launch_conv1d(a, B_, max_len, stream_);
-  CUDA_CHECK(cudaEventRecord(r.e1, stream_));
-  recs_.push_back(r);
-}
-
-void Engine::rb_conv(const ConvW& w, ConvArgs& a, int max_len, double len_sum) {
-  const bool mma_ok = use_mma_ && w.mma >= 0 && (a.epi == EPI_BIAS || a.epi == EPI_RES || a.epi == EPI_MRF);
-  if (!mma_ok) {
-    conv("dec.rb", a, max_len, len_sum);
-    return;
-  }
-  MmaConvArgs m;
-  m.x = a.x; m.y = a.y; m.y2 = a.y2; m.r = a.r;
-  m.w = weights16_.as<uint16_t>() + w.mma;
-  m.bias = a.bias; m.len = a.len; m.len_scale = a.len_scale;
-  m.ci = a.ci; m.co = a.rows; m.k = a.k; m.dil = a.dil; m.pad = a.pad;
-  m.pre = a.pre; m.slope = a.slope; m.epi = a.epi; m.mrf = a.mrf; m.mrf_n = a.mrf_n;
-  if (!profile_) {
-    launch_conv_mma(m, B_, max_len, stream_);
-    return;
-  }
-  if (ev_used_ + 2 > ev_pool_.size()) {
-    const size_t old = ev_pool_.size();
-    ev_pool_.resize(old + 256);
-    for (size_t i = old; i < ev_pool_.size(); ++i) CUDA_CHECK(cudaEventCreate(&ev_pool_[i]));
-  }
-  ProfRec r;
-  r.tag = "dec.rb.mma";
-  r.e0 = ev_pool_[ev_used_++];
-  r.e1 = ev_pool_[ev_used_++];
-  r.bytes = 4.0 * (len_sum * a.ci + len_sum * a.rows + double(a.ci) * a.rows * a.k + a.rows);
-  r.flops = 2.0 * len_sum * a.ci * a.rows * a.k;
-  CUDA_CHECK(cudaEventRecord(r.e0, stream_));
-  launch_conv_mma(m, B_, max_len, stream_);
+  go();
   CUDA_CHECK(cudaEventRecord(r.e1, stream_));
   recs_.push_back(r);
 }
@@ -164,7 +150,7 @@ std::string Engine::profile_json() {
   for (const ProfRec& r : recs_) {
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
-    Agg& a = agg[r.tag];
+    Agg& a = agg[std::string(r.tag) + (r.mma ? ".mma" : "")];
     a.n++; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
   }
   std::string out = "{";
@@ -491,12 +477,12 @@ void Engine::run_generator() {
         if (s.resblock == 1) {
           ConvArgs a1 = conv_args(rb.c1[c], y, ylen, rate);
           a1.pre = PRE_LRELU; a1.slope = 0.1f; a1.y = P; a1.epi = EPI_BIAS;
-          rb_conv(rb.c1[c], a1, L, sum_F_ * rate);
+          conv("dec.rb", a1, L, sum_F_ * rate);
           ConvArgs a2 = conv_args(rb.c2[c], P, ylen, rate);
           a2.pre = PRE_LRELU; a2.slope = 0.1f; a2.r = y;
           if (last) { a2.epi = EPI_MRF; a2.y2 = S; a2.mrf = mrf; a2.mrf_n = nk; }
           else { a2.epi = EPI_RES; a2.y = Q; }
-          rb_conv(rb.c2[c], a2, L, sum_F_ * rate);
+          conv("dec.rb", a2, L, sum_F_ * rate);
           y = Q;
         } else {
           ConvArgs a1 = conv_args(rb.c1[c], y, ylen, rate);
@@ -504,7 +490,7 @@ void Engine::run_generator() {
           View dst = (c & 1) ? Q : P;
           if (last) { a1.epi = EPI_MRF; a1.y2 = S; a1.mrf = mrf; a1.mrf_n = nk; }
           else { a1.epi = EPI_RES; a1.y = dst; }
-          rb_conv(rb.c1[c], a1, L, sum_F_ * rate);
+          conv("dec.rb", a1, L, sum_F_ * rate);
           y = dst;
         }
       }

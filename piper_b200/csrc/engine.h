@@ -81,8 +81,8 @@ class Engine {
   // per-launch CUDA-event timing of the conv kernel family, aggregated by pipeline stage (bench.py roofline)
   void set_profile(bool on) { profile_ = on; }
   std::string profile_json();
-  void set_mma(bool on) { use_mma_ = on; }
-  bool mma() const { return use_mma_; }
+  void set_mma(int mask) { mma_mask_ = mask; }
+  int mma() const { return mma_mask_; }
   void set_debug(bool on) { debug_ = on; }
   const HostTap* tap(const std::string& name) const;
   void set_max_frames(int64_t f) { max_frames_ = f; }
@@ -97,9 +97,9 @@ class Engine {
   void ensure_front(int B, int Tmax);
   void ensure_back(int B, int Fmax);
   void collect_stage_times();
+  // every dense conv goes through here: tensor-core path when the layer has a split-precision copy and its
+  // family (1 = generator, 2 = flow, 4 = text encoder) is enabled, CUDA-core kernel otherwise
   void conv(const char* tag, ConvArgs& a, int max_len, double len_sum);
-  // resblock conv: tensor-core path when the layer has a bf16 split copy and the path is enabled
-  void rb_conv(const ConvW& w, ConvArgs& a, int max_len, double len_sum);
   void profile_begin();
   void save_tap(const std::string& name, View v, int C, const int* len_host, int scale);
 
@@ -112,8 +112,8 @@ class Engine {
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[8] = {};
-  DeviceBuf weights_, weights16_;
-  bool use_mma_ = true;
+  DeviceBuf weights_, weights_mma_;
+  int mma_mask_ = 7;   // generator bf16x3; flow + encoder tf32x3 with chained accumulators
 
   // request state
   int B_ = 0, Tmax_ = 0, Tp_ = 0, Fmax_ = 0, Fp_ = 0;
@@ -135,7 +135,7 @@ class Engine {
   DeviceBuf ga_, gp_, gq_, gs_, audio_d_, audio16_d_, peak_d_;
   PinnedBuf ids_pin_, misc_pin_, audio_pin_, audio16_pin_, eps_pin_;
 
-  struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; };
+  struct ProfRec { const char* tag; bool mma; cudaEvent_t e0, e1; double bytes, flops; };
   bool profile_ = false;
   std::vector<cudaEvent_t> ev_pool_;
   size_t ev_used_ = 0;

@@ -7,6 +7,8 @@
 // its own zero padding (parity is per utterance against the B = 1 reference).
 #pragma once
 #include <cuda_runtime.h>
+
+#include "voice.h"
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -48,29 +50,28 @@ struct ConvArgs {
   int up = 1, up_pad = 0;       // EPI_UPSAMPLE
   int mrf = 0, mrf_n = 1;       // EPI_MRF
   int cic = 16;                 // input-channel chunk staged in shared memory (set by the launcher)
+  const ConvW* host_w = nullptr;  // host-side only: the layer this launch came from (tensor-core plan lookup)
 };
 
 // max_len = max over the batch of (len[b]*len_scale + q_extra): sizes the grid.
 void launch_conv1d(ConvArgs a, int B, int max_len, cudaStream_t st);
 
-// ---- tensor-core (tcgen05, bf16x3 split precision) Conv1d for the generator's resblocks ------------------
+// ---- tensor-core (tcgen05) Conv1d / ConvTranspose1d with split precision (conv_mma.cu) ----------------------
 struct MmaConvArgs {
   View x, y, y2, r;
-  const uint16_t* w = nullptr;   // packed by pack_conv_mma
+  const uint8_t* w = nullptr;    // packed by pack_conv_mma
   const float* bias = nullptr;
   const int* len = nullptr;
   int len_scale = 1;
-  int ci = 0, co = 0, k = 1, dil = 1, pad = 0;
+  int ci = 0, rows = 0, k = 1, dil = 1, pad = 0, q_extra = 0;
   int pre = PRE_NONE;
   float slope = 0.f;
-  int epi = EPI_BIAS;            // EPI_BIAS | EPI_RES | EPI_MRF
-  int mrf = 0, mrf_n = 1;
-  int kc = 0, rows = 0, tmem_cols = 0;   // filled by the launcher
+  int epi = EPI_BIAS;
+  int split = 0, first = 0, up = 1, up_pad = 0, mrf = 0, mrf_n = 1;
+  int kc = 0, stage_rows = 0, n_tile = 0, acc_cols = 0, tmem_cols = 0, a_slots = 1, w_slots = 2;   // from the MmaPlan
+  int chains = 1, sep_corr = 0, mh_stride = 0;
 };
-bool mma_conv_supported(int ci, int co, int k, int dil);
-int mma_conv_chunk(int ci, int co, int k, int dil);
-void pack_conv_mma(const float* w /*[co][ci][k]*/, int co, int ci, int k, int kc, std::vector<uint16_t>& out);
-void launch_conv_mma(MmaConvArgs a, int B, int max_len, cudaStream_t st);
+void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);
 
 // ---- text encoder -----------------------------------------------------------------------------
 void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float scale, View x, const int* len, int B,

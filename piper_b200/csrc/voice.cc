@@ -196,18 +196,17 @@ struct Packer {
     return r;
   }
 
-  // split-precision bf16 copy for the tcgen05 path (resblock convs only)
-  void add_mma(const std::string& prefix, ConvW& c) {
-    const OnnxTensor& w = get(prefix + ".weight", 3);
-    const int co = int(w.dims[0]), ci = int(w.dims[1]), k = int(w.dims[2]);
-    if (!mma_conv_supported(ci, co, k, c.dil)) return;
-    std::vector<uint16_t> packed;
-    c.mma_kc = mma_conv_chunk(ci, co, k, c.dil);
-    pack_conv_mma(w.f32(), co, ci, k, c.mma_kc, packed);
-    const size_t off = (v.blob16.size() + 63) / 64 * 64;   // 128-byte aligned units
-    v.blob16.resize(off + packed.size(), 0);
-    std::memcpy(&v.blob16[off], packed.data(), packed.size() * 2);
+  // split-precision copy for the tcgen05 path, built from the already packed fp32 [ci][k][rows_p] layout
+  void add_mma(ConvW& c, bool tf32) {
+    MmaPlan p;
+    if (c.w < 0 || !mma_plan(c.ci, c.rows, c.k, c.dil, tf32, p)) return;
+    std::vector<uint8_t> packed;
+    pack_conv_mma(&v.blob[size_t(c.w)], c.ci, c.k, c.rows, c.rows_p, p, packed);
+    const size_t off = (v.blob_mma.size() + 127) / 128 * 128;
+    v.blob_mma.resize(off + packed.size(), 0);
+    std::memcpy(&v.blob_mma[off], packed.data(), packed.size());
     c.mma = int64_t(off);
+    c.plan = p;
   }
 
   LayerNormW ln(const std::string& prefix, int c_expected) {
@@ -413,12 +412,10 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
         if (c1.pad * 2 != c1.dil * (c1.k - 1)) fail("'" + r + "': resblock conv is not same-padded");
         rb.k = c1.k;
         dils.push_back(c1.dil);
-        P.add_mma(r + first + std::to_string(id), c1);
         rb.c1.push_back(c1);
         if (s.resblock == 1) {
           ConvW c2 = P.conv(r + ".convs2." + std::to_string(id), Packer::kPlain, ch, ch);
           if (c2.pad * 2 != c2.dil * (c2.k - 1)) fail("'" + r + "': resblock conv is not same-padded");
-          P.add_mma(r + ".convs2." + std::to_string(id), c2);
           rb.c2.push_back(c2);
         }
       }
@@ -440,6 +437,22 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
     if (a.pad * 2 != v.post_k - 1 || a.dil != 1) fail("dec.conv_post is not same-padded");
     v.post_w = P.put(pw);
   }
+  // ---- tensor-core copies: bf16x3 for the generator, tf32x3 where outputs feed exp()/ceil() (flow, encoder)
+  for (EncLayerW& e : v.enc) { P.add_mma(e.qkv, true); P.add_mma(e.o, true); P.add_mma(e.ffn1, true); P.add_mma(e.ffn2, true); }
+  P.add_mma(v.enc_proj, true);
+  for (CouplingW& cw : v.flow) {
+    P.add_mma(cw.pre, true);
+    P.add_mma(cw.post, true);
+    for (ConvW& c : cw.in_layers) P.add_mma(c, true);
+    for (ConvW& c : cw.res_skip) P.add_mma(c, true);
+  }
+  P.add_mma(v.dec_pre, false);
+  for (ConvW& u : v.ups) P.add_mma(u, false);
+  for (auto& stage : v.resblocks)
+    for (ResBlockW& rb : stage) {
+      for (ConvW& c : rb.c1) P.add_mma(c, false);
+      for (ConvW& c : rb.c2) P.add_mma(c, false);
+    }
   // pad the tail so 16-byte vector loads of the last rows never leave the allocation
   v.blob.resize((v.blob.size() + 63) / 64 * 64 + 64, 0.f);
 }

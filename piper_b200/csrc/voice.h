@@ -14,6 +14,15 @@
 
 namespace pb200 {
 
+// Tiling of one layer on the tensor-core path (conv_mma.cu)
+struct MmaPlan {
+  bool tf32 = false;
+  int mt = 0, kc = 0, stage_rows = 0, n_tile = 0, n_tiles = 0, acc_cols = 0, tmem_cols = 0, a_slots = 1, w_slots = 2;
+  int chains = 1, mh_stride = 0;   // K-chains accumulated separately; TMEM columns per row half
+  bool sep_corr = false;           // hi*lo / lo*hi terms in their own accumulator
+  size_t smem = 0;
+};
+
 // A Conv1d / ConvTranspose1d lowered to "rows x (Ci*K)" with weights stored [Ci][K][RowsP]
 // (row index fastest) so a CTA's row tile is one contiguous, 16B-aligned run per (ci, tap).
 struct ConvW {
@@ -21,9 +30,9 @@ struct ConvW {
   int ci = 0, rows = 0, rows_p = 0, k = 1, dil = 1, pad = 0;
   // ConvTranspose lowering: rows = Co * up, output t = q*up + (row % up) - up_pad
   int up = 1, up_pad = 0;
-  // tensor-core copy (bf16 hi/lo units, see conv_mma.cu): offset in uint16 units into blob16, -1 if none
+  // tensor-core copy (split-precision hi/lo units, see conv_mma.cu): byte offset into blob_mma, -1 if none
   int64_t mma = -1;
-  int mma_kc = 0;
+  MmaPlan plan;
 };
 
 struct LayerNormW {
@@ -74,7 +83,7 @@ struct VoiceSpec {
 struct PackedVoice {
   VoiceSpec spec;
   std::vector<float> blob;
-  std::vector<uint16_t> blob16;   // split-precision bf16 weights of the generator resblock convs
+  std::vector<uint8_t> blob_mma;  // split-precision (bf16x3 / tf32x3) weight units for the tensor-core path
   int64_t emb = -1;
   std::vector<EncLayerW> enc;
   ConvW enc_proj;
@@ -99,8 +108,8 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& out);
 std::string describe_voice(const PackedVoice& v);
 
 // defined in conv_mma.cu (declared here so the host-only loader can call them)
-bool mma_conv_supported(int ci, int co, int k, int dil);
-int mma_conv_chunk(int ci, int co, int k, int dil);
-void pack_conv_mma(const float* w, int co, int ci, int k, int kc, std::vector<uint16_t>& out);
+bool mma_plan(int ci, int rows, int k, int dil, bool tf32, MmaPlan& p);
+void pack_conv_mma(const float* wsrc /*[ci][k][rows_p]*/, int ci, int k, int rows, int rows_p, const MmaPlan& p,
+                   std::vector<uint8_t>& out);
 
 }  // namespace pb200

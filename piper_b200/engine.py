@@ -173,8 +173,8 @@ class Voice:
         check(self._lib.pb200_stage_times(self._h, ms))
         return list(ms)
 
-    def set_mma(self, on: bool):
-        check(self._lib.pb200_set_mma(self._h, 1 if on else 0))
+    def set_mma(self, mask: int):
+        check(self._lib.pb200_set_mma(self._h, int(mask)))
 
     def set_profile(self, on: bool):
         check(self._lib.pb200_set_profile(self._h, 1 if on else 0))
