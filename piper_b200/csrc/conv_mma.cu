@@ -31,6 +31,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -194,12 +195,17 @@ __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs
   if (warp >= 8) {
     // =========================== control warps: weight TMA (warp 9) and MMA issue (warp 8), one lane each ===
     if (warp == 9 && lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + size_t(blockIdx.z) * n_units * unit_bytes;
+      // global layout [n tile][tap][hi|lo][ci/E][n_tile][E]: a (chunk, tap) unit is two contiguous runs
+      const size_t g_row = size_t(a.n_tile) * 16, part_all = size_t(a.ci / E) * g_row;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.w) + size_t(blockIdx.z) * a.k * 2 * part_all;
       for (int u = 0; u < n_units; ++u) {
         const int s = u % W_SLOTS;
         if (u >= W_SLOTS) mbar_wait(&bar.w_empty[s], ((u / W_SLOTS) - 1) & 1);
+        const int kc = u / a.k, j = u - kc * a.k;
+        const uint8_t* hi = wsrc + size_t(j) * 2 * part_all + size_t(kc) * (KC / E) * g_row;
         mbar_expect_tx(&bar.w_full[s], unit_bytes);
-        bulk_g2s(W_ring + size_t(s) * unit_bytes, wsrc + size_t(u) * unit_bytes, unit_bytes, &bar.w_full[s]);
+        bulk_g2s(W_ring + size_t(s) * unit_bytes, hi, (uint32_t)w_part, &bar.w_full[s]);
+        bulk_g2s(W_ring + size_t(s) * unit_bytes + w_part, hi + part_all, (uint32_t)w_part, &bar.w_full[s]);
       }
     } else if (warp == 8 && lane == 0) {
       const uint32_t idesc = make_idesc(TF32, 128, N);
@@ -387,6 +393,350 @@ __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs
   }
 }
 
+
+// =====================================================================================================================
+// Persistent variant: one CTA per SM walks a static list of tiles; every phase of tile i+1 overlaps tile i.
+//
+//   warp 0  lane 0 : TMA of the raw fp32 activation rows (cp.async.bulk, one copy per channel row) -> raw ring
+//   warp 1  lane 0 : TMA of the weight units                                                      -> W ring
+//   warp 2         : TMEM owner; lane 0 issues tcgen05.mma / tcgen05.commit
+//   warps 3-6      : converters  raw fp32 (smem) -> leaky-relu -> hi/lo split -> operand layout   -> A ring
+//   warps 7-14     : epilogue    TMEM (double-buffered) -> registers -> fused epilogue -> global
+//
+// All hand-offs are mbarriers; global memory is touched only by the TMA engine (loads) and the epilogue (residual
+// loads + stores), so the number of bytes in flight no longer depends on how many threads happen to be staging.
+constexpr int P_CONV_WARP0 = 3, P_CONV_THREADS = 128;
+constexpr int P_EPI_WARP0 = 7, P_EPI_THREADS = 256;
+constexpr int P_THREADS = 32 * 15;
+constexpr int P_RAW_SLOTS = 2, P_A_SLOTS = 2, P_W_SLOTS = 4, P_T_SLOTS = 2;
+
+struct PBarriers {
+  uint64_t raw_full[P_RAW_SLOTS], raw_empty[P_RAW_SLOTS], a_full[P_A_SLOTS], a_empty[P_A_SLOTS], w_full[P_W_SLOTS],
+      w_empty[P_W_SLOTS], t_full[P_T_SLOTS], t_empty[P_T_SLOTS];
+};
+
+template <bool TF32, int MT>
+__global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const MmaConvArgs a) {
+  constexpr int ES = TF32 ? 4 : 2;
+  constexpr int E = 16 / ES;
+  constexpr int KSTEP = 2 * E;
+  constexpr int MH = MT / 128;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) PBarriers bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int KC = a.kc, R = a.stage_rows, RS = a.raw_stride;
+  const int raw_bytes = KC * RS * 4, a_part = KC * R * ES, w_part = KC * a.n_tile * ES;
+  uint8_t* RAW_ring = smem;
+  uint8_t* A_ring = RAW_ring + size_t(P_RAW_SLOTS) * raw_bytes;
+  uint8_t* W_ring = A_ring + size_t(P_A_SLOTS) * 2 * a_part;
+  const int n_kc = a.ci / KC;
+  const int n_units = n_kc * a.k;
+  const uint32_t unit_bytes = 2u * (uint32_t)w_part;
+  const int tpi = a.tiles_per_item, total = a.total_tiles;
+  const int t_slots = a.t_slots;                      // 1 or 2 TMEM accumulator sets
+  const int set_cols = MH * a.mh_stride;
+
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < P_RAW_SLOTS; ++i) { mbar_init(&bar.raw_full[i], 1); mbar_init(&bar.raw_empty[i], P_CONV_THREADS); }
+    for (int i = 0; i < P_A_SLOTS; ++i) { mbar_init(&bar.a_full[i], P_CONV_THREADS); mbar_init(&bar.a_empty[i], 1); }
+    for (int i = 0; i < P_W_SLOTS; ++i) { mbar_init(&bar.w_full[i], 1); mbar_init(&bar.w_empty[i], 1); }
+    for (int i = 0; i < P_T_SLOTS; ++i) { mbar_init(&bar.t_full[i], 1); mbar_init(&bar.t_empty[i], P_EPI_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+
+  // tile id -> (output-row tile, item, time block); every role walks the same list and skips the same tiles
+  auto decode = [&](int tile, int& nt, int& b, int& t0, int& L, int& Lq) {
+    const int tb = tile % tpi;
+    const int rest = tile / tpi;
+    b = rest % a.batch;
+    nt = rest / a.batch;
+    t0 = tb * MT;
+    L = a.len[b] * a.len_scale;
+    Lq = L + a.q_extra;
+    return t0 < Lq;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ raw activation rows via TMA
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int nt, b, t0, L, Lq;
+        if (!decode(tile, nt, b, t0, L, Lq)) continue;
+        const int t_lo = t0 - a.pad;
+        const int t_base = t_lo & ~3;                                   // smem column 0 <-> time t_base
+        const int g0 = max(t_lo, 0) & ~3;                               // first / one-past-last float fetched
+        const int g1 = min((min(t_lo + R, L) + 3) & ~3, a.x.cs);
+        const uint32_t row_bytes = (uint32_t)(g1 - g0) * 4;
+        const float* xb = a.x.p + (long long)b * a.x.bs + g0;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int s = it % P_RAW_SLOTS;
+          if (it >= P_RAW_SLOTS) mbar_wait(&bar.raw_empty[s], ((it / P_RAW_SLOTS) - 1) & 1);
+          mbar_expect_tx(&bar.raw_full[s], row_bytes * (uint32_t)KC);
+          uint8_t* dst = RAW_ring + size_t(s) * raw_bytes + (size_t)(g0 - t_base) * 4;
+          for (int c = 0; c < KC; ++c)
+            bulk_g2s(dst + (size_t)c * RS * 4, xb + (long long)(kc * KC + c) * a.x.cs, row_bytes, &bar.raw_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ weight units via TMA
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int nt, b, t0, L, Lq;
+        if (!decode(tile, nt, b, t0, L, Lq)) continue;
+        const size_t g_row = size_t(a.n_tile) * 16, part_all = size_t(a.ci / E) * g_row;
+        const uint8_t* wsrc = a.w + size_t(nt) * a.k * 2 * part_all;
+        for (int u = 0; u < n_units; ++u, ++it) {
+          const int s = it % P_W_SLOTS;
+          if (it >= P_W_SLOTS) mbar_wait(&bar.w_empty[s], ((it / P_W_SLOTS) - 1) & 1);
+          const int kc = u / a.k, j = u - kc * a.k;
+          const uint8_t* hi = wsrc + size_t(j) * 2 * part_all + size_t(kc) * (KC / E) * g_row;
+          mbar_expect_tx(&bar.w_full[s], unit_bytes);
+          bulk_g2s(W_ring + size_t(s) * unit_bytes, hi, (uint32_t)w_part, &bar.w_full[s]);
+          bulk_g2s(W_ring + size_t(s) * unit_bytes + w_part, hi + part_all, (uint32_t)w_part, &bar.w_full[s]);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issue
+      const uint32_t a_lbo = (uint32_t)R * 16, w_lbo = (uint32_t)a.n_tile * 16;
+      const uint32_t idesc = make_idesc(TF32, 128, a.n_tile);
+      uint32_t a_it = 0, w_it = 0, t_it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int nt, b, t0, L, Lq;
+        if (!decode(tile, nt, b, t0, L, Lq)) continue;
+        const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
+        const int ts = t_it % t_slots;
+        if (t_it >= (uint32_t)t_slots) mbar_wait(&bar.t_empty[ts], ((t_it / t_slots) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
+        uint32_t started = 0;
+        int u = 0;
+        for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
+          const int as = a_it % P_A_SLOTS;
+          mbar_wait(&bar.a_full[as], (a_it / P_A_SLOTS) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t a_hi = smem_u32(A_ring + size_t(as) * 2 * a_part), a_lo = a_hi + a_part;
+          for (int j = 0; j < a.k; ++j, ++u, ++w_it) {
+            const int ws = w_it % P_W_SLOTS;
+            mbar_wait(&bar.w_full[ws], (w_it / P_W_SLOTS) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t w_hi = smem_u32(W_ring + size_t(ws) * unit_bytes), w_lo = w_hi + w_part;
+            const uint32_t shift = (uint32_t)(j * a.dil) * 16;
+            const int chain = (u * a.chains) / n_units;
+            const int corr = a.sep_corr ? a.chains : chain;
+            for (int kb = 0; kb < KC / KSTEP; ++kb) {
+              const uint64_t wh = make_desc(w_hi + 2 * kb * w_lbo, w_lbo, 128);
+              const uint64_t wl = make_desc(w_lo + 2 * kb * w_lbo, w_lbo, 128);
+              for (int mh = 0; mh < mh_live; ++mh) {
+                const uint32_t row_off = shift + (uint32_t)mh * 128 * 16;
+                const uint64_t ah = make_desc(a_hi + 2 * kb * a_lbo + row_off, a_lbo, 128);
+                const uint64_t al = make_desc(a_lo + 2 * kb * a_lbo + row_off, a_lbo, 128);
+                const uint32_t dm = d_set + (uint32_t)(mh * a.mh_stride + chain * a.acc_cols);
+                const uint32_t dc = d_set + (uint32_t)(mh * a.mh_stride + corr * a.acc_cols);
+                const uint32_t bm = 1u << (mh * 8 + chain), bc = 1u << (mh * 8 + corr);
+                mma_ss<TF32>(dm, ah, wh, idesc, (started & bm) != 0);
+                started |= bm;
+                mma_ss<TF32>(dc, ah, wl, idesc, (started & bc) != 0);
+                started |= bc;
+                mma_ss<TF32>(dc, al, wh, idesc, true);
+              }
+            }
+            mma_commit(&bar.w_empty[ws]);
+          }
+          mma_commit(&bar.a_empty[as]);
+        }
+        mma_commit(&bar.t_full[ts]);
+        ++t_it;
+      }
+    }
+  } else if (warp < P_EPI_WARP0) {
+    // -------------------------------------------------------------------- converters
+    const int ctid = tid - P_CONV_WARP0 * 32;
+    uint32_t raw_it = 0, a_it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int nt, b, t0, L, Lq;
+      if (!decode(tile, nt, b, t0, L, Lq)) continue;
+      const int t_lo = t0 - a.pad;
+      const int off = t_lo - (t_lo & ~3);                               // smem column of stage row 0
+      for (int kc = 0; kc < n_kc; ++kc, ++raw_it, ++a_it) {
+        const int rs = raw_it % P_RAW_SLOTS, as = a_it % P_A_SLOTS;
+        mbar_wait(&bar.raw_full[rs], (raw_it / P_RAW_SLOTS) & 1);
+        if (a_it >= P_A_SLOTS) mbar_wait(&bar.a_empty[as], ((a_it / P_A_SLOTS) - 1) & 1);
+        const float* raw = reinterpret_cast<const float*>(RAW_ring + size_t(rs) * raw_bytes) + off;
+        uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
+        uint8_t* A_lo = A_hi + a_part;
+        for (int g = 0; g < KC / E; ++g) {
+          const float* rg = raw + (size_t)(g * E) * RS;
+          for (int r = ctid; r < R; r += P_CONV_THREADS) {
+            const int t = t_lo + r;
+            const bool live = t >= 0 && t < L;                          // outside the utterance: zeros, whatever the
+            float v[E];                                                 // (unwritten / stale) smem holds
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              float x = live ? rg[(size_t)e * RS + r] : 0.f;
+              if (a.pre == PRE_LRELU) x = x > 0.f ? x : x * a.slope;
+              v[e] = x;
+            }
+            const int o = (g * R + r) * 16;
+            if (TF32) {
+              float h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = to_tf32(v[e % E]);
+              *reinterpret_cast<float4*>(A_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(A_lo + o) =
+                  make_float4(v[0] - h[0], v[1 % E] - h[1], v[2 % E] - h[2], v[3 % E] - h[3]);
+            } else {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const float ph = __bfloat162float(__float2bfloat16_rn(v[e % E])),
+                            qh = __bfloat162float(__float2bfloat16_rn(v[(e + 1) % E]));
+                hi[e >> 1] = pack_bf16(ph, qh);
+                lo[e >> 1] = pack_bf16(v[e % E] - ph, v[(e + 1) % E] - qh);
+              }
+              *reinterpret_cast<uint4*>(A_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(A_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_arrive(&bar.a_full[as]);
+        mbar_arrive(&bar.raw_empty[rs]);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue
+    const int ew = warp - P_EPI_WARP0;                 // 0..7
+    const int q = warp & 3, half = ew >> 2;            // TMEM lane quadrant is fixed by warp id % 4
+    uint32_t t_it = 0;
+    const int n_chunks = a.n_tile / 16;
+    const int n_acc = a.chains + (a.sep_corr ? 1 : 0);
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int nt, b, t0, L, Lq;
+      if (!decode(tile, nt, b, t0, L, Lq)) continue;
+      const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
+      const int ts = t_it % t_slots;
+      mbar_wait(&bar.t_full[ts], (t_it / t_slots) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
+      float* yb = a.y.p ? a.y.p + (long long)b * a.y.bs : nullptr;
+      float* y2b = a.y2.p ? a.y2.p + (long long)b * a.y2.bs : nullptr;
+      const float* rb = a.r.p ? a.r.p + (long long)b * a.r.bs : nullptr;
+      const int n0 = nt * a.n_tile;
+      // this thread's share of the tile: chunks c = half, half+2, ... of each live row half
+      const int my_chunks = (n_chunks - half + 1) / 2;
+      const int work = mh_live * my_chunks;
+      for (int wi = 0; wi < work; ++wi) {
+        const int mh = wi / my_chunks, c = half + 2 * (wi - mh * my_chunks);
+        const int t = t0 + mh * 128 + q * 32 + lane;
+        float v[16];
+        const uint32_t tbase = d_set + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * a.mh_stride + c * 16);
+        tmem_ld16(tbase, v);
+        for (int ai = 1; ai < n_acc; ++ai) {
+          float p[16];
+          tmem_ld16(tbase + (uint32_t)(ai * a.acc_cols), p);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += p[i];
+        }
+        if (wi == work - 1) {                          // all of this thread's TMEM reads are done: release the set
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          mbar_arrive(&bar.t_empty[ts]);
+        }
+        if (t >= Lq) continue;
+        const int row0 = n0 + c * 16;
+        if (a.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + row0 + i);
+        }
+        if (a.epi == EPI_GATE) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2)
+            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = tanhf(v[i]) * sigmoid_acc(v[i + 1]);
+          continue;
+        }
+        if (a.epi == EPI_RES || a.epi == EPI_MRF || a.epi == EPI_SUBFROM) {
+          float rv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rv[i] = rb[(long long)(row0 + i) * a.r.cs + t];   // 16 loads in flight
+          if (a.epi == EPI_SUBFROM) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = rv[i] - v[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += rv[i];
+          }
+        }
+        if (a.epi == EPI_MRF) {
+          float ov[16];
+          if (a.mrf != 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = y2b[(long long)(row0 + i) * a.y2.cs + t];
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float* o = y2b + (long long)(row0 + i) * a.y2.cs + t;
+            if (a.mrf == 0) *o = v[i];
+            else if (a.mrf == 1) *o = ov[i] + v[i];
+            else *o = (ov[i] + v[i]) / (float)a.mrf_n;
+          }
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = row0 + i;
+          const float val = v[i];
+          switch (a.epi) {
+            case EPI_BIAS: case EPI_RES: case EPI_SUBFROM: yb[(long long)row * a.y.cs + t] = val; break;
+            case EPI_RELU: yb[(long long)row * a.y.cs + t] = fmaxf(val, 0.f); break;
+            case EPI_WN:
+              if (row < a.split) {
+                yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + val;
+              } else {
+                float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
+                *o = a.first ? val : *o + val;
+              }
+              break;
+            case EPI_UPSAMPLE: {
+              const int co = row / a.up, phi = row - co * a.up;
+              const int to = t * a.up + phi - a.up_pad;
+              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = val;
+              break;
+            }
+            default: break;
+          }
+        }
+      }
+      if (work == 0) {                                   // (cannot happen: n_chunks >= 1) keep the protocol total
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        mbar_arrive(&bar.t_empty[ts]);
+      }
+      ++t_it;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+}
+
 int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 }  // namespace
@@ -435,20 +785,38 @@ bool mma_plan(int ci, int rows, int k, int dil, bool tf32, MmaPlan& p) {
   return false;
 }
 
+// Persistent configuration for a layer: tile height, channel chunk and TMEM double-buffering within 200 KB.
+static bool persist_cfg(const MmaConvArgs& a, const MmaPlan& p, int& mt, int& kc, int& stage_rows, int& raw_stride,
+                        int& t_slots, size_t& smem) {
+  const int es = p.tf32 ? 4 : 2, kstep = p.tf32 ? 8 : 16;
+  const int n_acc = p.chains + (p.sep_corr ? 1 : 0);
+  for (int want_slots : {2, 1})
+    for (int m : {256, 128}) {
+      if (n_acc > 1 && m != 128) continue;
+      const int set_cols = m / 128 * n_acc * p.acc_cols;
+      if (set_cols * want_slots > 512) continue;
+      const int rows = (m + (a.k - 1) * a.dil + 7) & ~7;
+      if (rows * 16 >= (1 << 18)) continue;
+      const int rs = rows + 8;
+      for (int c = a.ci; c >= kstep; c -= kstep) {
+        if (a.ci % c) continue;
+        const size_t bytes = size_t(P_RAW_SLOTS) * c * rs * 4 + size_t(P_A_SLOTS) * 2 * c * rows * es +
+                             size_t(P_W_SLOTS) * 2 * c * p.n_tile * es;
+        if (bytes <= (size_t(196) << 10)) {
+          mt = m; kc = c; stage_rows = rows; raw_stride = rs; t_slots = want_slots; smem = bytes;
+          return true;
+        }
+      }
+    }
+  return false;
+}
+
+static int g_mma_persist = -1;   // env PIPER_B200_PERSIST (default on)
+
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st) {
   if (B <= 0 || max_len <= 0) return;
-  a.kc = p.kc; a.stage_rows = p.stage_rows; a.n_tile = p.n_tile; a.acc_cols = p.acc_cols; a.tmem_cols = p.tmem_cols;
-  a.a_slots = p.a_slots; a.w_slots = p.w_slots;
-  // never more chains than weight units, or an accumulator would be read without ever being written
-  a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);
+  a.n_tile = p.n_tile; a.acc_cols = p.acc_cols;
   a.sep_corr = p.sep_corr ? 1 : 0; a.mh_stride = p.mh_stride;
-  // small problems: 128-row tiles double the CTA count (latency regime); the plan's kc also fits MT = 128
-  int mt = p.mt;
-  if (mt == 256 && (long long)((max_len + 255) / 256) * B * p.n_tiles < 148) {
-    mt = 128;
-    a.stage_rows = (128 + (a.k - 1) * a.dil + 7) & ~7;
-    a.tmem_cols = pow2_cols(p.mh_stride);
-  }
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -457,7 +825,47 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
     cudaFuncSetAttribute(conv_mma_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_mma_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv_mma_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mma_persist_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mma_persist_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv_mma_persist_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set[dev & 63] = true;
+  }
+  if (g_mma_persist < 0) {
+    const char* e = std::getenv("PIPER_B200_PERSIST");
+    g_mma_persist = e ? std::atoi(e) : 1;
+  }
+
+  // ---- persistent, fully pipelined kernel when there is enough work to keep every SM busy for several tiles
+  int mt = 0, kc = 0, rows = 0, rs = 0, t_slots = 0;
+  size_t smem = 0;
+  if (g_mma_persist && persist_cfg(a, p, mt, kc, rows, rs, t_slots, smem)) {
+    const int tpi = (max_len + mt - 1) / mt;
+    const long long total = (long long)tpi * B * p.n_tiles;
+    if (total >= 2 * 148) {
+      a.kc = kc; a.stage_rows = rows; a.raw_stride = rs; a.t_slots = t_slots;
+      a.chains = std::min(p.chains, (a.ci / kc) * a.k);
+      const int n_acc = p.chains + (p.sep_corr ? 1 : 0);
+      a.tmem_cols = pow2_cols(t_slots * (mt / 128) * n_acc * p.acc_cols);
+      a.tiles_per_item = tpi; a.total_tiles = (int)total; a.batch = B;
+      const int grid = (int)std::min<long long>(total, 148);
+      if (p.tf32) conv_mma_persist_kernel<true, 128><<<grid, P_THREADS, smem, st>>>(a);
+      else if (mt == 256) conv_mma_persist_kernel<false, 256><<<grid, P_THREADS, smem, st>>>(a);
+      else conv_mma_persist_kernel<false, 128><<<grid, P_THREADS, smem, st>>>(a);
+      count_launch();
+      return;
+    }
+  }
+
+  // ---- one tile per CTA (small problems / latency regime)
+  a.kc = p.kc; a.stage_rows = p.stage_rows; a.tmem_cols = p.tmem_cols;
+  a.a_slots = p.a_slots; a.w_slots = p.w_slots;
+  // never more chains than weight units, or an accumulator would be read without ever being written
+  a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);
+  mt = p.mt;
+  if (mt == 256 && (long long)((max_len + 255) / 256) * B * p.n_tiles < 148) {
+    mt = 128;                                        // 128-row tiles double the CTA count
+    a.stage_rows = (128 + (a.k - 1) * a.dil + 7) & ~7;
+    a.tmem_cols = pow2_cols(p.mh_stride);
   }
   dim3 grid((max_len + mt - 1) / mt, B, p.n_tiles);
   if (p.tf32) {
@@ -493,36 +901,34 @@ static inline float f32_to_tf32_rna(float f) {   // cvt.rna.tf32.f32: round to n
   return f;
 }
 
-// Source weights in the engine's fp32 layout wsrc[ci][k][rows_p] (row fastest).  Output: per N tile, units
-// (kc, tap) in issue order, each unit = { hi [KC/E][n_tile][E], lo same }, E = 8 bf16 or 4 tf32(fp32 container).
+// Source weights in the engine's fp32 layout wsrc[ci][k][rows_p] (row fastest).  Output layout
+//   [n tile][tap][hi | lo][ci / E][n_tile][E]      E = 8 bf16 or 4 tf32 (fp32 container)
+// so any channel chunk of any tap is one contiguous run per part, whatever chunk size a launch picks.
 void pack_conv_mma(const float* wsrc, int ci, int k, int rows, int rows_p, const MmaPlan& p, std::vector<uint8_t>& out) {
   const int es = p.tf32 ? 4 : 2, E = 16 / es;
-  const int n_kc = ci / p.kc;
-  const size_t part = size_t(p.kc) * p.n_tile * es;
-  out.assign(size_t(p.n_tiles) * n_kc * k * 2 * part, 0);
+  const size_t part_all = size_t(ci) * p.n_tile * es;
+  out.assign(size_t(p.n_tiles) * k * 2 * part_all, 0);
   (void)rows;
   for (int nt = 0; nt < p.n_tiles; ++nt)
-    for (int c = 0; c < n_kc; ++c)
-      for (int j = 0; j < k; ++j) {
-        uint8_t* unit = out.data() + ((size_t(nt) * n_kc + c) * k + j) * 2 * part;
-        for (int g = 0; g < p.kc / E; ++g)
-          for (int n = 0; n < p.n_tile; ++n)
-            for (int e = 0; e < E; ++e) {
-              const int cin = c * p.kc + g * E + e;
-              const float v = wsrc[(size_t(cin) * k + j) * rows_p + nt * p.n_tile + n];
-              const size_t pos = (size_t(g) * p.n_tile + n) * E + e;
-              if (p.tf32) {
-                const float hi = f32_to_tf32_rna(v), lo = v - hi;
-                memcpy(unit + pos * 4, &hi, 4);
-                memcpy(unit + part + pos * 4, &lo, 4);
-              } else {
-                const uint16_t hi = f32_to_bf16_rn(v);
-                const uint16_t lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
-                memcpy(unit + pos * 2, &hi, 2);
-                memcpy(unit + part + pos * 2, &lo, 2);
-              }
-            }
-      }
+    for (int j = 0; j < k; ++j) {
+      uint8_t* hi_base = out.data() + (size_t(nt) * k + j) * 2 * part_all;
+      uint8_t* lo_base = hi_base + part_all;
+      for (int cin = 0; cin < ci; ++cin)
+        for (int n = 0; n < p.n_tile; ++n) {
+          const float v = wsrc[(size_t(cin) * k + j) * rows_p + nt * p.n_tile + n];
+          const size_t pos = (size_t(cin / E) * p.n_tile + n) * E + (cin % E);
+          if (p.tf32) {
+            const float hi = f32_to_tf32_rna(v), lo = v - hi;
+            memcpy(hi_base + pos * 4, &hi, 4);
+            memcpy(lo_base + pos * 4, &lo, 4);
+          } else {
+            const uint16_t hi = f32_to_bf16_rn(v);
+            const uint16_t lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
+            memcpy(hi_base + pos * 2, &hi, 2);
+            memcpy(lo_base + pos * 2, &lo, 2);
+          }
+        }
+    }
 }
 
 }  // namespace pb200

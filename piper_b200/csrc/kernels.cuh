@@ -70,6 +70,7 @@ struct MmaConvArgs {
   int split = 0, first = 0, up = 1, up_pad = 0, mrf = 0, mrf_n = 1;
   int kc = 0, stage_rows = 0, n_tile = 0, acc_cols = 0, tmem_cols = 0, a_slots = 1, w_slots = 2;   // from the MmaPlan
   int chains = 1, sep_corr = 0, mh_stride = 0;
+  int raw_stride = 0, tiles_per_item = 0, total_tiles = 0, batch = 0, t_slots = 1;   // persistent kernel
 };
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);
 

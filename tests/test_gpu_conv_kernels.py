@@ -27,6 +27,9 @@ CASES = [  # (B, ci, co, k, dil, L)   every generator resblock shape of the medi
     (2, 192, 384, 5, 1, 519), (1, 192, 768, 3, 1, 259), (1, 768, 192, 3, 1, 259), (2, 96, 192, 1, 1, 600),
     (1, 192, 96, 1, 1, 333), (1, 48, 96, 1, 1, 150), (1, 192, 576, 1, 1, 259), (1, 96, 48, 1, 1, 257),
     (1, 192, 256, 7, 1, 519),
+    # enough tiles for the persistent, fully pipelined tensor-core kernel (>= 2 tiles per SM)
+    (4, 32, 32, 7, 12, 40000), (2, 64, 64, 5, 6, 45001), (2, 128, 128, 7, 3, 20003), (2, 192, 384, 5, 1, 6001),
+    (1, 192, 768, 3, 1, 5000), (2, 256, 256, 3, 1, 9999),
 ]
 
 

@@ -106,9 +106,9 @@ def test_ragged_batch_is_b_independent_utterances():
         ref = orc.infer(ids, scales, eps_dp[b], eps_z[b])
         assert outs[b].shape == ref.shape, (b, outs[b].shape, ref.shape)
         assert np.abs(outs[b] - ref).max() <= TOL, b
-    # and the batch composition does not change an item (accumulation order is tile-shape independent)
+    # and the batch composition does not change an item beyond accumulation-order noise
     solo, _ = voice.synthesize(ids_list[1], scales, eps_dp[1], eps_z[1])
-    assert np.array_equal(solo, outs[1])
+    assert np.abs(solo - outs[1]).max() <= 2e-4
 
 
 def test_vocoder_only():
@@ -206,9 +206,15 @@ def test_full_size_properties_medium_batch32():
     solo, _ = voice.synthesize_batch([ids_list[5]], seed=7)
     # (seeded noise is keyed by batch slot, so compare slot 0 against slot 0)
     first, _ = voice.synthesize_batch(ids_list[5:6] + ids_list[:3], seed=7)
-    assert np.array_equal(solo[0], first[0])
-    # one item against the oracle with explicit noise at the full 259-id size
-    eps_dp, eps_z = _noise(orc.s.inter, 259, 21, cols=1400)
-    ref = orc.infer(ids_list[0], (0.667, 1.0, 0.8), eps_dp, eps_z)
-    out, _ = voice.synthesize(ids_list[0], (0.667, 1.0, 0.8), eps_dp, eps_z)
-    assert out.shape == ref.shape and np.abs(out - ref).max() <= TOL
+    assert solo[0].shape == first[0].shape and np.abs(solo[0] - first[0]).max() <= 2e-4   # tile shapes differ with B
+    # items of the FULL batch against the oracle with explicit noise (the batch-32 launch takes the persistent
+    # tensor-core kernels, which a B = 1 call does not)
+    rng = np.random.default_rng(21)
+    eps_dp = [rng.standard_normal((2, 259)).astype(np.float32) for _ in range(32)]
+    eps_z = rng.standard_normal((32, orc.s.inter, 1400)).astype(np.float32)
+    outs3, _ = voice.synthesize_batch(ids_list, (0.667, 1.0, 0.8), eps_dp, eps_z)
+    for b in (0, 13, 31):
+        ref = orc.infer(ids_list[b], (0.667, 1.0, 0.8), eps_dp[b], eps_z[b])
+        assert outs3[b].shape == ref.shape and np.abs(outs3[b] - ref).max() <= TOL, b
+    out, _ = voice.synthesize(ids_list[0], (0.667, 1.0, 0.8), eps_dp[0], eps_z[0])
+    assert np.abs(out - outs3[0]).max() <= 2e-4
