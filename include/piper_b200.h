@@ -120,6 +120,10 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
                        const float* bias, int32_t co, int32_t k, int32_t dil, float pre_slope, const float* resid,
                        float* y);
 
+/* Developer microbenchmark: issue `iters` tcgen05.mma (M=128, given N, bf16 or tf32, no-swizzle K-major smem operands)
+ * rotating over n_acc accumulators; cycles[0] = issue time, cycles[1] = until the last one retired. */
+int pb200_debug_mma_bench(int32_t N, int32_t tf32, int32_t n_acc, int32_t iters, int32_t shift, uint64_t* cycles);
+
 void pb200_release(pb200_voice* v, const void* audio);
 
 /* Test taps: when debug is on, intermediate tensors of the last call are kept on the host.

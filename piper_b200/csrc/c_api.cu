@@ -1,6 +1,8 @@
 // C ABI of the engine (declared in include/piper_b200.h).
 #include "../../include/piper_b200.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <exception>
@@ -243,6 +245,15 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy2D(y, size_t(L) * 4, dy, size_t(Lp) * 4, size_t(L) * 4, size_t(B) * co, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dy); cudaFree(dr); cudaFree(dw); cudaFree(db); cudaFree(dlen); cudaFree(dw16);
+  });
+}
+
+int pb200_debug_mma_bench(int32_t N, int32_t tf32, int32_t n_acc, int32_t iters, int32_t shift, uint64_t* cycles) {
+  return guarded([&] {
+    unsigned long long o[2] = {0, 0};
+    pb200::run_mma_bench(N, tf32, n_acc, iters, shift, o);
+    cycles[0] = o[0];
+    cycles[1] = o[1];
   });
 }
 

@@ -61,6 +61,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// The MMA issuer is a single thread: descriptor arithmetic per instruction must stay at a couple of integer ops or the
+// issue loop, not the tensor pipe, paces small-N layers.  hi word (SBO, version) is constant; the lo word is
+// (LBO >> 4) << 16 | (start >> 4), and advancing the start address is one 32-bit add.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo) {
+  constexpr uint32_t hi = (128u >> 4) | (1u << 14);     // SBO = 128 bytes, descriptor version 1
+  return ((uint64_t)hi << 32) | lo;
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (bits 4-5 = 1), A/B format at bits 7-9 / 10-12
 // (1 = BF16, 2 = TF32), both operands K-major, N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N) {
@@ -737,6 +748,90 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
   }
 }
 
+template <bool TF32, bool ACC>
+__device__ __forceinline__ void mma_ss_imm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  // accumulate flag as a compile-time predicate: no setp in the issue loop
+  if (TF32) {
+    if (ACC) asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+  } else {
+    if (ACC) asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+  }
+}
+
+// One lane of a converged warp (elect.sync).  The MMA / TMA issue loops are executed by the WHOLE warp with only the
+// instruction itself predicated on the elected lane: inside an `if (lane == 0)` region the compiler has to build the
+// 64-bit descriptors in vector registers and move them to the uniform register file (R2UR) for every UTCHMMA, which
+// measured at ~200 cycles per instruction; in warp-uniform code they live in uniform registers (tools/mma_bench.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}\n"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
+// (developer microbenchmark below; its findings are summarised in DESIGN.md)
+// ---- microbenchmark: cycles per tcgen05.mma (SS operands, no-swizzle K-major) for a given N, dependent vs rotating
+// accumulators.  Developer tool (tools/mma_bench.py); results are quoted in DESIGN.md.
+__global__ void __launch_bounds__(128) mma_bench_kernel(int N, int tf32, int n_acc, int iters, int a_rows_shift,
+                                                        unsigned long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) { mbar_init(&done, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_d = tmem_base_s;
+  if (warp == 0) {
+    // whole warp runs the loop; only the tcgen05 instructions are predicated on the elected lane
+    const int mode = a_rows_shift;
+    const int M = (mode & 256) ? 64 : 128;
+    const uint32_t layout = (uint32_t)((mode >> 4) & 7);
+    const uint32_t idesc = make_idesc(tf32 != 0, M, N);
+    const uint32_t a_lbo = layout ? 16 : 256 * 16, w_lbo = layout ? 16 : (uint32_t)N * 16;
+    const uint32_t a0 = desc_lo(smem_u32(smem), a_lbo), w0 = desc_lo(smem_u32(smem + 16 * 1024), w_lbo);
+    const uint64_t hi_extra = ((uint64_t)layout << 61) | (layout ? ((uint64_t)((1024u >> 4) - (128u >> 4)) << 32) : 0);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t d = tmem_d + (uint32_t)((i % n_acc) * N);
+      const uint64_t ad = desc_join(a0 + (uint32_t)((i * (mode & 3)) & 63)) + hi_extra, wd = desc_join(w0) + hi_extra;
+      const int reps = (mode & 512) ? 0 : (mode & 1024) ? 4 : 1;
+      if (elect_one()) {
+        for (int r = 0; r < reps; ++r) {
+          if (tf32) mma_ss_imm<true, true>(d, ad, wd, idesc);
+          else mma_ss_imm<false, true>(d, ad, wd, idesc);
+        }
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (elect_one()) mma_commit(&done);
+    __syncwarp();
+    mbar_wait(&done, 0);
+    const long long t2 = clock64();
+    if (tid == 0) {
+      out[0] = (unsigned long long)(t1 - t0);
+      out[1] = (unsigned long long)(t2 - t0);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(512u) : "memory");
+}
+
 int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 }  // namespace
@@ -745,13 +840,15 @@ int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <
 bool mma_plan(int ci, int rows, int k, int dil, bool tf32, MmaPlan& p) {
   const int es = tf32 ? 4 : 2, kstep = tf32 ? 8 : 16;
   if (ci % kstep != 0 || rows % 16 != 0 || rows < 16) return false;
-  // accumulators per row half: tf32x3 layers use 3 K-chains + 1 correction accumulator (see the MMA issuer)
-  p.chains = tf32 ? 3 : 1;
+  // accumulators per row half: tf32x3 layers use 2 K-chains + 1 correction accumulator (see the MMA issuer)
+  p.chains = tf32 ? 2 : 1;
   p.sep_corr = tf32;
   const int n_acc = p.chains + (p.sep_corr ? 1 : 0);
   // output-row tile: multiple of 16 dividing the rows evenly; <= 256 columns of TMEM per CTA for all its
   // accumulators when several are needed (two CTAs per SM), <= 256 rows otherwise
-  const int max_tile = n_acc > 1 ? 256 / n_acc : 256;
+  // multi-accumulator (tf32x3) layers: 128-row tiles when the reduction is long (the epilogue is a small share of the
+  // tile; 3 x 128 columns fill TMEM so it cannot be double-buffered), 64-row tiles with double-buffered TMEM otherwise
+  const int max_tile = n_acc > 1 ? ((ci * k >= 900 && rows >= 256) ? 128 : 64) : 256;
   int nt = 1;
   while (rows / nt > max_tile || rows % nt != 0 || (rows / nt) % 16 != 0) {
     if (++nt > 64) return false;
@@ -876,6 +973,16 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
     else conv_mma_kernel<false, 128><<<grid, MMA_THREADS, p.smem, st>>>(a);
   }
   count_launch();
+}
+
+void run_mma_bench(int N, int tf32, int n_acc, int iters, int shift, unsigned long long out[2]) {
+  unsigned long long* d = nullptr;
+  cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  mma_bench_kernel<<<1, 128, 48 * 1024>>>(N, tf32, n_acc, iters, shift, d);
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
 }
 
 // ---- host-side packing ---------------------------------------------------------------------------------------

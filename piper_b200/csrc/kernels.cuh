@@ -70,9 +70,11 @@ struct MmaConvArgs {
   int split = 0, first = 0, up = 1, up_pad = 0, mrf = 0, mrf_n = 1;
   int kc = 0, stage_rows = 0, n_tile = 0, acc_cols = 0, tmem_cols = 0, a_slots = 1, w_slots = 2;   // from the MmaPlan
   int chains = 1, sep_corr = 0, mh_stride = 0;
-  int raw_stride = 0, tiles_per_item = 0, total_tiles = 0, batch = 0, t_slots = 1;   // persistent kernel
+  int raw_stride = 0, tiles_per_item = 0, total_tiles = 0, batch = 0, t_slots = 1, tpu = 1;   // persistent kernel
+  unsigned long long* prof = nullptr;   // optional: per-role stall cycle counters (tools/conv_diag.py)
 };
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);
+void run_mma_bench(int N, int tf32, int n_acc, int iters, int shift, unsigned long long out[2]);
 
 // ---- text encoder -----------------------------------------------------------------------------
 void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float scale, View x, const int* len, int B,
