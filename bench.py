@@ -204,7 +204,11 @@ def run_engine(args):
     if use_dist:
         dist.barrier()
     path = voicegen.cached_voice(ARCH)
-    voice = engine.Voice(path, local)
+    if use_dist:
+        from piper_b200 import dist as pdist
+        voice = pdist.load_voice_broadcast(path, local, rank)     # weights: rank 0 uploads, NCCL broadcast to the rest
+    else:
+        voice = engine.Voice(path, local)
     ids_list = workload_ids(rank)
     hop = voice.hop
 
@@ -343,7 +347,25 @@ def run_engine(args):
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the driver wants exactly one JSON line there.
+    Point fd 1 at stderr for the duration of the run and return a file object on the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global print
+    _real_stdout = _claim_stdout()
+    _print = print
+
+    def print(*a, **k):     # noqa: A001 - every print in this file goes to the real stdout
+        k.setdefault("file", _real_stdout)
+        _print(*a, **k)
+        _real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

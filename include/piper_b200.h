@@ -62,6 +62,13 @@ typedef struct pb200_noise {
 
 /* Parse `onnx_path`, pack the weights and upload them to CUDA device `device`. */
 int pb200_voice_load(const char* onnx_path, int device, pb200_voice** out);
+/* Multi-GPU load: every rank parses the file (host only), rank 0 uploads, the other ranks pass
+ * PB200_LOAD_NO_UPLOAD and receive the two packed blobs (fp32 layout, split-precision tensor-core layout) by an
+ * NCCL broadcast over NVLink into the device buffers returned by pb200_voice_weight_buffers.  The hot path itself
+ * has no collective: utterances are independent. */
+#define PB200_LOAD_NO_UPLOAD 1
+int pb200_voice_load_ex(const char* onnx_path, int device, int32_t flags, pb200_voice** out);
+int pb200_voice_weight_buffers(pb200_voice* v, void** fp32, int64_t* fp32_bytes, void** mma, int64_t* mma_bytes);
 void pb200_voice_free(pb200_voice* v);
 int pb200_voice_get_info(const pb200_voice* v, pb200_voice_info* info);
 

@@ -29,6 +29,8 @@ class Noise(C.Structure):
 _p = C.POINTER
 SYMBOLS = {
     "pb200_voice_load": (C.c_int, [C.c_char_p, C.c_int, _p(C.c_void_p)]),
+    "pb200_voice_load_ex": (C.c_int, [C.c_char_p, C.c_int, C.c_int32, _p(C.c_void_p)]),
+    "pb200_voice_weight_buffers": (C.c_int, [C.c_void_p, _p(C.c_void_p), _p(C.c_int64), _p(C.c_void_p), _p(C.c_int64)]),
     "pb200_voice_free": (None, [C.c_void_p]),
     "pb200_voice_get_info": (C.c_int, [C.c_void_p, _p(VoiceInfo)]),
     "pb200_voice_describe": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64]),

@@ -13,7 +13,7 @@
 
 struct pb200_voice {
   pb200::Engine engine;
-  pb200_voice(const char* path, int device) : engine(path, device) {}
+  pb200_voice(const char* path, int device, bool upload = true) : engine(path, device, upload) {}
 };
 
 namespace {
@@ -50,6 +50,20 @@ int pb200_voice_load(const char* onnx_path, int device, pb200_voice** out) {
   return guarded([&] {
     if (!onnx_path || !out) throw std::runtime_error("pb200_voice_load: null argument");
     *out = new pb200_voice(onnx_path, device);
+  });
+}
+
+int pb200_voice_load_ex(const char* onnx_path, int device, int32_t flags, pb200_voice** out) {
+  return guarded([&] {
+    if (!onnx_path || !out) throw std::runtime_error("pb200_voice_load_ex: null argument");
+    *out = new pb200_voice(onnx_path, device, (flags & PB200_LOAD_NO_UPLOAD) == 0);
+  });
+}
+
+int pb200_voice_weight_buffers(pb200_voice* v, void** fp32, int64_t* fp32_bytes, void** mma, int64_t* mma_bytes) {
+  return guarded([&] {
+    if (!v || !fp32 || !fp32_bytes || !mma || !mma_bytes) throw std::runtime_error("pb200_voice_weight_buffers: null argument");
+    v->engine.weight_buffers(fp32, fp32_bytes, mma, mma_bytes);
   });
 }
 

@@ -44,7 +44,7 @@ void PinnedBuf::release() {
 
 static int round4(int v) { return (v + 3) & ~3; }
 
-Engine::Engine(const std::string& onnx_path, int device) : device_(device) {
+Engine::Engine(const std::string& onnx_path, int device, bool upload) : device_(device) {
   load_voice_file(onnx_path, voice_);
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -61,10 +61,12 @@ Engine::Engine(const std::string& onnx_path, int device) : device_(device) {
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   for (auto& ev : ev_) CUDA_CHECK(cudaEventCreate(&ev));
   weights_.ensure(voice_.blob.size() * sizeof(float));
-  CUDA_CHECK(cudaMemcpy(weights_.p, voice_.blob.data(), voice_.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (upload)
+    CUDA_CHECK(cudaMemcpy(weights_.p, voice_.blob.data(), voice_.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (!voice_.blob_mma.empty()) {
     weights_mma_.ensure(voice_.blob_mma.size());
-    CUDA_CHECK(cudaMemcpy(weights_mma_.p, voice_.blob_mma.data(), voice_.blob_mma.size(), cudaMemcpyHostToDevice));
+    if (upload)
+      CUDA_CHECK(cudaMemcpy(weights_mma_.p, voice_.blob_mma.data(), voice_.blob_mma.size(), cudaMemcpyHostToDevice));
   }
   if (const char* e = std::getenv("PIPER_B200_MMA")) mma_mask_ = std::atoi(e);
 }

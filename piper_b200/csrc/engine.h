@@ -47,7 +47,8 @@ struct HostTap {
 
 class Engine {
  public:
-  Engine(const std::string& onnx_path, int device);
+  // upload = false: allocate the HBM weight buffers but leave them unfilled (a peer broadcasts into them)
+  Engine(const std::string& onnx_path, int device, bool upload = true);
   ~Engine();
   Engine(const Engine&) = delete;
   Engine& operator=(const Engine&) = delete;
@@ -56,6 +57,11 @@ class Engine {
   const PackedVoice& voice() const { return voice_; }
   int device() const { return device_; }
   int64_t weight_bytes() const { return int64_t(voice_.blob.size()) * 4; }
+  // device pointers of the two weight blobs (fp32 layout, split-precision tensor-core layout) for load-time broadcast
+  void weight_buffers(void** fp32, int64_t* fp32_bytes, void** mma, int64_t* mma_bytes) const {
+    *fp32 = weights_.p; *fp32_bytes = int64_t(voice_.blob.size()) * 4;
+    *mma = weights_mma_.p; *mma_bytes = int64_t(voice_.blob_mma.size());
+  }
 
   // ---- whole pipeline, host buffers in / host buffer out (the reference-facing call)
   // ids_concat: int64 [sum lens]; returns pointer to pinned fp32 audio (valid until the next call),

@@ -38,10 +38,11 @@ def pack(onnx_path: str) -> np.ndarray:
 
 
 class Voice:
-    def __init__(self, onnx_path: str, device: int = 0):
+    def __init__(self, onnx_path: str, device: int = 0, upload: bool = True):
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        check(self._lib.pb200_voice_load(onnx_path.encode(), device, C.byref(self._h)))
+        check(self._lib.pb200_voice_load_ex(onnx_path.encode(), device, 0 if upload else 1, C.byref(self._h)))
+        self.device = device
         info = VoiceInfo()
         check(self._lib.pb200_voice_get_info(self._h, C.byref(info)))
         self.info = info
@@ -172,6 +173,13 @@ class Voice:
         ms = (C.c_float * 5)()
         check(self._lib.pb200_stage_times(self._h, ms))
         return list(ms)
+
+    def weight_buffers(self):
+        """[(device pointer, bytes)] of the fp32 blob and the tensor-core blob (for the load-time NCCL broadcast)."""
+        p0, p1 = C.c_void_p(), C.c_void_p()
+        n0, n1 = C.c_int64(0), C.c_int64(0)
+        check(self._lib.pb200_voice_weight_buffers(self._h, C.byref(p0), C.byref(n0), C.byref(p1), C.byref(n1)))
+        return [(p0.value, n0.value), (p1.value, n1.value)]
 
     def set_mma(self, mask: int):
         check(self._lib.pb200_set_mma(self._h, int(mask)))
