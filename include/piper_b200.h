@@ -114,8 +114,8 @@ int pb200_set_profile(pb200_voice* v, int32_t on);
 int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap);
 
 /* Select which layer families run on the tcgen05 tensor cores (split precision): bit 0 = generator (bf16x3),
- * bit 1 = flow (tf32x3), bit 2 = text encoder (tf32x3); cleared bits use the fp32 CUDA-core kernel.
- * Default 7.  The tensor core truncates (RZ) when adding into its fp32 accumulator; the tf32x3 layers therefore split
+ * bit 1 = flow (tf32x3), bit 2 = text encoder (tf32x3), bit 3 = duration predictor (tf32x3); cleared bits use the fp32
+ * CUDA-core kernel.  Default 15.  The tensor core truncates (RZ) when adding into its fp32 accumulator; the tf32x3 layers therefore split
  * K into 3 chains plus a separate accumulator for the correction terms and combine them in fp32 RN in the epilogue,
  * which restores fp32-grade accuracy on the ill-conditioned real test voice.
  * Env PIPER_B200_MMA=<mask> sets the default at load. */

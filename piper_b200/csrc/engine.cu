@@ -101,7 +101,7 @@ ConvArgs Engine::conv_args(const ConvW& c, View x, const int* len, int len_scale
 void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   // route through the tensor cores when the layer has a split-precision copy and its family is enabled
   const ConvW* w = a.host_w;
-  const int family = tag[0] == 'd' && tag[1] == 'e' ? 1 : tag[0] == 'f' ? 2 : tag[0] == 'e' ? 4 : 0;
+  const int family = tag[0] == 'd' && tag[1] == 'e' ? 1 : tag[0] == 'f' ? 2 : tag[0] == 'e' ? 4 : tag[0] == 'd' && tag[1] == 'p' ? 8 : 0;
   const bool mma = w && w->mma >= 0 && (mma_mask_ & family);
   MmaConvArgs m;
   if (mma) {

@@ -104,7 +104,7 @@ class Engine {
   void ensure_back(int B, int Fmax);
   void collect_stage_times();
   // every dense conv goes through here: tensor-core path when the layer has a split-precision copy and its
-  // family (1 = generator, 2 = flow, 4 = text encoder) is enabled, CUDA-core kernel otherwise
+  // family (1 = generator, 2 = flow, 4 = text encoder, 8 = duration predictor) is enabled, CUDA-core kernel otherwise
   void conv(const char* tag, ConvArgs& a, int max_len, double len_sum);
   void profile_begin();
   void save_tap(const std::string& name, View v, int C, const int* len_host, int scale);
@@ -119,7 +119,7 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[8] = {};
   DeviceBuf weights_, weights_mma_;
-  int mma_mask_ = 7;   // generator bf16x3; flow + encoder tf32x3 with chained accumulators
+  int mma_mask_ = 15;  // generator bf16x3; flow, encoder, duration predictor tf32x3 with chained accumulators
 
   // request state
   int B_ = 0, Tmax_ = 0, Tp_ = 0, Fmax_ = 0, Fp_ = 0;

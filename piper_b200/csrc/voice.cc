@@ -446,6 +446,12 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
     for (ConvW& c : cw.in_layers) P.add_mma(c, true);
     for (ConvW& c : cw.res_skip) P.add_mma(c, true);
   }
+  // duration predictor 1x1 convs (their output feeds exp()/ceil(): tf32x3)
+  P.add_mma(v.dp_pre, true);
+  P.add_mma(v.dp_proj, true);
+  for (DDSLayerW& l : v.dp_dds.layers) P.add_mma(l.pw, true);
+  for (ConvFlowW& cf : v.dp_flows)
+    for (DDSLayerW& l : cf.dds.layers) P.add_mma(l.pw, true);
   P.add_mma(v.dec_pre, false);
   for (ConvW& u : v.ups) P.add_mma(u, false);
   for (auto& stage : v.resblocks)
