@@ -421,6 +421,34 @@ constexpr int P_EPI_WARP0 = 7, P_EPI_THREADS = 256;
 constexpr int P_THREADS = 32 * 15;
 constexpr int P_RAW_SLOTS = 2, P_A_SLOTS = 2, P_W_SLOTS = 4, P_T_SLOTS = 2;
 
+// ConvTranspose pixel-shuffle store of one 16-row chunk: rows (co*UP + phase) are contiguous, so each thread owns UP
+// consecutive output samples per output channel -> vector stores, a warp writes 32*UP*4 contiguous bytes per channel.
+template <int UP>
+__device__ __forceinline__ void store_upsampled(const float (&v)[16], float* yb, int cs, int row0, int t, int up_pad, int Lout) {
+#pragma unroll
+  for (int i = 0; i < 16; i += UP) {
+    const int co = (row0 + i) / UP;
+    const int to = t * UP - up_pad;
+    float* dst = yb + (long long)co * cs + to;
+    if (to >= 0 && to + UP <= Lout) {
+      if (UP % 4 == 0 && (to & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < UP; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[i + j], v[i + j + 1], v[i + j + 2], v[i + j + 3]);
+      } else if (UP % 2 == 0 && (to & 1) == 0) {
+#pragma unroll
+        for (int j = 0; j < UP; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[i + j], v[i + j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < UP; ++j) dst[j] = v[i + j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < UP; ++j)
+        if (to + j >= 0 && to + j < Lout) dst[j] = v[i + j];
+    }
+  }
+}
+
 struct PBarriers {
   uint64_t raw_full[P_RAW_SLOTS], raw_empty[P_RAW_SLOTS], a_full[P_A_SLOTS], a_empty[P_A_SLOTS], w_full[P_W_SLOTS],
       w_empty[P_W_SLOTS], t_full[P_T_SLOTS], t_empty[P_T_SLOTS];
@@ -692,6 +720,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += rv[i];
           }
+        }
+        if (a.epi == EPI_UPSAMPLE && (a.up == 8 || a.up == 4 || a.up == 2)) {
+          if (a.up == 8) store_upsampled<8>(v, yb, a.y.cs, row0, t, a.up_pad, L * 8);
+          else if (a.up == 4) store_upsampled<4>(v, yb, a.y.cs, row0, t, a.up_pad, L * 4);
+          else store_upsampled<2>(v, yb, a.y.cs, row0, t, a.up_pad, L * 2);
+          continue;
         }
         if (a.epi == EPI_MRF) {
           float ov[16];

@@ -16,27 +16,33 @@ constexpr int POST_MAXK = 15;
 __global__ void __launch_bounds__(256) conv_post_kernel(View x, const float* __restrict__ w, int C, int k, float slope,
                                                         float* __restrict__ out, const long long* __restrict__ out_off,
                                                         const int* __restrict__ len, int len_scale) {
-  extern __shared__ float sm[];   // weights [C][k]
+  extern __shared__ float sm[];   // weights [C][k] | activated input tile [C][POST_TT + k - 1]
   const int b = blockIdx.z;
   const int L = len[b] * len_scale;
   const int t0 = blockIdx.x * POST_TT;
   if (t0 >= L) return;
-  for (int i = threadIdx.x; i < C * k; i += 256) sm[i] = w[i];
+  const int half = (k - 1) / 2;
+  const int span = POST_TT + k - 1;
+  float* ws = sm;
+  float* xs = sm + C * k;
+  for (int i = threadIdx.x; i < C * k; i += 256) ws[i] = w[i];
+  const float* xb = x.p + (long long)b * x.bs;
+  for (int c = 0; c < C; ++c) {                       // coalesced rows, leaky-relu applied once per element
+    const float* xr = xb + (long long)c * x.cs;
+    for (int u = threadIdx.x; u < span; u += 256) {
+      const int tt = t0 - half + u;
+      float v = (tt >= 0 && tt < L) ? __ldg(xr + tt) : 0.f;
+      xs[c * span + u] = v > 0.f ? v : v * slope;
+    }
+  }
   __syncthreads();
   const int t = t0 + threadIdx.x;
   if (t >= L) return;
-  const int half = (k - 1) / 2;
-  const float* xb = x.p + (long long)b * x.bs;
   float acc = 0.f;
   for (int c = 0; c < C; ++c) {
-    const float* xr = xb + (long long)c * x.cs;
-    const float* wr = sm + c * k;
-    for (int j = 0; j < k; ++j) {
-      const int tt = t + j - half;
-      float v = (tt >= 0 && tt < L) ? __ldg(xr + tt) : 0.f;
-      v = v > 0.f ? v : v * slope;
-      acc = fmaf(wr[j], v, acc);
-    }
+    const float* xr = xs + c * span + threadIdx.x;
+    const float* wr = ws + c * k;
+    for (int j = 0; j < k; ++j) acc = fmaf(wr[j], xr[j], acc);
   }
   out[out_off[b] + t] = tanhf(acc);
 }
@@ -77,7 +83,16 @@ void launch_conv_post(View x, const float* w, int C, int k, float slope, float* 
   if (B <= 0 || max_len <= 0) return;
   if (k > POST_MAXK) throw std::runtime_error("conv_post: kernel too wide");
   dim3 grid((max_len + POST_TT - 1) / POST_TT, 1, B);
-  conv_post_kernel<<<grid, 256, size_t(C) * k * sizeof(float), st>>>(x, w, C, k, slope, out, out_off, len, len_scale);
+  const size_t smem = (size_t(C) * k + size_t(C) * (POST_TT + k - 1)) * sizeof(float);
+  if (smem > 96 * 1024) throw std::runtime_error("conv_post: too many channels");
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaFuncSetAttribute(conv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set[dev & 63] = true;
+  }
+  conv_post_kernel<<<grid, 256, smem, st>>>(x, w, C, k, slope, out, out_off, len, len_scale);
   count_launch();
 }
 
