@@ -26,9 +26,12 @@ __global__ void embed_kernel(const int* __restrict__ ids, int ids_pitch, const f
   for (int c = blockIdx.y; c < H; c += gridDim.y) xb[(long long)c * x.cs + t] = __ldg(e + c) * scale;
 }
 
-// One warp per query row, 8 query rows per CTA, keys/values streamed through shared memory in
-// chunks of 32 with an online softmax.  dk <= 128 (lane owns channels d = lane + 32*r, r < 4).
-constexpr int ATT_Q = 8;
+// ATT_QPW query rows per warp, 8 warps per CTA.  Keys/values stream through shared memory in chunks of 32 with an
+// online softmax; within a chunk every K element read feeds ATT_QPW score FMAs and every V element read feeds ATT_QPW
+// accumulator FMAs (the probability of key jj for query qq comes by warp shuffle).  The banded relative-value term
+// touches at most 2*window+1 keys per query and is added separately.  dk <= 128 (lane owns d = lane + 32*r, r < 4).
+constexpr int ATT_QPW = 2;
+constexpr int ATT_Q = 8 * ATT_QPW;
 constexpr int ATT_MAXR = 4;
 
 __global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, const float* __restrict__ rel_k,
@@ -53,24 +56,34 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, 
   const float* vg = base + (long long)(2 * H + h * dk) * qkv.cs;
 
   for (int idx = threadIdx.x; idx < ATT_Q * dk; idx += 256) {
-    const int qi = idx / dk, d = idx - qi * dk;
+    const int d = idx / ATT_Q, qi = idx - d * ATT_Q;          // consecutive threads -> consecutive query positions
     const int i = i0 + qi;
-    Qs[idx] = i < T ? qg[(long long)d * qkv.cs + i] / sqrtf((float)dk) : 0.f;   // query / sqrt(k_channels), attentions.py:232
+    Qs[qi * dk + d] = i < T ? qg[(long long)d * qkv.cs + i] / sqrtf((float)dk) : 0.f;   // query / sqrt(k_channels), attentions.py:232
   }
   for (int idx = threadIdx.x; idx < nrel * dk; idx += 256) Ev[idx] = rel_v[idx];
   __syncthreads();
   // relative-key logits: Rl[qi][r] = q_i . emb_rel_k[r]
-  for (int r = 0; r < nrel; ++r) {
-    float p = 0.f;
-    for (int d = lane; d < dk; d += 32) p += Qs[warp * dk + d] * __ldg(rel_k + r * dk + d);
-    for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    if (lane == 0) Rl[warp * nrel + r] = p;
+#pragma unroll
+  for (int qq = 0; qq < ATT_QPW; ++qq) {
+    const int qi = warp * ATT_QPW + qq;
+    for (int r = 0; r < nrel; ++r) {
+      float p = 0.f;
+      for (int d = lane; d < dk; d += 32) p += Qs[qi * dk + d] * __ldg(rel_k + r * dk + d);
+      for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (lane == 0) Rl[qi * nrel + r] = p;
+    }
   }
   __syncwarp();
 
-  const int i = i0 + warp;
-  float m_run = -INFINITY, l_run = 0.f;
-  float acc[ATT_MAXR] = {0.f, 0.f, 0.f, 0.f};
+  float m_run[ATT_QPW], l_run[ATT_QPW], acc[ATT_QPW][ATT_MAXR];
+#pragma unroll
+  for (int qq = 0; qq < ATT_QPW; ++qq) {
+    m_run[qq] = -INFINITY;
+    l_run[qq] = 0.f;
+#pragma unroll
+    for (int r = 0; r < ATT_MAXR; ++r) acc[qq][r] = 0.f;
+  }
+  const int iq0 = i0 + warp * ATT_QPW;            // first query row of this warp
 
   for (int j0 = 0; j0 < T; j0 += 32) {
     __syncthreads();  // previous chunk fully consumed
@@ -86,48 +99,73 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, 
       Vs[d * 33 + jj] = vv;
     }
     __syncthreads();
-    if (i < T) {
-      const int j = j0 + lane;
-      float s = 0.f;
-      const float* q = Qs + warp * dk;
-      for (int d = 0; d < dk; ++d) s = fmaf(q[d], Ks[d * 33 + lane], s);
-      const int rel = j - i + window;
-      if (rel >= 0 && rel < nrel) s += Rl[warp * nrel + rel];
-      if (j >= T) s = -INFINITY;   // keys past the utterance: masked_fill(-1e4) -> exp underflows to exactly 0
-      float cmax = s;
-      for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-      const float m_new = fmaxf(m_run, cmax);
-      const float corr = expf(m_run - m_new);
-      const float p = expf(s - m_new);
-      float psum = p;
-      for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-      l_run = l_run * corr + psum;
+    if (iq0 >= T) continue;                        // warp-uniform; the barriers above are still reached
+    const int j = j0 + lane;
+    const int jn = min(32, T - j0);
+    float s[ATT_QPW];
 #pragma unroll
-      for (int r = 0; r < ATT_MAXR; ++r) acc[r] *= corr;
-      const int jn = min(32, T - j0);
-      for (int jj = 0; jj < jn; ++jj) {
-        const float pj = __shfl_sync(0xffffffffu, p, jj);
-        const int relj = j0 + jj - i + window;
-        const bool band = relj >= 0 && relj < nrel;
+    for (int qq = 0; qq < ATT_QPW; ++qq) s[qq] = 0.f;
+    for (int d = 0; d < dk; ++d) {
+      const float kd = Ks[d * 33 + lane];
+#pragma unroll
+      for (int qq = 0; qq < ATT_QPW; ++qq) s[qq] = fmaf(Qs[(warp * ATT_QPW + qq) * dk + d], kd, s[qq]);
+    }
+    float p[ATT_QPW];
+#pragma unroll
+    for (int qq = 0; qq < ATT_QPW; ++qq) {
+      const int i = iq0 + qq;
+      float sc = s[qq];
+      const int rel = j - i + window;
+      if (rel >= 0 && rel < nrel) sc += Rl[(warp * ATT_QPW + qq) * nrel + rel];
+      if (j >= T || i >= T) sc = -INFINITY;   // keys past the utterance: masked_fill(-1e4) -> exp underflows to exactly 0
+      float cmax = sc;
+      for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      const float m_new = fmaxf(m_run[qq], cmax);
+      const float corr = (m_new == -INFINITY) ? 1.f : expf(m_run[qq] - m_new);
+      p[qq] = (m_new == -INFINITY) ? 0.f : expf(sc - m_new);
+      float psum = p[qq];
+      for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      l_run[qq] = l_run[qq] * corr + psum;
+#pragma unroll
+      for (int r = 0; r < ATT_MAXR; ++r) acc[qq][r] *= corr;
+      m_run[qq] = m_new;
+      // banded relative values: keys j with |j - i| <= window inside this chunk
+      const int jlo = max(j0, i - window), jhi = min(j0 + jn - 1, i + window);
+      for (int jb = jlo; jb <= jhi; ++jb) {
+        const float pj = __shfl_sync(0xffffffffu, p[qq], jb - j0);
+        const int relj = jb - i + window;
 #pragma unroll
         for (int r = 0; r < ATT_MAXR; ++r) {
           const int d = lane + 32 * r;
-          if (d < dk) {
-            float v = Vs[d * 33 + jj];
-            if (band) v += Ev[relj * dk + d];
-            acc[r] = fmaf(pj, v, acc[r]);
-          }
+          if (d < dk) acc[qq][r] = fmaf(pj, Ev[relj * dk + d], acc[qq][r]);
         }
       }
-      m_run = m_new;
+    }
+    // P.V: one V read per (key, channel) shared by the warp's queries
+    for (int jj = 0; jj < jn; ++jj) {
+      float pj[ATT_QPW];
+#pragma unroll
+      for (int qq = 0; qq < ATT_QPW; ++qq) pj[qq] = __shfl_sync(0xffffffffu, p[qq], jj);
+#pragma unroll
+      for (int r = 0; r < ATT_MAXR; ++r) {
+        const int d = lane + 32 * r;
+        if (d < dk) {
+          const float v = Vs[d * 33 + jj];
+#pragma unroll
+          for (int qq = 0; qq < ATT_QPW; ++qq) acc[qq][r] = fmaf(pj[qq], v, acc[qq][r]);
+        }
+      }
     }
   }
-  if (i < T) {
-    float* ob = out.p + (long long)b * out.bs + (long long)(h * dk) * out.cs;
+  float* ob = out.p + (long long)b * out.bs + (long long)(h * dk) * out.cs;
+#pragma unroll
+  for (int qq = 0; qq < ATT_QPW; ++qq) {
+    const int i = iq0 + qq;
+    if (i >= T) continue;
 #pragma unroll
     for (int r = 0; r < ATT_MAXR; ++r) {
       const int d = lane + 32 * r;
-      if (d < dk) ob[(long long)d * out.cs + i] = acc[r] / l_run;
+      if (d < dk) ob[(long long)d * out.cs + i] = acc[qq][r] / l_run[qq];
     }
   }
 }
