@@ -134,7 +134,7 @@ def time_oracle(orc, ids_list, budget_s: float, min_runs: int = 3):
     one(ids_list[0])
     samples, secs, n = 0, 0.0, 0
     t_start = time.perf_counter()
-    while n < min_runs or (time.perf_counter() - t_start < budget_s and n < len(ids_list)):
+    while n < min_runs or (time.perf_counter() - t_start < budget_s and n < 4 * len(ids_list)):
         dt, ns = one(ids_list[n % len(ids_list)])
         secs += dt; samples += ns; n += 1
     return samples / secs, n, secs
@@ -287,8 +287,13 @@ def run_engine(args):
     d = agg[dom]
     gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9
     tflops = d["flops"] / (d["ms"] * 1e-3) / 1e12
-    roofline = {"kernel": f"conv1d_kernel ({dom})", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):           # dram__bytes_read+write per launch from the committed `ncu --set full` capture
+        traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+    kname = "conv_mma_persist_kernel (tcgen05)" if dom.endswith(".mma") else "conv1d_kernel (fp32 FFMA)"
+    roofline = {"kernel": f"{kname}: {dom}", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": traffic,
                 "peak_source": peaks["source"], "avg_launch_us": d["ms"] / d["launches"] * 1e3,
                 "launches_per_step": d["launches"] / prof_steps,
                 "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
@@ -316,7 +321,7 @@ def run_engine(args):
         spec, w, attrs = load_voice(path)
         orc = Oracle(spec, w, attrs)
         pick_threads(orc, ids_list[0])
-        v, n, secs = time_oracle(orc, ids_list, budget_s=15.0)
+        v, n, secs = time_oracle(orc, ids_list, budget_s=12.0)
         cpu_baseline = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                         "host_cpus": os.cpu_count(),
                         "sample": f"{n} utterances of the batch (259 ids each), B=1 calls, {secs:.1f} s of CPU work, best of 4..ncpu threads; "
