@@ -100,6 +100,16 @@ int pb200_synthesize_int16(pb200_voice* v, const int64_t* ids_concat, const int6
 int pb200_vocode(pb200_voice* v, const float* z, int32_t B, int64_t frames, const float** audio,
                  double* infer_seconds);
 
+/* The reference's streaming split (src/python/piper_train/export_onnx_streaming.py:19-69):
+ *   pb200_encode = VitsEncoder.forward  (text encoder, duration predictor, length regulator, prior sample)
+ *                  ids -> z_p fp32 [inter][frames] (engine-owned host memory, valid until the next call)
+ *   pb200_decode = VitsDecoder.forward  (flow reverse + generator) on z_p [B][inter][frames] -> audio [B][frames*hop]
+ * The chunk / halo scheduling of infer_onnx_streaming.py:76-108 lives on the host (piper_b200/streaming.py). */
+int pb200_encode(pb200_voice* v, const int64_t* ids, int64_t n_ids, const float scales[3], const pb200_noise* noise,
+                 const float** z_p, int64_t* frames, double* infer_seconds);
+int pb200_decode(pb200_voice* v, const float* z_p, int32_t B, int64_t frames, const float** audio,
+                 double* infer_seconds);
+
 /* Device-resident timing: stage inputs in HBM once, then run the kernels (no host<->device traffic except
  * the B-int output-length read-back the graph's data-dependent shape requires). */
 int pb200_stage(pb200_voice* v, const int64_t* ids_concat, const int64_t* lens, int32_t B, const float scales[3],

@@ -79,6 +79,29 @@ def main():
         path = voicegen.cached_voice(arch)
         mint(f"synthetic_{arch}", path, f"synthetic:{arch}:1234", voicegen.benchmark_ids(n_ph, seed=99),
              (0.667, 1.0, 0.8), 4321)
+    mint_streaming()
+
+
+def mint_streaming():
+    """Chunked streaming golden: the reference's own chunk loop (infer_onnx_streaming.py:76-108) driving the
+    reference PyTorch decoder on the reference encoder's z_p."""
+    from oracle.vits_oracle import Oracle
+    path = voicegen.cached_voice("tiny")
+    spec, w, attrs = load_voice(path)
+    net = ref_bridge.build_reference_model(spec, w)
+    ids = voicegen.benchmark_ids(40, seed=2)
+    rng = np.random.default_rng(3)
+    eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
+    eps_z = rng.standard_normal((spec.inter, 6 * len(ids))).astype(np.float32)
+    r = ref_bridge.reference_infer(net, ids, (0.667, 1.0, 0.8), eps_dp, eps_z)
+    pieces = ref_bridge.reference_stream_chunks(net, r["z_p"], r["y_len"])
+    np.savez_compressed(os.path.join(OUT, "stream_tiny.npz"), ids=ids, scales=np.asarray((0.667, 1.0, 0.8), np.float32),
+                        eps_dp=eps_dp, eps_z=eps_z[:, : r["y_len"]].copy(), z_p=r["z_p"].astype(np.float32),
+                        piece_lens=np.asarray([len(p) for p in pieces], np.int64),
+                        audio=np.concatenate(pieces).astype(np.float32), chunk_size=np.int64(45),
+                        chunk_padding=np.int64(10), voice=np.array("synthetic:tiny:1234"),
+                        weights_sha256=np.array(weights_digest(w)))
+    print("stream_tiny:", r["y_len"], "frames ->", [len(p) for p in pieces])
 
 
 if __name__ == "__main__":

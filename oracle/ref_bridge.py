@@ -105,3 +105,36 @@ def reference_infer(net, ids, scales, eps_dp=None, eps_z=None):
     w_ceil = attn[0, 0].sum(0)
     return dict(o=o[0, 0].numpy(), w_ceil=w_ceil.numpy(), z=z[0].numpy(), z_p=z_p[0].numpy(),
                 y_len=int(y_mask.sum().item()))
+
+
+def reference_stream_chunks(net, z_p, y_len, chunk_size=45, chunk_padding=10):
+    """Run the reference's OWN chunking loop (`SpeechStreamer.chunk`,
+    /root/reference/src/python/piper_train/infer_onnx_streaming.py:76-108) with its decoder call replaced by the
+    reference PyTorch decoder (flow reverse + generator = VitsDecoder, export_onnx_streaming.py:61-69).
+    onnxruntime is absent, so the module is imported with a stub in its place; only `chunk` is exercised."""
+    import importlib
+    if REF_PY not in sys.path:
+        sys.path.insert(0, REF_PY)
+    for name in ("onnxruntime",):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    _import_models()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("piper_train.infer_onnx_streaming")
+    streamer = mod.SpeechStreamer.__new__(mod.SpeechStreamer)
+    streamer.chunk_size, streamer.chunk_padding, streamer.sample_rate = chunk_size, chunk_padding, 22050
+
+    def decoder_infer(z, y_mask, g=None):
+        with torch.no_grad():
+            zt, mt = torch.from_numpy(np.ascontiguousarray(z)), torch.from_numpy(np.ascontiguousarray(y_mask))
+            zz = net.flow(zt, mt, g=None, reverse=True)
+            return net.dec(zz * mt).squeeze().numpy()
+
+    streamer.decoder_infer = decoder_infer
+    z = np.asarray(z_p, np.float32)[None]
+    y_mask = np.ones((1, 1, z.shape[2]), np.float32)
+    out = streamer.chunk([z, y_mask])
+    if isinstance(out, np.ndarray):          # "too short to stream": chunk() returns the audio itself
+        return [out]
+    return [np.asarray(a) for a in out]

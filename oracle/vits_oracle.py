@@ -232,9 +232,24 @@ class Oracle:
         x = self.conv(x, "dec.conv_post", pad=3)
         return torch.tanh(x)[0]
 
+    # ------------------------------------------------- streaming split (export_onnx_streaming.py:19-69)
+    @torch.no_grad()
+    def encode(self, ids, scales, eps_dp=None, eps_z=None):
+        """VitsEncoder.forward: everything before the flow -> z_p [inter, T'] (np.ndarray)."""
+        dump = {}
+        self.infer(ids, scales, eps_dp, eps_z, dump=dump, stop_before_flow=True)
+        return dump["z_p"].numpy()
+
+    @torch.no_grad()
+    def decode(self, z_p):
+        """VitsDecoder.forward: flow reverse + generator on z_p [inter, frames] -> waveform."""
+        z = self.flow_reverse(torch.as_tensor(np.asarray(z_p), dtype=torch.float32))
+        return self.generator(z).numpy()
+
     # ------------------------------------------------------------------ infer
     @torch.no_grad()
-    def infer(self, ids, scales, eps_dp=None, eps_z=None, w_ceil_override=None, dump: Optional[dict] = None):
+    def infer(self, ids, scales, eps_dp=None, eps_z=None, w_ceil_override=None, dump: Optional[dict] = None,
+              stop_before_flow: bool = False):
         """ids int64 [T]; scales = (noise_scale, length_scale, noise_w).
         eps_dp [2,T] / eps_z [inter, >=T'] default to zeros (deterministic graph).
         Returns fp32 waveform [T' * hop] (np.ndarray)."""
@@ -263,6 +278,9 @@ class Oracle:
             eps_z = torch.zeros(s.inter, y_len)
         eps_z = torch.as_tensor(np.asarray(eps_z), dtype=torch.float32)[:, :y_len]
         z_p = m_e + eps_z * torch.exp(logs_e) * noise_scale
+        if stop_before_flow:
+            dump.update(z_p=z_p, w_ceil=w_ceil)
+            return None
         z = self.flow_reverse(z_p)
         o = self.generator(z, dump)
         if dump is not None:

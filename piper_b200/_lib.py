@@ -42,6 +42,9 @@ SYMBOLS = {
     "pb200_synthesize_int16": (C.c_int, [C.c_void_p, _p(C.c_int64), _p(C.c_int64), C.c_int32, _p(C.c_float), _p(Noise),
                                          _p(_p(C.c_int16)), _p(C.c_int64), _p(C.c_double)]),
     "pb200_vocode": (C.c_int, [C.c_void_p, _p(C.c_float), C.c_int32, C.c_int64, _p(_p(C.c_float)), _p(C.c_double)]),
+    "pb200_encode": (C.c_int, [C.c_void_p, _p(C.c_int64), C.c_int64, _p(C.c_float), _p(Noise), _p(_p(C.c_float)),
+                               _p(C.c_int64), _p(C.c_double)]),
+    "pb200_decode": (C.c_int, [C.c_void_p, _p(C.c_float), C.c_int32, C.c_int64, _p(_p(C.c_float)), _p(C.c_double)]),
     "pb200_stage": (C.c_int, [C.c_void_p, _p(C.c_int64), _p(C.c_int64), C.c_int32, _p(C.c_float), _p(Noise),
                               _p(C.c_int32)]),
     "pb200_run_staged": (C.c_int, [C.c_void_p, _p(C.c_int64), _p(C.c_float)]),

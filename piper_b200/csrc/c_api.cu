@@ -142,7 +142,23 @@ int pb200_vocode(pb200_voice* v, const float* z, int32_t B, int64_t frames, cons
                  double* infer_seconds) {
   return guarded([&] {
     if (!v || !z || !audio) throw std::runtime_error("pb200_vocode: null argument");
-    *audio = v->engine.vocode(z, B, frames, infer_seconds);
+    *audio = v->engine.vocode(z, B, frames, false, infer_seconds);
+  });
+}
+
+int pb200_decode(pb200_voice* v, const float* z_p, int32_t B, int64_t frames, const float** audio,
+                 double* infer_seconds) {
+  return guarded([&] {
+    if (!v || !z_p || !audio) throw std::runtime_error("pb200_decode: null argument");
+    *audio = v->engine.vocode(z_p, B, frames, true, infer_seconds);
+  });
+}
+
+int pb200_encode(pb200_voice* v, const int64_t* ids, int64_t n_ids, const float scales[3], const pb200_noise* noise,
+                 const float** z_p, int64_t* frames, double* infer_seconds) {
+  return guarded([&] {
+    if (!v || !ids || !scales || !z_p || !frames) throw std::runtime_error("pb200_encode: null argument");
+    *z_p = v->engine.encode(ids, n_ids, scales, to_spec(noise), frames, infer_seconds);
   });
 }
 

@@ -503,17 +503,11 @@ void Engine::run_generator() {
                    off_d_.as<long long>(), ylen, rate, B, F * rate, stream_);
 }
 
-void Engine::run_back() {
+void Engine::run_flow() {
   const VoiceSpec& s = voice_.spec;
   const int B = B_, H = s.hidden, I = s.inter, Fp = Fp_, F = Fmax_;
   const int* ylen = ylen_d_.as<int>();
-  const int* len = len_d_.as<int>();
-  CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
-  View stats = view(stats_.as<float>(), 2 * I, Tp_);
   View z = view(z_.as<float>(), I, Fp);
-  launch_expand(stats, I, cum_d_.as<int>(), Tp_, len, ylen, z, have_eps_z_ ? epsz_d_.as<float>() : nullptr,
-                (long long)I * z_stride_, int(z_stride_), seed_, scales_[0], B, F, stream_);
-  if (debug_) save_tap("z_p", z, I, ylen_h_.data(), 1);
   // ---- flow, reverse (models.py:251-253; modules.py:447-466,184-209)
   View fh = view(fh_.as<float>(), H, Fp), acts = view(facts_.as<float>(), H, Fp), out = view(fout_.as<float>(), H, Fp);
   const int half = I / 2;
@@ -537,6 +531,20 @@ void Engine::run_back() {
     p.epi = EPI_SUBFROM; p.y = x1; p.r = x1;
     conv("flow", p, F, sum_F_);
   }
+}
+
+void Engine::run_back() {
+  const VoiceSpec& s = voice_.spec;
+  const int B = B_, H = s.hidden, I = s.inter, Fp = Fp_, F = Fmax_;
+  const int* ylen = ylen_d_.as<int>();
+  const int* len = len_d_.as<int>();
+  CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
+  View stats = view(stats_.as<float>(), 2 * I, Tp_);
+  View z = view(z_.as<float>(), I, Fp);
+  launch_expand(stats, I, cum_d_.as<int>(), Tp_, len, ylen, z, have_eps_z_ ? epsz_d_.as<float>() : nullptr,
+                (long long)I * z_stride_, int(z_stride_), seed_, scales_[0], B, F, stream_);
+  if (debug_) save_tap("z_p", z, I, ylen_h_.data(), 1);
+  run_flow();
   if (debug_) save_tap("z", z, I, ylen_h_.data(), 1);
   CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
   run_generator();
@@ -622,7 +630,32 @@ const int16_t* Engine::synthesize_int16(const int64_t* ids_concat, const int64_t
   return audio16_pin_.as<int16_t>();
 }
 
-const float* Engine::vocode(const float* z, int B, int64_t frames, double* infer_seconds) {
+const float* Engine::encode(const int64_t* ids, int64_t n_ids, const float scales[3], const NoiseSpec& noise,
+                            int64_t* frames, double* infer_seconds) {
+  // Encoder half of the reference's streaming split (export_onnx_streaming.py:19-58): text encoder, duration
+  // predictor, length regulator and the prior sample z_p [inter][T'] - everything before the flow.
+  const auto t0 = std::chrono::steady_clock::now();
+  int64_t lens[1] = {n_ids};
+  upload_inputs(ids, lens, 1, scales, noise, nullptr);
+  run_front();
+  plan_back();
+  const VoiceSpec& s = voice_.spec;
+  View stats = view(stats_.as<float>(), 2 * s.inter, Tp_);
+  View z = view(z_.as<float>(), s.inter, Fp_);
+  launch_expand(stats, s.inter, cum_d_.as<int>(), Tp_, len_d_.as<int>(), ylen_d_.as<int>(), z,
+                have_eps_z_ ? epsz_d_.as<float>() : nullptr, (long long)s.inter * z_stride_, int(z_stride_), seed_,
+                scales_[0], 1, Fmax_, stream_);
+  const int F = ylen_h_[0];
+  audio_pin_.ensure(size_t(s.inter) * F * 4);
+  CUDA_CHECK(cudaMemcpy2DAsync(audio_pin_.p, size_t(F) * 4, z.p, size_t(Fp_) * 4, size_t(F) * 4, size_t(s.inter),
+                               cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (frames) *frames = F;
+  if (infer_seconds) *infer_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return audio_pin_.as<float>();
+}
+
+const float* Engine::vocode(const float* z, int B, int64_t frames, bool with_flow, double* infer_seconds) {
   const VoiceSpec& s = voice_.spec;
   if (B <= 0 || frames <= 0 || !z) throw std::runtime_error("vocode: bad arguments");
   if (frames > max_frames_) throw std::runtime_error("vocode: too many frames");
@@ -643,6 +676,7 @@ const float* Engine::vocode(const float* z, int B, int64_t frames, double* infer
   // z host [B][inter][frames] -> device [B][inter][Fp]
   CUDA_CHECK(cudaMemcpy2DAsync(z_.p, size_t(Fp_) * 4, z, size_t(frames) * 4, size_t(frames) * 4, size_t(B) * s.inter,
                                cudaMemcpyHostToDevice, stream_));
+  if (with_flow) run_flow();                 // decoder half of the reference's streaming split (flow + generator)
   CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
   run_generator();
   CUDA_CHECK(cudaEventRecord(ev_[5], stream_));

@@ -73,7 +73,10 @@ class Engine {
   const int16_t* synthesize_int16(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3],
                                   const NoiseSpec& noise, int64_t* n_samples, double* infer_seconds);
   // Generator only: z host [B][inter][frames] -> audio [B][frames*hop]
-  const float* vocode(const float* z, int B, int64_t frames, double* infer_seconds);
+  const float* vocode(const float* z, int B, int64_t frames, bool with_flow, double* infer_seconds);
+  // encoder half of the streaming split: ids -> z_p [inter][frames] (host, pinned)
+  const float* encode(const int64_t* ids, int64_t n_ids, const float scales[3], const NoiseSpec& noise, int64_t* frames,
+                      double* infer_seconds);
 
   // ---- staged execution for device-resident timing (bench.py `value`)
   void stage(const int64_t* ids_concat, const int64_t* lens, int B, const float scales[3], const NoiseSpec& noise,
@@ -99,6 +102,7 @@ class Engine {
   void run_front();              // encoder + duration predictor, ends with the y_len D2H + sync
   void plan_back();              // host: sizes, offsets, workspace growth
   void run_back();               // expand + flow + generator -> audio_d_
+  void run_flow();               // in place on z_
   void run_generator();
   void ensure_front(int B, int Tmax);
   void ensure_back(int B, int Fmax);

@@ -152,6 +152,31 @@ class Voice:
         check(self._lib.pb200_vocode(self._h, _fptr(z), B, Fr, C.byref(audio), C.byref(sec)))
         return np.ctypeslib.as_array(audio, shape=(B, Fr * self.hop)).copy(), sec.value
 
+    def encode(self, ids: Sequence[int], scales=(0.667, 1.0, 0.8), eps_dp=None, eps_z=None, seed=0) -> np.ndarray:
+        """Encoder half of the streaming split: ids -> z_p [inter][frames]."""
+        ids_a = np.ascontiguousarray(np.asarray(ids, np.int64))
+        sc = np.asarray(scales, np.float32)
+        n, keep = self._noise(None if eps_dp is None else [eps_dp],
+                              None if eps_z is None else np.asarray(eps_z, np.float32)[None], seed)
+        zp = C.POINTER(C.c_float)()
+        fr = C.c_int64(0)
+        sec = C.c_double(0)
+        check(self._lib.pb200_encode(self._h, ids_a.ctypes.data_as(C.POINTER(C.c_int64)), len(ids_a), _fptr(sc),
+                                     C.byref(n), C.byref(zp), C.byref(fr), C.byref(sec)))
+        return np.ctypeslib.as_array(zp, shape=(self.inter, fr.value)).copy()
+
+    def decode(self, z_p: np.ndarray):
+        """Decoder half: flow reverse + generator on z_p [B][inter][frames] -> [B][frames*hop]."""
+        z = np.ascontiguousarray(np.asarray(z_p, np.float32))
+        if z.ndim == 2:
+            z = z[None]
+        B, I, Fr = z.shape
+        assert I == self.inter
+        audio = C.POINTER(C.c_float)()
+        sec = C.c_double(0)
+        check(self._lib.pb200_decode(self._h, _fptr(z), B, Fr, C.byref(audio), C.byref(sec)))
+        return np.ctypeslib.as_array(audio, shape=(B, Fr * self.hop)).copy()
+
     def stage(self, ids_list, scales=(0.667, 1.0, 0.8), seed=0, w_ceil_override=None):
         cat, lens = self._ids(ids_list)
         sc = np.asarray(scales, np.float32)

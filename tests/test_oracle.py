@@ -25,7 +25,8 @@ def _oracle_for(tag):
     return Oracle(spec, w, attrs), w
 
 
-@pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))))
+@pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                                        if not os.path.basename(p).startswith("stream_")))
 def test_oracle_matches_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     orc, w = _oracle_for(str(g["voice"]))
@@ -95,3 +96,51 @@ def test_oracle_edge_cases():
     # all-zero durations: clamp_min(sum, 1) gives exactly one frame (models.py:704)
     o3 = orc.infer([1, 0, 2], (0.0, 1.0, 0.0), w_ceil_override=[0, 0, 0])
     assert len(o3) == 256
+
+
+def test_streaming_chunks_match_golden():
+    """Chunk plan + oracle decoder against the fixture minted with the reference's own chunk loop."""
+    from piper_b200 import streaming
+    g = np.load(os.path.join(GOLDEN, "stream_tiny.npz"))
+    orc, _ = _oracle_for(str(g["voice"]))
+    z_p = orc.encode(g["ids"], g["scales"], g["eps_dp"], g["eps_z"])
+    assert np.abs(z_p - g["z_p"]).max() <= 1e-4
+
+    class _V:
+        hop = orc.s.hop
+    st = streaming.SpeechStreamer(_V(), int(g["chunk_size"]), int(g["chunk_padding"]), reference_quirks=True)
+    pieces = list(st.chunk(z_p, decode=orc.decode))
+    assert [len(p) for p in pieces] == g["piece_lens"].tolist()
+    assert np.abs(np.concatenate(pieces) - g["audio"]).max() <= 1e-3
+    # without the reference's stale right-trim the last chunk keeps its tail: total = frames * hop
+    full = list(streaming.SpeechStreamer(_V(), 45, 10, reference_quirks=False).chunk(z_p, decode=orc.decode))
+    assert sum(len(p) for p in full) == z_p.shape[1] * orc.s.hop
+
+
+def test_chunk_plan_properties():
+    from piper_b200.streaming import plan_chunks
+    assert plan_chunks(65) == [(0, 65, 0, 0)]                       # too short to stream
+    for n in (66, 90, 135, 136, 161, 500):
+        plan = plan_chunks(n, 45, 10, reference_quirks=False)
+        kept = sum((hi - lo) - tl - tr for lo, hi, tl, tr in plan)
+        assert kept == n and plan[0][0] == 0 and plan[-1][1] == n
+        assert all(hi - lo <= 45 + 20 for lo, hi, _, _ in plan)
+
+
+@pytest.mark.needs_reference
+def test_streaming_matches_reference_chunk_loop():
+    from oracle import ref_bridge
+    from piper_b200 import streaming
+    if not ref_bridge.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    orc, w = _oracle_for("synthetic:tiny:1234")
+    net = ref_bridge.build_reference_model(orc.s, w)
+    ids = voicegen.benchmark_ids(70, seed=5)
+    z_p = orc.encode(ids, (0.667, 1.0, 0.8))
+    ref = ref_bridge.reference_stream_chunks(net, z_p, z_p.shape[1], 45, 10)
+
+    class _V:
+        hop = orc.s.hop
+    mine = list(streaming.SpeechStreamer(_V(), 45, 10, True).chunk(z_p, decode=orc.decode))
+    assert [len(a) for a in mine] == [len(a) for a in ref]
+    assert max(np.abs(a - b).max() for a, b in zip(mine, ref)) <= 1e-4
