@@ -45,6 +45,8 @@ typedef struct pb200_voice_info {
   int32_t hop;             /* samples per frame = prod(upsample_rates) */
   int32_t up_initial;
   int32_t device;
+  int32_t n_speakers;      /* rows of emb_g (1 for single-speaker voices) */
+  int32_t gin;             /* speaker-embedding width, 0 for single-speaker voices */
   int64_t n_params;        /* fp32 parameters read from the file */
   int64_t weight_bytes;    /* packed blob resident in HBM */
 } pb200_voice_info;
@@ -79,7 +81,7 @@ int pb200_voice_describe(const char* onnx_path, char* buf, int64_t cap);
 int pb200_voice_pack(const char* onnx_path, float* blob, int64_t* n_floats);
 
 /* One utterance.  ids: int64 [n_ids]; scales = {noise_scale, length_scale, noise_w};
- * sid must be NULL (single-speaker voices).  On success *audio points at fp32 samples owned by the
+ * sid: speaker id for multi-speaker voices (the graph's `sid` input, piper.cpp:367-377) or NULL (speaker 0).  On success *audio points at fp32 samples owned by the
  * engine (pinned host memory), valid until the next call on this voice or pb200_release(). */
 int pb200_synthesize(pb200_voice* v, const int64_t* ids, int64_t n_ids, const float scales[3], const int64_t* sid,
                      const pb200_noise* noise, const float** audio, int64_t* n_samples, double* infer_seconds);
@@ -142,6 +144,10 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
 int pb200_debug_mma_bench(int32_t N, int32_t tf32, int32_t n_acc, int32_t iters, int32_t shift, uint64_t* cycles);
 
 void pb200_release(pb200_voice* v, const void* audio);
+
+/* Speaker ids for the following batch / staged / decode calls on this voice: item b uses sids[min(b, n-1)]
+ * (n = 0 resets to speaker 0).  Single-speaker voices ignore it. */
+int pb200_set_speakers(pb200_voice* v, const int64_t* sids, int32_t n);
 
 /* Test taps: when debug is on, intermediate tensors of the last call are kept on the host.
  * names: x, stats, logw, cum, z_p, z, up<i>, stage<i>, audio.  Copies item b as [C][len] into buf. */

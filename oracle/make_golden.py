@@ -33,7 +33,7 @@ def weights_digest(w) -> str:
     return h.hexdigest()
 
 
-def mint(name, voice_path, voice_tag, ids, scales, seed):
+def mint(name, voice_path, voice_tag, ids, scales, seed, sid=None):
     spec, w, _ = load_voice(voice_path)
     net = ref_bridge.build_reference_model(spec, w)
     ids = np.asarray(ids, np.int64)
@@ -42,7 +42,7 @@ def mint(name, voice_path, voice_tag, ids, scales, seed):
         rng = np.random.default_rng(seed)
         eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
         eps_z = rng.standard_normal((spec.inter, 3 * len(ids))).astype(np.float32)
-    r = ref_bridge.reference_infer(net, ids, scales, eps_dp, eps_z)
+    r = ref_bridge.reference_infer(net, ids, scales, eps_dp, eps_z, sid=sid)
     if eps_z is not None:
         assert r["y_len"] <= eps_z.shape[1]
         eps_z = eps_z[:, : r["y_len"]].copy()
@@ -51,6 +51,8 @@ def mint(name, voice_path, voice_tag, ids, scales, seed):
                voice=np.array(voice_tag), weights_sha256=np.array(weights_digest(w)))
     if eps_dp is not None:
         out.update(eps_dp=eps_dp, eps_z=eps_z)
+    if sid is not None:
+        out.update(sid=np.int64(sid))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(f"{name}: ids={len(ids)} frames={r['y_len']} max|o|={np.abs(r['o']).max():.6f} "
           f"mean|o|={np.abs(r['o']).mean():.6f} o[0:3]={r['o'][:3]}")
@@ -79,6 +81,8 @@ def main():
         path = voicegen.cached_voice(arch)
         mint(f"synthetic_{arch}", path, f"synthetic:{arch}:1234", voicegen.benchmark_ids(n_ph, seed=99),
              (0.667, 1.0, 0.8), 4321)
+    mint("synthetic_tiny-ms_sid3", voicegen.cached_voice("tiny-ms"), "synthetic:tiny-ms:1234",
+         voicegen.benchmark_ids(32, seed=99), (0.667, 1.0, 0.8), 4321, sid=3)
     mint_streaming()
 
 

@@ -49,7 +49,8 @@ def build_reference_model(spec, weights: Dict[str, np.ndarray]):
             resblock=str(spec.resblock), resblock_kernel_sizes=tuple(spec.rb_kernels),
             resblock_dilation_sizes=tuple(tuple(d) for d in spec.rb_dilations),
             upsample_rates=tuple(spec.up_rates), upsample_initial_channel=spec.up_initial,
-            upsample_kernel_sizes=tuple(spec.up_kernels), n_speakers=1, gin_channels=0, use_sdp=True)
+            upsample_kernel_sizes=tuple(spec.up_kernels), n_speakers=getattr(spec, "n_speakers", 1),
+            gin_channels=getattr(spec, "gin", 0), use_sdp=True)
         net.eval()
         import contextlib, io
         with contextlib.redirect_stdout(io.StringIO()):
@@ -70,7 +71,7 @@ def build_reference_model(spec, weights: Dict[str, np.ndarray]):
 
 
 @torch.no_grad()
-def reference_infer(net, ids, scales, eps_dp=None, eps_z=None):
+def reference_infer(net, ids, scales, eps_dp=None, eps_z=None, sid=None):
     """Call the reference's `SynthesizerTrn.infer` (models.py:681-722) with injected noise.
 
     torch.randn / torch.randn_like are patched for the duration of the call so that the
@@ -98,8 +99,8 @@ def reference_infer(net, ids, scales, eps_dp=None, eps_z=None):
     torch.randn, torch.randn_like = fake_randn, fake_randn_like
     try:
         o, attn, y_mask, (z, z_p, m_p, logs_p) = net.infer(
-            ids_t, lens, noise_scale=float(scales[0]), length_scale=float(scales[1]),
-            noise_scale_w=float(scales[2]))
+            ids_t, lens, sid=None if sid is None else torch.tensor([int(sid)]), noise_scale=float(scales[0]),
+            length_scale=float(scales[1]), noise_scale_w=float(scales[2]))
     finally:
         torch.randn, torch.randn_like = real_randn, real_randn_like
     w_ceil = attn[0, 0].sum(0)

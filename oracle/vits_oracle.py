@@ -150,9 +150,11 @@ class Oracle:
         out = root * in_w + in_cw
         return torch.where(inside, out, x)
 
-    def duration_logw(self, x, eps_dp, noise_w):
+    def duration_logw(self, x, eps_dp, noise_w, g=None):
         s = self.s
         c = self.conv(x, "dp.pre")
+        if g is not None:                                   # models.py:66-68
+            c = c + self.conv(g, "dp.cond")
         c = self.dds_conv(c, "dp.convs")
         c = self.conv(c, "dp.proj")
         z = eps_dp * noise_w                                             # [2,T]
@@ -173,14 +175,17 @@ class Oracle:
         return z[0]
 
     # ------------------------------------------------------------------- flow
-    def wn(self, h, prefix):
+    def wn(self, h, prefix, g=None):
         s = self.s
         H = h.shape[0]
         out = torch.zeros_like(h)
         k = s.wn_kernel
+        gc = self.conv(g, f"{prefix}.cond_layer") if g is not None else None      # modules.py:188-197
         for i in range(s.wn_layers):
             d = s.wn_dilation_rate ** i
             a = self.conv(h, f"{prefix}.in_layers.{i}", dilation=d, pad=(k * d - d) // 2)
+            if gc is not None:
+                a = a + gc[i * 2 * H:(i + 1) * 2 * H]
             acts = torch.tanh(a[:H]) * torch.sigmoid(a[H:])
             rs = self.conv(acts, f"{prefix}.res_skip_layers.{i}")
             if i < s.wn_layers - 1:
@@ -190,21 +195,23 @@ class Oracle:
                 out = out + rs
         return out
 
-    def flow_reverse(self, z):
+    def flow_reverse(self, z, g=None):
         half = self.s.inter // 2
         for f in self.s.flow_layers:
             z = z.flip(0)
             x0, x1 = z[:half], z[half:]
             h = self.conv(x0, f"flow.flows.{f}.pre")
-            h = self.wn(h, f"flow.flows.{f}.enc")
+            h = self.wn(h, f"flow.flows.{f}.enc", g)
             m = self.conv(h, f"flow.flows.{f}.post")
             z = torch.cat([x0, x1 - m], 0)
         return z
 
     # -------------------------------------------------------------- generator
-    def generator(self, z, dump: Optional[dict] = None):
+    def generator(self, z, dump: Optional[dict] = None, g=None):
         s = self.s
         x = self.conv(z, "dec.conv_pre", pad=3)
+        if g is not None:                                   # models.py:350-351
+            x = x + self.conv(g, "dec.cond")
         nk = len(s.rb_kernels)
         for i, (u, k, p) in enumerate(zip(s.up_rates, s.up_kernels, s.up_pads)):
             x = F.leaky_relu(x, 0.1)
@@ -249,7 +256,7 @@ class Oracle:
     # ------------------------------------------------------------------ infer
     @torch.no_grad()
     def infer(self, ids, scales, eps_dp=None, eps_z=None, w_ceil_override=None, dump: Optional[dict] = None,
-              stop_before_flow: bool = False):
+              stop_before_flow: bool = False, sid: Optional[int] = None):
         """ids int64 [T]; scales = (noise_scale, length_scale, noise_w).
         eps_dp [2,T] / eps_z [inter, >=T'] default to zeros (deterministic graph).
         Returns fp32 waveform [T' * hop] (np.ndarray)."""
@@ -258,10 +265,13 @@ class Oracle:
         T = ids.numel()
         noise_scale, length_scale, noise_w = (float(v) for v in scales)
         x, m_p, logs_p = self.text_encoder(ids)
+        g = None
+        if s.n_speakers > 1:                                # models.py:692-696
+            g = self.w["emb_g.weight"][int(sid or 0)][:, None]
         if eps_dp is None:
             eps_dp = torch.zeros(2, T)
         eps_dp = torch.as_tensor(np.asarray(eps_dp), dtype=torch.float32)
-        logw = self.duration_logw(x, eps_dp, noise_w)
+        logw = self.duration_logw(x, eps_dp, noise_w, g)
         w = torch.exp(logw) * length_scale
         w_ceil = torch.ceil(w)
         if w_ceil_override is not None:
@@ -281,8 +291,8 @@ class Oracle:
         if stop_before_flow:
             dump.update(z_p=z_p, w_ceil=w_ceil)
             return None
-        z = self.flow_reverse(z_p)
-        o = self.generator(z, dump)
+        z = self.flow_reverse(z_p, g)
+        o = self.generator(z, dump, g)
         if dump is not None:
             dump.update(x=x, m_p=m_p, logs_p=logs_p, logw=logw, w_ceil=w_ceil, z_p=z_p, z=z, o=o)
         return o.numpy()

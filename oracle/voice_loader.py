@@ -56,6 +56,8 @@ class VoiceSpec:
     rb_kernels: List[int] = field(default_factory=list)
     rb_dilations: List[List[int]] = field(default_factory=list)
     hop: int = 0
+    n_speakers: int = 1
+    gin: int = 0             # speaker-embedding width (0 = single speaker)
 
 
 def canonicalize(model: onnx_wire.Model) -> Tuple[Dict[str, np.ndarray], Dict[str, ConvAttr]]:
@@ -149,6 +151,8 @@ def infer_spec(w: Dict[str, np.ndarray], attrs: Dict[str, ConvAttr]) -> VoiceSpe
         s.up_kernels.append(a.kernel)
         s.up_pads.append(a.pad)
     s.hop = int(np.prod(s.up_rates))
+    if "emb_g.weight" in w:
+        s.n_speakers, s.gin = int(w["emb_g.weight"].shape[0]), int(w["emb_g.weight"].shape[1])
     s.resblock = 1 if any(k.startswith("dec.resblocks.0.convs1.") for k in w) else 2
     n_rb = len(_indices(w, r"dec\.resblocks\.(\d+)\."))
     per_stage = n_rb // len(ups)

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libpiper_b200.so")
 class VoiceInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("n_vocab", "hidden", "inter", "filter", "n_heads", "n_layers", "window", "resblock",
-                 "n_upsamples", "hop", "up_initial", "device")] + \
+                 "n_upsamples", "hop", "up_initial", "device", "n_speakers", "gin")] + \
                [("n_params", C.c_int64), ("weight_bytes", C.c_int64)]
 
 
@@ -57,6 +57,7 @@ SYMBOLS = {
                                      _p(C.c_float)]),
     "pb200_debug_mma_bench": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _p(C.c_uint64)]),
     "pb200_release": (None, [C.c_void_p, C.c_void_p]),
+    "pb200_set_speakers": (C.c_int, [C.c_void_p, _p(C.c_int64), C.c_int32]),
     "pb200_set_debug": (C.c_int, [C.c_void_p, C.c_int32]),
     "pb200_tap_shape": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, _p(C.c_int32), _p(C.c_int32)]),
     "pb200_tap_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, _p(C.c_float), C.c_int64]),

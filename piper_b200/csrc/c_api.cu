@@ -77,6 +77,7 @@ int pb200_voice_get_info(const pb200_voice* v, pb200_voice_info* info) {
     info->n_heads = s.n_heads; info->n_layers = s.n_layers; info->window = s.window; info->resblock = s.resblock;
     info->n_upsamples = int32_t(s.up_rates.size()); info->hop = s.hop; info->up_initial = s.up_initial;
     info->device = v->engine.device();
+    info->n_speakers = s.n_speakers; info->gin = s.gin;
     info->n_params = v->engine.voice().n_params;
     info->weight_bytes = v->engine.weight_bytes();
   });
@@ -112,7 +113,7 @@ int pb200_synthesize(pb200_voice* v, const int64_t* ids, int64_t n_ids, const fl
                      const pb200_noise* noise, const float** audio, int64_t* n_samples, double* infer_seconds) {
   return guarded([&] {
     if (!v || !ids || !scales || !audio || !n_samples) throw std::runtime_error("pb200_synthesize: null argument");
-    if (sid) throw std::runtime_error("speaker id given but this build supports single-speaker voices only");
+    if (sid) v->engine.set_speakers(sid, 1);
     int64_t lens[1] = {n_ids};
     *audio = v->engine.synthesize(ids, lens, 1, scales, to_spec(noise), nullptr, n_samples, infer_seconds);
   });
@@ -289,6 +290,13 @@ int pb200_debug_mma_bench(int32_t N, int32_t tf32, int32_t n_acc, int32_t iters,
 
 void pb200_release(pb200_voice*, const void*) {
   // Output buffers are engine-owned pinned staging areas reused by the next call; nothing to free.
+}
+
+int pb200_set_speakers(pb200_voice* v, const int64_t* sids, int32_t n) {
+  return guarded([&] {
+    if (!v || (n > 0 && !sids)) throw std::runtime_error("pb200_set_speakers: null argument");
+    v->engine.set_speakers(sids, n);
+  });
 }
 
 int pb200_set_debug(pb200_voice* v, int32_t on) {

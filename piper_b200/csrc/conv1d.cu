@@ -160,7 +160,10 @@ __global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs a) {
   const int rbase = row0 + wr * CPT;
   float bv[CPT];
 #pragma unroll
-  for (int r = 0; r < CPT; ++r) bv[r] = (a.bias != nullptr && rbase + r < a.rows) ? __ldg(a.bias + rbase + r) : 0.f;
+  for (int r = 0; r < CPT; ++r) {
+    bv[r] = (a.bias != nullptr && rbase + r < a.rows) ? __ldg(a.bias + rbase + r) : 0.f;
+    if (a.bias_item != nullptr && rbase + r < a.rows) bv[r] += __ldg(a.bias_item + (long long)b * a.bias_item_stride + rbase + r);
+  }
 
   float* yb = a.y.p ? a.y.p + (long long)b * a.y.bs : nullptr;
   float* y2b = a.y2.p ? a.y2.p + (long long)b * a.y2.bs : nullptr;

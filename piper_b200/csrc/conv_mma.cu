@@ -353,6 +353,10 @@ __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + row0 + i);
         }
+        if (a.bias_item) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias_item + (long long)b * a.bias_item_stride + row0 + i);
+        }
         if (a.epi == EPI_GATE) {
 #pragma unroll
           for (int i = 0; i < 16; i += 2)
@@ -702,6 +706,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
         if (a.bias) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias + row0 + i);
+        }
+        if (a.bias_item) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(a.bias_item + (long long)b * a.bias_item_stride + row0 + i);
         }
         if (a.epi == EPI_GATE) {
 #pragma unroll

@@ -34,6 +34,22 @@ __device__ float philox_normal(unsigned long long seed, uint32_t stream, uint32_
   return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
+// one warp per (row, item): dot product over gin with a shuffle reduction
+__global__ void __launch_bounds__(256) speaker_cond_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                           const float* __restrict__ emb_g, const int* __restrict__ sid,
+                                                           float* __restrict__ cond, int rows, int gin) {
+  const int b = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* e = emb_g + (long long)sid[b] * gin;
+  const float* wr = w + (long long)row * gin;
+  float acc = 0.f;
+  for (int k = lane; k < gin; k += 32) acc = fmaf(__ldg(wr + k), __ldg(e + k), acc);
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) cond[(long long)b * rows + row] = acc + __ldg(bias + row);
+}
+
 __global__ void dp_noise_kernel(View z, const float* __restrict__ eps, const long long* __restrict__ eps_off,
                                 unsigned long long seed, float noise_w, const int* __restrict__ len) {
   const int b = blockIdx.z, ch = blockIdx.y;
@@ -207,6 +223,14 @@ __global__ void __launch_bounds__(256) expand_kernel(View stats, int inter, cons
 }
 
 }  // namespace
+
+void launch_speaker_cond(const float* w, const float* bias, const float* emb_g, const int* sid, float* cond, int rows,
+                         int gin, int B, cudaStream_t st) {
+  if (B <= 0 || rows <= 0) return;
+  dim3 grid((rows + 7) / 8, B);
+  speaker_cond_kernel<<<grid, 256, 0, st>>>(w, bias, emb_g, sid, cond, rows, gin);
+  count_launch();
+}
 
 void launch_dp_noise(View z, const float* eps, const long long* eps_off, unsigned long long seed, float noise_w,
                      const int* len, int B, int Tmax, cudaStream_t st) {

@@ -75,7 +75,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   DeviceBuf* dbs[] = {&weights_, &weights_mma_, &ids_d_, &len_d_, &ylen_d_, &cum_d_, &logw_d_, &override_d_, &epsdp_d_, &epsoff_d_,
-                      &off_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
+                      &off_d_, &sid_d_, &cond_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
                       &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_};
   for (auto* d : dbs) d->release();
   PinnedBuf* pbs[] = {&ids_pin_, &misc_pin_, &audio_pin_, &audio16_pin_, &eps_pin_};
@@ -107,7 +107,8 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   if (mma) {
     m.x = a.x; m.y = a.y; m.y2 = a.y2; m.r = a.r;
     m.w = weights_mma_.as<uint8_t>() + w->mma;
-    m.bias = a.bias; m.len = a.len; m.len_scale = a.len_scale;
+    m.bias = a.bias; m.bias_item = a.bias_item; m.bias_item_stride = a.bias_item_stride;
+    m.len = a.len; m.len_scale = a.len_scale;
     m.ci = a.ci; m.rows = a.rows; m.k = a.k; m.dil = a.dil; m.pad = a.pad; m.q_extra = a.q_extra;
     m.pre = a.pre; m.slope = a.slope; m.epi = a.epi; m.split = a.split; m.first = a.first;
     m.up = a.up; m.up_pad = a.up_pad; m.mrf = a.mrf; m.mrf_n = a.mrf_n;
@@ -277,6 +278,29 @@ void Engine::upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B
   CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
+void Engine::set_speakers(const int64_t* sids, int n) {
+  sids_.clear();
+  for (int i = 0; i < n; ++i) {
+    if (sids[i] < 0 || sids[i] >= voice_.spec.n_speakers)
+      throw std::runtime_error("speaker id " + std::to_string(sids[i]) + " outside [0," + std::to_string(voice_.spec.n_speakers) + ")");
+    sids_.push_back(int(sids[i]));
+  }
+}
+
+void Engine::upload_speakers(int B) {
+  const VoiceSpec& s = voice_.spec;
+  if (s.gin <= 0) return;
+  std::vector<int> sid(B, 0);
+  for (int b = 0; b < B; ++b)
+    if (!sids_.empty()) sid[b] = sids_[std::min<size_t>(b, sids_.size() - 1)];
+  sid_d_.ensure(size_t(B) * 4);
+  cond_d_.ensure(size_t(B) * voice_.cond_rows * 4);
+  CUDA_CHECK(cudaMemcpyAsync(sid_d_.p, sid.data(), size_t(B) * 4, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));      // `sid` is a stack vector
+  launch_speaker_cond(W(voice_.cond_w), W(voice_.cond_b), W(voice_.emb_g), sid_d_.as<int>(), cond_d_.as<float>(),
+                      voice_.cond_rows, s.gin, B, stream_);
+}
+
 void Engine::dds(const DDSW& d, View h, View u, View v, int C) {
   const int* len = len_d_.as<int>();
   for (const DDSLayerW& l : d.layers) {
@@ -322,6 +346,7 @@ void Engine::run_front() {
   View x = view(x_.as<float>(), H, Tp), t1 = view(t1_.as<float>(), H, Tp), qkv = view(qkv_.as<float>(), 3 * H, Tp),
        att = view(att_.as<float>(), H, Tp), ffn = view(ffn_.as<float>(), s.filter, Tp),
        stats = view(stats_.as<float>(), 2 * I, Tp);
+  upload_speakers(B);
   CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
   // ---- text encoder (models.py:198-209)
   launch_embed(ids_d_.as<int>(), Tp, W(voice_.emb), H, std::sqrt(float(H)), x, len, B, T, stream_);
@@ -363,6 +388,8 @@ void Engine::run_front() {
   {
     ConvArgs c = conv_args(voice_.dp_pre, x, len, 1);
     c.y = h;
+    c.bias_item = cond_row(voice_.dp_cond_row);      // x = pre(x) + cond(g)  (models.py:66-68)
+    c.bias_item_stride = voice_.cond_rows;
     conv("dp", c, T, sum_T_);
     dds(voice_.dp_dds, h, u, v, H);
     c = conv_args(voice_.dp_proj, h, len, 1);
@@ -446,6 +473,8 @@ void Engine::run_generator() {
   {
     ConvArgs c = conv_args(voice_.dec_pre, z, ylen, 1);
     c.y = S;
+    c.bias_item = cond_row(voice_.dec_cond_row);     // x = conv_pre(x) + cond(g)  (models.py:350-351)
+    c.bias_item_stride = voice_.cond_rows;
     conv("dec.pre", c, F, sum_F_);
   }
   int rate = 1;
@@ -521,6 +550,10 @@ void Engine::run_flow() {
     for (int i = 0; i < nl; ++i) {
       ConvArgs a = conv_args(cw.in_layers[i], fh, ylen, 1);
       a.y = acts; a.epi = EPI_GATE;
+      if (cw.cond_row >= 0) {                          // in_act = x_in + g_l  (modules.py:188-199)
+        a.bias_item = cond_row(cw.cond_row + i * 2 * H);
+        a.bias_item_stride = voice_.cond_rows;
+      }
       conv("flow", a, F, sum_F_);
       ConvArgs r = conv_args(cw.res_skip[i], acts, ylen, 1);
       r.epi = EPI_WN; r.y = fh; r.r = fh; r.y2 = out; r.first = i == 0;
@@ -672,6 +705,7 @@ const float* Engine::vocode(const float* z, int B, int64_t frames, bool with_flo
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   have_eps_z_ = false;
   plan_back();
+  upload_speakers(B);
   if (debug_) taps_.clear();
   // z host [B][inter][frames] -> device [B][inter][Fp]
   CUDA_CHECK(cudaMemcpy2DAsync(z_.p, size_t(Fp_) * 4, z, size_t(frames) * 4, size_t(frames) * 4, size_t(B) * s.inter,

@@ -92,6 +92,8 @@ class Engine {
   std::string profile_json();
   void set_mma(int mask) { mma_mask_ = mask; }
   int mma() const { return mma_mask_; }
+  // speaker ids for the next calls (multi-speaker voices); item b uses sids[min(b, n-1)], default speaker 0
+  void set_speakers(const int64_t* sids, int n);
   void set_debug(bool on) { debug_ = on; }
   const HostTap* tap(const std::string& name) const;
   void set_max_frames(int64_t f) { max_frames_ = f; }
@@ -137,6 +139,10 @@ class Engine {
   int64_t max_frames_ = 1 << 17;
 
   // phoneme-rate workspace
+  std::vector<int> sids_;
+  DeviceBuf sid_d_, cond_d_;
+  void upload_speakers(int B);   // sid per item -> device, cond = W_cond * emb_g[sid] + b (no-op for single-speaker voices)
+  const float* cond_row(int row) const { return row >= 0 && cond_d_.p ? cond_d_.as<float>() + row : nullptr; }
   DeviceBuf ids_d_, len_d_, ylen_d_, cum_d_, logw_d_, override_d_, epsdp_d_, epsoff_d_, off_d_;
   DeviceBuf x_, t1_, qkv_, att_, ffn_, stats_, g_, h_, u_, v_, pr_, z2_;
   // frame-rate workspace

@@ -39,6 +39,8 @@ struct ConvArgs {
   View x, y, y2, r;
   const float* w = nullptr;     // [ci][k][rows_p]
   const float* bias = nullptr;  // [rows] or null
+  const float* bias_item = nullptr;  // optional per-item bias (speaker conditioning): + bias_item[b * bias_item_stride + row]
+  int bias_item_stride = 0;
   const int* len = nullptr;     // per item
   int len_scale = 1;            // valid input length = len[b] * len_scale
   int ci = 0, rows = 0, rows_p = 0, k = 1, dil = 1, pad = 0;
@@ -61,6 +63,8 @@ struct MmaConvArgs {
   View x, y, y2, r;
   const uint8_t* w = nullptr;    // packed by pack_conv_mma
   const float* bias = nullptr;
+  const float* bias_item = nullptr;   // optional per-item bias (speaker conditioning)
+  int bias_item_stride = 0;
   const int* len = nullptr;
   int len_scale = 1;
   int ci = 0, rows = 0, k = 1, dil = 1, pad = 0, q_extra = 0;
@@ -100,6 +104,10 @@ struct LnArgs {
   const int* len = nullptr;
 };
 void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st);
+
+// cond[b][r] = bias[r] + sum_k w[r][k] * emb_g[sid[b]][k]        (g = emb_g(sid), then every 1x1 conditioning conv at once)
+void launch_speaker_cond(const float* w, const float* bias, const float* emb_g, const int* sid, float* cond, int rows,
+                         int gin, int B, cudaStream_t st);
 
 // ---- stochastic duration predictor ------------------------------------------------------------
 // z[b][ch][t] = eps * noise_w  (eps explicit [sum_b 2*len_b] item-major, or Philox(seed) when eps == null)

@@ -257,9 +257,6 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
   load_onnx(onnx_path, m);
   Canon c;
   canonicalize(m, c);
-  for (const auto& kv : c.w)
-    if (starts_with(kv.first, "emb_g.") || kv.first.find(".cond") != std::string::npos)
-      fail("multi-speaker voice (tensor '" + kv.first + "'): speaker conditioning is not implemented yet");
   Packer P(c, v);
   VoiceSpec& s = v.spec;
 
@@ -294,6 +291,11 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
   }
   const int H = s.hidden, I = s.inter;
   if (I % 2) fail("inter_channels must be even");
+  if (P.has("emb_g.weight")) {
+    const OnnxTensor& eg = P.get("emb_g.weight", 2);
+    s.n_speakers = int(eg.dims[0]);
+    s.gin = int(eg.dims[1]);
+  }
 
   // ---- text encoder
   v.emb = P.put(emb);
@@ -437,6 +439,45 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
     if (a.pad * 2 != v.post_k - 1 || a.dil != 1) fail("dec.conv_post is not same-padded");
     v.post_w = P.put(pw);
   }
+  // ---- speaker conditioning matrix (multi-speaker voices)
+  if (s.gin > 0) {
+    v.emb_g = P.put_named("emb_g.weight", 2);
+    std::vector<const OnnxTensor*> ws, bs;
+    std::vector<int> perm_layers;   // > 0: rows are n WN layers of 2H rows each, to be gate-interleaved
+    auto add = [&](const std::string& prefix, int expect_rows, int wn_layers_of) {
+      const OnnxTensor& w = P.get(prefix + ".weight", 3);
+      if (w.dims[0] != expect_rows || w.dims[1] != s.gin || w.dims[2] != 1)
+        fail("'" + prefix + "': expected a " + std::to_string(expect_rows) + " x gin pointwise conditioning conv");
+      ws.push_back(&w);
+      bs.push_back(&P.get(prefix + ".bias", 1));
+      perm_layers.push_back(wn_layers_of);
+      const int row = v.cond_rows;
+      v.cond_rows += expect_rows;
+      return row;
+    };
+    v.dp_cond_row = add("dp.cond", H, 0);
+    for (size_t ci = 0; ci < v.flow.size(); ++ci)
+      v.flow[ci].cond_row = add("flow.flows." + std::to_string(s.flow_layers[ci]) + ".enc.cond_layer", 2 * H * s.wn_layers, s.wn_layers);
+    v.dec_cond_row = add("dec.cond", s.up_initial, 0);
+    v.cond_w = P.alloc(int64_t(v.cond_rows) * s.gin);
+    v.cond_b = P.alloc(v.cond_rows);
+    int row = 0;
+    for (size_t t = 0; t < ws.size(); ++t) {
+      const int rows = int(ws[t]->dims[0]);
+      for (int r = 0; r < rows; ++r) {
+        int src = r;
+        if (perm_layers[t] > 0) {           // (tanh_j, sigmoid_j) interleave inside each layer's 2H rows
+          const int layer = r / (2 * H), in = r % (2 * H);
+          src = layer * 2 * H + ((in & 1) ? H + in / 2 : in / 2);
+        }
+        std::memcpy(&v.blob[size_t(v.cond_w + int64_t(row + r) * s.gin)], ws[t]->f32() + size_t(src) * s.gin, size_t(s.gin) * 4);
+        v.blob[size_t(v.cond_b + row + r)] = bs[t]->f32()[src];
+      }
+      row += rows;
+      v.n_params += ws[t]->numel() + rows;
+    }
+  }
+
   // ---- tensor-core copies: bf16x3 for the generator, tf32x3 where outputs feed exp()/ceil() (flow, encoder)
   for (EncLayerW& e : v.enc) { P.add_mma(e.qkv, true); P.add_mma(e.o, true); P.add_mma(e.ffn1, true); P.add_mma(e.ffn2, true); }
   P.add_mma(v.enc_proj, true);
@@ -483,7 +524,7 @@ std::string describe_voice(const PackedVoice& v) {
     << ",\"n_heads\":" << s.n_heads << ",\"n_layers\":" << s.n_layers << ",\"window\":" << s.window
     << ",\"ffn_kernel\":" << s.ffn_kernel << ",\"dds_layers\":" << s.dds_layers << ",\"spline_bins\":" << s.spline_bins
     << ",\"wn_layers\":" << s.wn_layers << ",\"wn_kernel\":" << s.wn_kernel << ",\"wn_dilation_rate\":" << s.wn_dilation_rate
-    << ",\"resblock\":" << s.resblock << ",\"up_initial\":" << s.up_initial << ",\"hop\":" << s.hop << ",\"dp_flows\":";
+    << ",\"n_speakers\":" << s.n_speakers << ",\"gin\":" << s.gin << ",\"cond_rows\":" << v.cond_rows << ",\"resblock\":" << s.resblock << ",\"up_initial\":" << s.up_initial << ",\"hop\":" << s.hop << ",\"dp_flows\":";
   jlist(o, s.dp_flows);
   o << ",\"flow_layers\":";
   jlist(o, s.flow_layers);

@@ -65,6 +65,7 @@ struct CouplingW {
   ConvW pre, post;
   std::vector<ConvW> in_layers;   // rows interleaved (tanh_i, sigmoid_i) for the gate epilogue
   std::vector<ConvW> res_skip;
+  int cond_row = -1;              // first row of this coupling's WN cond_layer in the speaker-conditioning matrix
 };
 
 struct ResBlockW {
@@ -76,6 +77,7 @@ struct VoiceSpec {
   int n_vocab = 0, hidden = 0, inter = 0, filter = 0, n_heads = 0, n_layers = 0, window = 0, ffn_kernel = 0;
   int dds_layers = 0, spline_bins = 10, wn_layers = 0, wn_kernel = 0, wn_dilation_rate = 1;
   int resblock = 2, up_initial = 0, hop = 1;
+  int n_speakers = 1, gin = 0;   // multi-speaker voices: emb_g [n_speakers][gin]
   std::vector<int> dp_flows, flow_layers, up_rates, up_kernels, up_pads, rb_kernels;
   std::vector<std::vector<int>> rb_dilations;
 };
@@ -97,6 +99,10 @@ struct PackedVoice {
   std::vector<std::vector<ResBlockW>> resblocks;  // [stage][kernel]
   int64_t post_w = -1;              // conv_post [C][k] (no bias, models.py:342)
   int post_c = 0, post_k = 7;
+  // speaker conditioning (models.py:692-696; modules.py:188-197): one [cond_rows][gin] matrix holding dp.cond, every
+  // WN cond_layer (rows in the gate-interleaved order of the in_layers) and dec.cond; cond = W * emb_g[sid] + b
+  int64_t emb_g = -1, cond_w = -1, cond_b = -1;
+  int cond_rows = 0, dp_cond_row = -1, dec_cond_row = -1;
   int64_t n_params = 0;             // fp32 parameters read from the file (before packing/padding)
 };
 

@@ -87,7 +87,7 @@ class Voice:
         return cat, lens
 
     # ------------------------------------------------------------------ public
-    def synthesize(self, ids: Sequence[int], scales=(0.667, 1.0, 0.8), eps_dp=None, eps_z=None, seed=0):
+    def synthesize(self, ids: Sequence[int], scales=(0.667, 1.0, 0.8), eps_dp=None, eps_z=None, seed=0, sid=None):
         """One utterance through `pb200_synthesize` -> (fp32 waveform, infer_seconds)."""
         ids_a = np.ascontiguousarray(np.asarray(ids, np.int64))
         sc = np.asarray(scales, np.float32)
@@ -96,8 +96,9 @@ class Voice:
         audio = C.POINTER(C.c_float)()
         ns = C.c_int64(0)
         sec = C.c_double(0)
+        sid_c = None if sid is None else C.byref(C.c_int64(int(sid)))
         check(self._lib.pb200_synthesize(self._h, ids_a.ctypes.data_as(C.POINTER(C.c_int64)), len(ids_a), _fptr(sc),
-                                         None, C.byref(n), C.byref(audio), C.byref(ns), C.byref(sec)))
+                                         sid_c, C.byref(n), C.byref(audio), C.byref(ns), C.byref(sec)))
         out = np.ctypeslib.as_array(audio, shape=(ns.value,)).copy()
         return out, sec.value
 
@@ -205,6 +206,11 @@ class Voice:
         n0, n1 = C.c_int64(0), C.c_int64(0)
         check(self._lib.pb200_voice_weight_buffers(self._h, C.byref(p0), C.byref(n0), C.byref(p1), C.byref(n1)))
         return [(p0.value, n0.value), (p1.value, n1.value)]
+
+    def set_speakers(self, sids):
+        """Speaker ids for the following calls (item b uses sids[min(b, len-1)]); empty -> speaker 0."""
+        a = np.ascontiguousarray(np.asarray(list(sids), np.int64))
+        check(self._lib.pb200_set_speakers(self._h, a.ctypes.data_as(C.POINTER(C.c_int64)), len(a)))
 
     def set_mma(self, mask: int):
         check(self._lib.pb200_set_mma(self._h, int(mask)))

@@ -46,6 +46,15 @@ ARCHS: Dict[str, dict] = {
     "tiny": dict(hidden=32, inter=32, filter=64, heads=2, layers=2, resblock=2,
                  up_rates=(8, 8, 4), up_kernels=(16, 16, 8), up_initial=64,
                  rb_kernels=(3, 5, 7), rb_dilations=((1, 2), (2, 6), (3, 12)), sample_rate=22050),
+    # multi-speaker variants (emb_g + dp.cond + WN cond_layer + dec.cond; gin 512 in piper: lightning.py:81-83)
+    "tiny-ms": dict(hidden=32, inter=32, filter=64, heads=2, layers=2, resblock=2,
+                    up_rates=(8, 8, 4), up_kernels=(16, 16, 8), up_initial=64,
+                    rb_kernels=(3, 5, 7), rb_dilations=((1, 2), (2, 6), (3, 12)), sample_rate=22050,
+                    n_speakers=5, gin=48),
+    "medium-ms": dict(hidden=192, inter=192, filter=768, heads=2, layers=6, resblock=2,
+                      up_rates=(8, 8, 4), up_kernels=(16, 16, 8), up_initial=256,
+                      rb_kernels=(3, 5, 7), rb_dilations=((1, 2), (2, 6), (3, 12)), sample_rate=22050,
+                      n_speakers=8, gin=512),
     "tiny-high": dict(hidden=32, inter=32, filter=64, heads=2, layers=2, resblock=1,
                       up_rates=(8, 8, 2, 2), up_kernels=(16, 16, 4, 4), up_initial=64,
                       rb_kernels=(3, 7, 11), rb_dilations=((1, 3, 5), (1, 3, 5), (1, 3, 5)),
@@ -109,7 +118,14 @@ def build(arch: str = "medium", seed: int = 1234, n_vocab: int = 256) -> onnx_wi
     H, inter, Fc = cfg["hidden"], cfg["inter"], cfg["filter"]
     heads, dk = cfg["heads"], cfg["hidden"] // cfg["heads"]
     b = _Builder(seed)
-    b.add("sid", b.normal((n_vocab, H), H ** -0.5))
+    n_spk, gin = cfg.get("n_speakers", 1), cfg.get("gin", 0)
+    if n_spk > 1:
+        # a real `sid` graph input exists, so the exporter keeps the embedding tables' own names
+        b.m.inputs = ["input", "input_lengths", "scales", "sid"]
+        b.add("enc_p.emb.weight", b.normal((n_vocab, H), H ** -0.5))
+        b.add("emb_g.weight", b.normal((n_spk, gin), 1.0))
+    else:
+        b.add("sid", b.normal((n_vocab, H), H ** -0.5))
     # ---- text encoder (attentions.py:60-74)
     for l in range(cfg["layers"]):
         p = f"enc_p.encoder.attn_layers.{l}"
@@ -146,6 +162,8 @@ def build(arch: str = "medium", seed: int = 1234, n_vocab: int = 256) -> onnx_wi
         dds(f"dp.flows.{f}.convs")
         b.conv(f"dp.flows.{f}.proj", 29, H, 1, std=0.05)
     b.conv("dp.pre", H, H, 1)
+    if n_spk > 1:
+        b.conv("dp.cond", H, gin, 1, gain=0.25)
     b.conv("dp.proj", H, H, 1)
     dds("dp.convs")
     # Sub(z, m) -> Mul(., exp(-logs)) : the only trace dp.flows.0.logs leaves in an export
@@ -159,6 +177,8 @@ def build(arch: str = "medium", seed: int = 1234, n_vocab: int = 256) -> onnx_wi
     for f in (0, 2, 4, 6):
         p = f"flow.flows.{f}"
         b.conv(p + ".pre", H, inter // 2, 1)
+        if n_spk > 1:   # weight-normed like the in/res_skip layers -> constant-folded to an anonymous tensor
+            b.conv(f"{p}.enc.cond_layer", 2 * H * 4, gin, 1, anonymous=True, gain=0.25)
         for i in range(4):
             b.conv(f"{p}.enc.in_layers.{i}", 2 * H, H, 5, pad=2, anonymous=True, gain=2.0)
             b.conv(f"{p}.enc.res_skip_layers.{i}", 2 * H if i < 3 else H, H, 1, anonymous=True, gain=2.0)
@@ -166,6 +186,8 @@ def build(arch: str = "medium", seed: int = 1234, n_vocab: int = 256) -> onnx_wi
     # ---- generator (models.py:299-368)
     C = cfg["up_initial"]
     b.conv("dec.conv_pre", C, inter, 7, pad=3)
+    if n_spk > 1:
+        b.conv("dec.cond", C, gin, 1, gain=0.25)
     nk = len(cfg["rb_kernels"])
     for i, (u, k) in enumerate(zip(cfg["up_rates"], cfg["up_kernels"])):
         b.conv(f"dec.ups.{i}", C // 2, C, k, transpose=True, stride=u, pad=(k - u) // 2, gain=2.0)
@@ -184,6 +206,7 @@ def build(arch: str = "medium", seed: int = 1234, n_vocab: int = 256) -> onnx_wi
 
 
 def voice_config(arch: str, n_vocab: int = 256) -> dict:
+    n_spk = ARCHS[arch].get("n_speakers", 1)
     """The `.onnx.json` twin (fields parsed at /root/reference/src/cpp/piper.cpp:47-214)."""
     symbols = ["_", "^", "$", " "] + [chr(0x61 + i) for i in range(26)] + [chr(0x250 + i) for i in range(96)]
     id_map = {s: [i] for i, s in enumerate(symbols[:n_vocab])}
@@ -195,8 +218,8 @@ def voice_config(arch: str, n_vocab: int = 256) -> dict:
         "phoneme_map": {},
         "phoneme_id_map": id_map,
         "num_symbols": n_vocab,
-        "num_speakers": 1,
-        "speaker_id_map": {},
+        "num_speakers": n_spk,
+        "speaker_id_map": {f"speaker{i}": i for i in range(n_spk)} if n_spk > 1 else {},
     }
 
 

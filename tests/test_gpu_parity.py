@@ -52,7 +52,7 @@ def test_engine_matches_reference_golden(name):
     voice, _ = _pair(str(g["voice"]))
     voice.set_debug(True)
     audio, _ = voice.synthesize(g["ids"], g["scales"], g["eps_dp"] if "eps_dp" in g else None,
-                                g["eps_z"] if "eps_z" in g else None)
+                                g["eps_z"] if "eps_z" in g else None, sid=int(g["sid"]) if "sid" in g else None)
     cum = voice.tap("cum")[0]
     voice.set_debug(False)
     w_ceil = np.diff(np.concatenate([[0], cum])).astype(np.int32)
@@ -263,3 +263,36 @@ def test_cpp_shim_test_program():
     with wave.open(out) as w:
         assert w.getframerate() == 16000 and w.getnchannels() == 1 and w.getsampwidth() == 2
         assert w.getnframes() % 256 == 0 and 100 * 256 <= w.getnframes() <= 250 * 256   # ~150-170 frames for this line
+
+
+@pytest.mark.parametrize("tag,n_ph", [("synthetic:tiny-ms:1234", 30), ("synthetic:medium-ms:1234", 64)])
+def test_multi_speaker_conditioning(tag, n_ph):
+    """sid -> emb_g -> dp.cond, WN cond_layer (per layer slice), dec.cond."""
+    voice, orc = _pair(tag)
+    assert voice.info.n_speakers == orc.s.n_speakers > 1 and voice.info.gin == orc.s.gin
+    ids = voicegen.benchmark_ids(n_ph, seed=12)
+    eps_dp, eps_z = _noise(orc.s.inter, len(ids), 5)
+    scales = (0.667, 1.0, 0.8)
+    outs = {}
+    for sid in (0, orc.s.n_speakers - 1):
+        ref = orc.infer(ids, scales, eps_dp, eps_z, sid=sid)
+        out, _ = voice.synthesize(ids, scales, eps_dp, eps_z, sid=sid)
+        assert out.shape == ref.shape and np.abs(out - ref).max() <= TOL, sid
+        outs[sid] = out
+    a, b = outs.values()
+    assert a.shape != b.shape or np.abs(a - b).max() > 1e-2, "speakers must actually differ"
+    # batch with one speaker per item (and the streaming decode half sees the speaker too)
+    sids = [1, 0, orc.s.n_speakers - 1]
+    voice.set_speakers(sids)
+    zs = 6 * len(ids) + 16
+    rng = np.random.default_rng(9)
+    eps_z3 = rng.standard_normal((3, orc.s.inter, zs)).astype(np.float32)
+    eps_dp3 = [rng.standard_normal((2, len(ids))).astype(np.float32) for _ in range(3)]
+    batch, _ = voice.synthesize_batch([ids] * 3, scales, eps_dp3, eps_z3)
+    for bi, sid in enumerate(sids):
+        ref = orc.infer(ids, scales, eps_dp3[bi], eps_z3[bi], sid=sid)
+        assert batch[bi].shape == ref.shape and np.abs(batch[bi] - ref).max() <= TOL, (bi, sid)
+    voice.set_speakers([])
+    from piper_b200._lib import PiperB200Error
+    with pytest.raises(PiperB200Error, match="speaker id"):
+        voice.synthesize(ids, sid=orc.s.n_speakers)

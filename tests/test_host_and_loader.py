@@ -95,6 +95,17 @@ def test_cpp_loader_real_voice(lib_built):
     assert 4.9e6 < d["n_params"] < 5.1e6
 
 
+def test_cpp_loader_multi_speaker(lib_built):
+    from oracle.voice_loader import load_voice
+    from piper_b200 import engine
+    path = voicegen.cached_voice("tiny-ms")
+    spec, w, _ = load_voice(path)
+    d = engine.describe(path)
+    H = spec.hidden
+    assert (d["n_speakers"], d["gin"]) == (spec.n_speakers, spec.gin) == (5, 48)
+    assert d["cond_rows"] == H + len(spec.flow_layers) * 2 * H * spec.wn_layers + spec.up_initial
+
+
 def test_cpp_loader_errors(lib_built, tmp_path):
     from piper_b200 import engine
     from piper_b200._lib import PiperB200Error

@@ -34,7 +34,7 @@ def test_oracle_matches_golden(name):
     assert weights_digest(w) == str(g["weights_sha256"]), "voice weights differ from the ones the golden was minted on"
     dump = {}
     o = orc.infer(g["ids"], g["scales"], g["eps_dp"] if "eps_dp" in g else None,
-                  g["eps_z"] if "eps_z" in g else None, dump=dump)
+                  g["eps_z"] if "eps_z" in g else None, dump=dump, sid=int(g["sid"]) if "sid" in g else None)
     assert np.array_equal(dump["w_ceil"].numpy().astype(np.int32), g["w_ceil"])   # durations: exact
     assert o.shape == g["audio"].shape
     assert np.abs(dump["z"].numpy() - g["z"]).max() <= 1e-3
@@ -61,7 +61,8 @@ def test_oracle_matches_survey_anchors():
 @pytest.mark.needs_reference
 @pytest.mark.parametrize("tag,n_ph,scales", [("real:test_voice", 0, (0.667, 1.0, 0.8)),
                                              ("synthetic:tiny:1234", 40, (0.667, 1.3, 0.8)),
-                                             ("synthetic:tiny-high:1234", 12, (0.3, 0.8, 1.0))])
+                                             ("synthetic:tiny-high:1234", 12, (0.3, 0.8, 1.0)),
+                                             ("synthetic:tiny-ms:1234", 25, (0.667, 1.0, 0.8))])
 def test_oracle_matches_reference_source(tag, n_ph, scales):
     from oracle import ref_bridge
     if not ref_bridge.available():
@@ -75,9 +76,10 @@ def test_oracle_matches_reference_source(tag, n_ph, scales):
     rng = np.random.default_rng(11)
     eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
     eps_z = rng.standard_normal((orc.s.inter, 6 * len(ids))).astype(np.float32)
+    sid = 2 if orc.s.n_speakers > 1 else None             # multi-speaker: emb_g / dp.cond / WN cond_layer / dec.cond
     dump = {}
-    o = orc.infer(ids, scales, eps_dp, eps_z, dump=dump)
-    r = ref_bridge.reference_infer(net, ids, scales, eps_dp, eps_z)
+    o = orc.infer(ids, scales, eps_dp, eps_z, dump=dump, sid=sid)
+    r = ref_bridge.reference_infer(net, ids, scales, eps_dp, eps_z, sid=sid)
     assert np.array_equal(dump["w_ceil"].numpy(), r["w_ceil"])
     assert np.abs(dump["z_p"].numpy() - r["z_p"]).max() < 1e-4
     assert np.abs(dump["z"].numpy() - r["z"]).max() < 1e-3
