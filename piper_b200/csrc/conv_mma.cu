@@ -153,6 +153,88 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 __device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
 
+template <bool TF32, bool ACC>
+__device__ __forceinline__ void mma_ss_imm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  // accumulate flag as a compile-time predicate: no setp in the issue loop
+  if (TF32) {
+    if (ACC) asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+  } else {
+    if (ACC) asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+    else asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
+  }
+}
+
+// One lane of a converged warp (elect.sync).  The MMA / TMA issue loops are executed by the WHOLE warp with only the
+// instruction itself predicated on the elected lane: inside an `if (lane == 0)` region the compiler has to build the
+// 64-bit descriptors in vector registers and move them to the uniform register file (R2UR) for every UTCHMMA, which
+// measured at ~200 cycles per instruction; in warp-uniform code they live in uniform registers (tools/mma_bench.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}\n"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
+// ---- lean issue path --------------------------------------------------------------------------------------------
+// Measured (tools/mma_bench.py): a tcgen05.mma retires in ~16-100 cycles (N = 32..256) but every instruction the
+// single issuing thread executes between two MMAs costs ~5-6 cycles of dependent latency, so ~30 instructions of
+// descriptor / index arithmetic per MMA throttled the first versions of this kernel to one MMA per ~200 cycles.
+// The loop below spends ~3 instructions per MMA: descriptors are (constant hi word, running lo word) pairs
+// assembled inside the asm statement, the accumulate flag is a predicate set once per k-step.
+template <bool TF32>
+__device__ __forceinline__ void mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  constexpr uint32_t HI = (128u >> 4) | (1u << 14);     // SBO = 128 bytes, descriptor version 1
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(HI)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(HI)
+        : "memory");
+  }
+}
+
+// All k-steps of one tap for up to two row halves.  acc_main / acc_corr: 0 => the first k-step overwrites that
+// accumulator.  Descriptor lo words advance by a_step / w_step (16-byte units) per k-step.
+template <bool TF32, int MH>
+__device__ __forceinline__ void issue_tap(uint32_t ah, uint32_t al, uint32_t wh, uint32_t wl, int ksteps, uint32_t a_step,
+                                          uint32_t w_step, bool two_halves, uint32_t dm, uint32_t dc, uint32_t mh_cols,
+                                          uint32_t idesc, uint32_t acc_main, uint32_t acc_corr) {
+  // Executed by the WHOLE (converged) MMA warp: all operands are warp-uniform, so the compiler keeps them in
+  // uniform registers, which is what UTCHMMA reads; only the instruction itself is predicated on the elected lane.
+#pragma unroll 1
+  for (int kb = 0; kb < ksteps; ++kb) {
+    if (elect_one()) {
+      mma_lo<TF32>(dm, ah, wh, idesc, acc_main);
+      mma_lo<TF32>(dc, ah, wl, idesc, acc_corr);
+      mma_lo<TF32>(dc, al, wh, idesc, 1u);
+    }
+    if (MH == 2 && two_halves) {
+      if (elect_one()) {
+        mma_lo<TF32>(dm + mh_cols, ah + 128u, wh, idesc, acc_main);
+        mma_lo<TF32>(dc + mh_cols, ah + 128u, wl, idesc, acc_corr);
+        mma_lo<TF32>(dc + mh_cols, al + 128u, wh, idesc, 1u);
+      }
+    }
+    __syncwarp();
+    acc_main = 1u;
+    acc_corr = 1u;
+    ah += a_step; al += a_step; wh += w_step; wl += w_step;
+  }
+}
+
 struct Barriers {
   uint64_t a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS], w_full[MAX_W_SLOTS], w_empty[MAX_W_SLOTS], d_full;
 };
@@ -468,7 +550,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
   __shared__ __align__(8) PBarriers bar;
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // warp index through a shuffle ("canonical warp index"): the role branches below are then provably warp-uniform and
+  // the MMA warp's operands can live in uniform registers
+  const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int KC = a.kc, R = a.stage_rows, RS = a.raw_stride;
   const int raw_bytes = KC * RS * 4, a_part = KC * R * ES, w_part = KC * a.n_tile * ES;
   uint8_t* RAW_ring = smem;
@@ -555,56 +639,57 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
       }
     }
   } else if (warp == 2) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issue
+    {
+      // ------------------------------------------------------------------ MMA issue: the WHOLE warp runs the loop,
+      // only the tcgen05 instructions are predicated on one elected lane (see issue_tap)
+      const uint32_t tmem_du = __shfl_sync(0xffffffffu, tmem_d, 0);
       const uint32_t a_lbo = (uint32_t)R * 16, w_lbo = (uint32_t)a.n_tile * 16;
       const uint32_t idesc = make_idesc(TF32, 128, a.n_tile);
+      const uint32_t a_step = 2u * (uint32_t)R, w_step = 2u * (uint32_t)a.n_tile;   // 16-byte units per k-step
       uint32_t a_it = 0, w_it = 0, t_it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         int nt, b, t0, L, Lq;
-        if (!decode(tile, nt, b, t0, L, Lq)) continue;
+        bool ok = decode(tile, nt, b, t0, L, Lq);
+        Lq = __shfl_sync(0xffffffffu, Lq, 0);                      // loaded from global: make its uniformity explicit
+        ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+        if (!ok) continue;
         const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
         const int ts = t_it % t_slots;
         if (t_it >= (uint32_t)t_slots) mbar_wait(&bar.t_empty[ts], ((t_it / t_slots) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
+        const uint32_t d_set = tmem_du + (uint32_t)(ts * set_cols);
         uint32_t started = 0;
         int u = 0;
         for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
           const int as = a_it % P_A_SLOTS;
           mbar_wait(&bar.a_full[as], (a_it / P_A_SLOTS) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          const uint32_t a_hi = smem_u32(A_ring + size_t(as) * 2 * a_part), a_lo = a_hi + a_part;
+          const uint32_t a_hi = smem_u32(A_ring + size_t(as) * 2 * a_part);
+          const uint32_t ah_base = desc_lo(a_hi, a_lbo), al_base = desc_lo(a_hi + a_part, a_lbo);
           for (int j = 0; j < a.k; ++j, ++u, ++w_it) {
             const int ws = w_it % P_W_SLOTS;
             mbar_wait(&bar.w_full[ws], (w_it / P_W_SLOTS) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t w_hi = smem_u32(W_ring + size_t(ws) * unit_bytes), w_lo = w_hi + w_part;
-            const uint32_t shift = (uint32_t)(j * a.dil) * 16;
             const int chain = (u * a.chains) / n_units;
             const int corr = a.sep_corr ? a.chains : chain;
-            for (int kb = 0; kb < KC / KSTEP; ++kb) {
-              const uint64_t wh = make_desc(w_hi + 2 * kb * w_lbo, w_lbo, 128);
-              const uint64_t wl = make_desc(w_lo + 2 * kb * w_lbo, w_lbo, 128);
-              for (int mh = 0; mh < mh_live; ++mh) {
-                const uint32_t row_off = shift + (uint32_t)mh * 128 * 16;
-                const uint64_t ah = make_desc(a_hi + 2 * kb * a_lbo + row_off, a_lbo, 128);
-                const uint64_t al = make_desc(a_lo + 2 * kb * a_lbo + row_off, a_lbo, 128);
-                const uint32_t dm = d_set + (uint32_t)(mh * a.mh_stride + chain * a.acc_cols);
-                const uint32_t dc = d_set + (uint32_t)(mh * a.mh_stride + corr * a.acc_cols);
-                const uint32_t bm = 1u << (mh * 8 + chain), bc = 1u << (mh * 8 + corr);
-                mma_ss<TF32>(dm, ah, wh, idesc, (started & bm) != 0);
-                started |= bm;
-                mma_ss<TF32>(dc, ah, wl, idesc, (started & bc) != 0);
-                started |= bc;
-                mma_ss<TF32>(dc, al, wh, idesc, true);
-              }
-            }
-            mma_commit(&bar.w_empty[ws]);
+            const uint32_t bm = 1u << chain, bc = 1u << corr;
+            const uint32_t acc_m = (started & bm) ? 1u : 0u;
+            started |= bm;
+            const uint32_t acc_c = (started & bc) ? 1u : 0u;
+            started |= bc;
+            const uint32_t wh = desc_lo(smem_u32(W_ring + size_t(ws) * unit_bytes), w_lbo);
+            const uint32_t row = (uint32_t)(j * a.dil);
+            issue_tap<TF32, MH>(ah_base + row, al_base + row, wh, wh + ((uint32_t)w_part >> 4), KC / KSTEP, a_step, w_step,
+                                mh_live == 2, d_set + (uint32_t)(chain * a.acc_cols), d_set + (uint32_t)(corr * a.acc_cols),
+                                (uint32_t)a.mh_stride, idesc, acc_m, acc_c);
+            if (elect_one()) mma_commit(&bar.w_empty[ws]);
+            __syncwarp();
           }
-          mma_commit(&bar.a_empty[as]);
+          if (elect_one()) mma_commit(&bar.a_empty[as]);
+          __syncwarp();
         }
-        mma_commit(&bar.t_full[ts]);
+        if (elect_one()) mma_commit(&bar.t_full[ts]);
+        __syncwarp();
         ++t_it;
       }
     }
@@ -788,33 +873,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"((uint32_t)a.tmem_cols)
                  : "memory");
   }
-}
-
-template <bool TF32, bool ACC>
-__device__ __forceinline__ void mma_ss_imm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-  // accumulate flag as a compile-time predicate: no setp in the issue loop
-  if (TF32) {
-    if (ACC) asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
-    else asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
-  } else {
-    if (ACC) asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
-    else asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc) : "memory");
-  }
-}
-
-// One lane of a converged warp (elect.sync).  The MMA / TMA issue loops are executed by the WHOLE warp with only the
-// instruction itself predicated on the elected lane: inside an `if (lane == 0)` region the compiler has to build the
-// 64-bit descriptors in vector registers and move them to the uniform register file (R2UR) for every UTCHMMA, which
-// measured at ~200 cycles per instruction; in warp-uniform code they live in uniform registers (tools/mma_bench.py).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, %1;\n\t"
-      "@px mov.s32 %0, 1;\n\t}\n"
-      : "+r"(pred)
-      : "r"(0xFFFFFFFFu));
-  return pred != 0;
 }
 
 // (developer microbenchmark below; its findings are summarised in DESIGN.md)
