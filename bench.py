@@ -312,6 +312,7 @@ def run_engine(args):
         flat, counts, _ = voice.synthesize_batch(one, SCALES, seed=1, copy=False)
         lat.append(time.perf_counter() - t); n1 = int(counts.sum())
     lat_s = statistics.median(lat)
+    b1_stage = voice.stage_times()
     rtf = lat_s / (n1 / 22050.0)
 
     cpu_baseline = None
@@ -345,7 +346,8 @@ def run_engine(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "batch1": {"latency_ms": lat_s * 1e3, "rtf": rtf, "samples": n1, "samples_per_s": n1 / lat_s},
+            "batch1": {"latency_ms": lat_s * 1e3, "rtf": rtf, "samples": n1, "samples_per_s": n1 / lat_s,
+                       "stage_ms": dict(zip(["text_encoder", "duration_predictor", "host_length_roundtrip", "expand_flow", "generator"], b1_stage))},
         }), flush=True)
     voice.close()
     if use_dist:

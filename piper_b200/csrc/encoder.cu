@@ -30,7 +30,7 @@ __global__ void embed_kernel(const int* __restrict__ ids, int ids_pitch, const f
 // online softmax; within a chunk every K element read feeds ATT_QPW score FMAs and every V element read feeds ATT_QPW
 // accumulator FMAs (the probability of key jj for query qq comes by warp shuffle).  The banded relative-value term
 // touches at most 2*window+1 keys per query and is added separately.  dk <= 128 (lane owns d = lane + 32*r, r < 4).
-constexpr int ATT_QPW = 2;
+constexpr int ATT_QPW = 4;
 constexpr int ATT_Q = 8 * ATT_QPW;
 constexpr int ATT_MAXR = 4;
 
