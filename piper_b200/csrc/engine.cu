@@ -414,6 +414,7 @@ void Engine::run_front() {
   launch_durations(z2.offset_channels(lw_ch), voice_.ea_m[0], voice_.ea_scale[0], scales_[1],
                    have_override_ ? override_d_.as<int>() : nullptr, Tp, cum_d_.as<int>(), Tp, ylen_d_.as<int>(),
                    logw_d_.as<float>(), len, B, T, stream_);
+  CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
   // ---- the one data-dependent host round trip: output lengths size everything downstream
   misc_pin_.ensure(size_t(B) * 32);
@@ -581,6 +582,7 @@ void Engine::run_back() {
   if (debug_) save_tap("z", z, I, ylen_h_.data(), 1);
   CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
   run_generator();
+  CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(ev_[5], stream_));
 }
 
