@@ -1038,7 +1038,7 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
   if (g_mma_persist && persist_cfg(a, p, mt, kc, rows, rs, t_slots, smem)) {
     const int tpi = (max_len + mt - 1) / mt;
     const long long total = (long long)tpi * B * p.n_tiles;
-    if (total >= 2 * 148) {
+    if (total >= 148) {
       a.kc = kc; a.stage_rows = rows; a.raw_stride = rs; a.t_slots = t_slots;
       a.chains = std::min(p.chains, (a.ci / kc) * a.k);
       const int n_acc = p.chains + (p.sep_corr ? 1 : 0);
