@@ -835,29 +835,47 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
           }
           continue;
         }
+        // the switch is OUTSIDE the unrolled loops: one compact 16-wide loop per epilogue kind keeps the epilogue's
+        // instruction footprint small (15 warps in 5 roles share the instruction caches)
+        switch (a.epi) {
+          case EPI_RELU:
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int row = row0 + i;
-          const float val = v[i];
-          switch (a.epi) {
-            case EPI_BIAS: case EPI_RES: case EPI_SUBFROM: yb[(long long)row * a.y.cs + t] = val; break;
-            case EPI_RELU: yb[(long long)row * a.y.cs + t] = fmaxf(val, 0.f); break;
-            case EPI_WN:
-              if (row < a.split) {
-                yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + val;
-              } else {
-                float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
-                *o = a.first ? val : *o + val;
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = fmaxf(v[i], 0.f);
+            break;
+          case EPI_WN:
+            if (row0 + 16 <= a.split) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                yb[(long long)(row0 + i) * a.y.cs + t] = rb[(long long)(row0 + i) * a.r.cs + t] + v[i];
+            } else if (row0 >= a.split) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float* o = y2b + (long long)(row0 + i - a.split) * a.y2.cs + t;
+                *o = a.first ? v[i] : *o + v[i];
               }
-              break;
-            case EPI_UPSAMPLE: {
+            } else {
+              for (int i = 0; i < 16; ++i) {
+                const int row = row0 + i;
+                if (row < a.split) yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + v[i];
+                else {
+                  float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
+                  *o = a.first ? v[i] : *o + v[i];
+                }
+              }
+            }
+            break;
+          case EPI_UPSAMPLE:                              // generic stride (the common ones took the vector path above)
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + i;
               const int co = row / a.up, phi = row - co * a.up;
               const int to = t * a.up + phi - a.up_pad;
-              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = val;
-              break;
+              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = v[i];
             }
-            default: break;
-          }
+            break;
+          default:                                        // EPI_BIAS, and EPI_RES / EPI_SUBFROM after the residual fold
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i];
+            break;
         }
       }
       if (work == 0) {                                   // (cannot happen: n_chunks >= 1) keep the protocol total
