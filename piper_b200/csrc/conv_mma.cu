@@ -445,39 +445,52 @@ __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs
             yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = tanhf(v[i]) * sigmoid_acc(v[i + 1]);
           continue;
         }
+        // one compact loop per epilogue kind (the switch stays outside the unrolled loops: smaller instruction footprint)
+        switch (a.epi) {
+          case EPI_RELU:
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int row = row0 + i;
-          const float val = v[i];
-          switch (a.epi) {
-            case EPI_BIAS: yb[(long long)row * a.y.cs + t] = val; break;
-            case EPI_RELU: yb[(long long)row * a.y.cs + t] = fmaxf(val, 0.f); break;
-            case EPI_RES: yb[(long long)row * a.y.cs + t] = val + rb[(long long)row * a.r.cs + t]; break;
-            case EPI_WN:
-              if (row < a.split) {
-                yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + val;
-              } else {
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = fmaxf(v[i], 0.f);
+            break;
+          case EPI_RES:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i] + rb[(long long)(row0 + i) * a.r.cs + t];
+            break;
+          case EPI_SUBFROM:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = rb[(long long)(row0 + i) * a.r.cs + t] - v[i];
+            break;
+          case EPI_WN:
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + i;
+              if (row < a.split) yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + v[i];
+              else {
                 float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
-                *o = a.first ? val : *o + val;
+                *o = a.first ? v[i] : *o + v[i];
               }
-              break;
-            case EPI_SUBFROM: yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] - val; break;
-            case EPI_UPSAMPLE: {
+            }
+            break;
+          case EPI_UPSAMPLE:
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + i;
               const int co = row / a.up, phi = row - co * a.up;
               const int to = t * a.up + phi - a.up_pad;
-              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = val;
-              break;
+              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = v[i];
             }
-            case EPI_MRF: {
-              const float v2 = val + rb[(long long)row * a.r.cs + t];
-              float* o = y2b + (long long)row * a.y2.cs + t;
+            break;
+          case EPI_MRF:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float v2 = v[i] + rb[(long long)(row0 + i) * a.r.cs + t];
+              float* o = y2b + (long long)(row0 + i) * a.y2.cs + t;
               if (a.mrf == 0) *o = v2;
               else if (a.mrf == 1) *o = *o + v2;
               else *o = (*o + v2) / (float)a.mrf_n;
-              break;
             }
-            default: break;
-          }
+            break;
+          default:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i];
+            break;
         }
       }
     }
