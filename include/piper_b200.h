@@ -139,6 +139,11 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
                        const float* bias, int32_t co, int32_t k, int32_t dil, float pre_slope, const float* resid,
                        float* y);
 
+/* Host-only: the tensor-core tiling chosen for a layer shape.  out = {supported, rows per tile (MT), channel chunk,
+ * staged rows, output rows per tile, number of row tiles, TMEM columns per accumulator, TMEM columns allocated,
+ * activation slots, weight slots, accumulators per row half, dynamic shared memory bytes}. */
+int pb200_debug_mma_plan(int32_t ci, int32_t rows, int32_t k, int32_t dil, int32_t tf32, int32_t out[12]);
+
 /* Developer microbenchmark: issue `iters` tcgen05.mma (M=128, given N, bf16 or tf32, no-swizzle K-major smem operands)
  * rotating over n_acc accumulators; cycles[0] = issue time, cycles[1] = until the last one retired. */
 int pb200_debug_mma_bench(int32_t N, int32_t tf32, int32_t n_acc, int32_t iters, int32_t shift, uint64_t* cycles);

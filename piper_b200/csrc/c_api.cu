@@ -279,6 +279,17 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
   });
 }
 
+int pb200_debug_mma_plan(int32_t ci, int32_t rows, int32_t k, int32_t dil, int32_t tf32, int32_t out[12]) {
+  return guarded([&] {
+    if (!out) throw std::runtime_error("pb200_debug_mma_plan: null argument");
+    pb200::MmaPlan p;
+    const bool ok = pb200::mma_plan(ci, rows, k, dil, tf32 != 0, p);
+    const int32_t v[12] = {ok, p.mt, p.kc, p.stage_rows, p.n_tile, p.n_tiles, p.acc_cols, p.tmem_cols, p.a_slots, p.w_slots,
+                           p.chains + (p.sep_corr ? 1 : 0), int32_t(p.smem)};
+    for (int i = 0; i < 12; ++i) out[i] = v[i];
+  });
+}
+
 int pb200_debug_mma_bench(int32_t N, int32_t tf32, int32_t n_acc, int32_t iters, int32_t shift, uint64_t* cycles) {
   return guarded([&] {
     unsigned long long o[2] = {0, 0};
