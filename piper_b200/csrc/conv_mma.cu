@@ -152,6 +152,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 __device__ __forceinline__ float sigmoid_acc(float v) { return 1.f / (1.f + expf(-v)); }
+// WaveNet gate tanh(a) * sigmoid(b) (commons.py:99-106) as ONE out-of-line copy: tanhf / expf expand to ~100 instructions
+// and the epilogues call it 8 times per 16-row chunk; inlined, that alone was several KB of the kernel's hot path.
+__device__ __noinline__ float wn_gate(float a, float b) { return tanhf(a) * sigmoid_acc(b); }
 
 template <bool TF32, bool ACC>
 __device__ __forceinline__ void mma_ss_imm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
@@ -442,7 +445,7 @@ __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs
         if (a.epi == EPI_GATE) {
 #pragma unroll
           for (int i = 0; i < 16; i += 2)
-            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = tanhf(v[i]) * sigmoid_acc(v[i + 1]);
+            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = wn_gate(v[i], v[i + 1]);
           continue;
         }
         // one compact loop per epilogue kind (the switch stays outside the unrolled loops: smaller instruction footprint)
@@ -812,7 +815,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
         if (a.epi == EPI_GATE) {
 #pragma unroll
           for (int i = 0; i < 16; i += 2)
-            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = tanhf(v[i]) * sigmoid_acc(v[i + 1]);
+            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = wn_gate(v[i], v[i + 1]);
           continue;
         }
         if (a.epi == EPI_RES || a.epi == EPI_MRF || a.epi == EPI_SUBFROM) {
@@ -834,17 +837,21 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
           continue;
         }
         if (a.epi == EPI_MRF) {
-          float ov[16];
-          if (a.mrf != 0) {
+          if (a.mrf == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = v[i];
+          } else {
+            float ov[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) ov[i] = y2b[(long long)(row0 + i) * a.y2.cs + t];
-          }
+            const float inv_n = (float)a.mrf_n;
+            if (a.mrf == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float* o = y2b + (long long)(row0 + i) * a.y2.cs + t;
-            if (a.mrf == 0) *o = v[i];
-            else if (a.mrf == 1) *o = ov[i] + v[i];
-            else *o = (ov[i] + v[i]) / (float)a.mrf_n;
+              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = ov[i] + v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = (ov[i] + v[i]) / inv_n;
+            }
           }
           continue;
         }
