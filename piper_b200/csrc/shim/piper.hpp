@@ -27,71 +27,77 @@ struct pb200_voice;
 
 namespace piper {
 
-typedef int64_t SpeakerId;
-typedef char32_t Phoneme;     // piper-phonemize: UTF-32 codepoint
-typedef int64_t PhonemeId;    // backs an int64 tensor (piper.cpp:351-355)
+// ---- scalar types ------------------------------------------------------------------------------------------------
+using SpeakerId = int64_t;   // row of emb_g; the graph's optional `sid` input
+using Phoneme = char32_t;    // one UTF-32 codepoint (piper-phonemize's Phoneme)
+using PhonemeId = int64_t;   // the id vector is handed to the engine as int64 without conversion
 using json = minijson::Value;
 
+// ---- host-side phonemisation hook --------------------------------------------------------------------------------
 struct eSpeakConfig {
-  std::string voice = "en-us";
+  std::string voice = "en-us";   // espeak-ng voice name from "espeak": {"voice": ...}
 };
 
-// text (UTF-8), espeak voice -> one phoneme vector per sentence
+// Turns UTF-8 text into one phoneme vector per sentence.  espeak-ng lives on the host; a program that links
+// piper-phonemize assigns its phonemize_eSpeak here.
 using Phonemizer =
-    std::function<void(const std::string&, const eSpeakConfig&, std::vector<std::vector<Phoneme>>&)>;
+    std::function<void(const std::string& /*text*/, const eSpeakConfig&, std::vector<std::vector<Phoneme>>& /*sentences*/)>;
 
 struct PiperConfig {
-  std::string eSpeakDataPath;
+  Phonemizer phonemizer;                            // unset: textToAudio throws, phonemesToAudio still works
+  std::string eSpeakDataPath;                       // kept for source compatibility with callers that set it
+  std::optional<std::string> tashkeelModelPath;     // idem (libtashkeel is not part of this build)
   bool useESpeak = true;
   bool useTashkeel = false;
-  std::optional<std::string> tashkeelModelPath;
-  Phonemizer phonemizer;  // host hook (espeak-ng); unset => textToAudio throws, phonemesToAudio still works
 };
 
+// ---- what the voice JSON describes -------------------------------------------------------------------------------
 enum PhonemeType { eSpeakPhonemes, TextPhonemes };
 
 struct PhonemizeConfig {
-  PhonemeType phonemeType = eSpeakPhonemes;
-  std::optional<std::map<Phoneme, std::vector<Phoneme>>> phonemeMap;
-  std::map<Phoneme, std::vector<PhonemeId>> phonemeIdMap;
-  PhonemeId idPad = 0;
-  PhonemeId idBos = 1;
-  PhonemeId idEos = 2;
-  bool interspersePad = true;
+  std::map<Phoneme, std::vector<PhonemeId>> phonemeIdMap;               // "phoneme_id_map" (required)
+  std::optional<std::map<Phoneme, std::vector<Phoneme>>> phonemeMap;    // "phoneme_map" (rarely used)
+  PhonemeType phonemeType = eSpeakPhonemes;                             // "phoneme_type": "text" selects codepoints
   eSpeakConfig eSpeak;
+  // id layout produced by phonemes_to_ids: BOS, PAD, (ids, PAD)*, EOS
+  PhonemeId idPad = 0, idBos = 1, idEos = 2;
+  bool interspersePad = true;
 };
 
 struct SynthesisConfig {
+  // "inference" block: the three entries of the graph's `scales` input, in that order
   float noiseScale = 0.667f;
   float lengthScale = 1.0f;
   float noiseW = 0.8f;
-  int sampleRate = 22050;
-  int sampleWidth = 2;
+  // audio format of the produced PCM
+  int sampleRate = 22050;   // "audio": {"sample_rate": ...}
+  int sampleWidth = 2;      // bytes per sample
   int channels = 1;
-  std::optional<SpeakerId> speakerId;
-  float sentenceSilenceSeconds = 0.2f;
-  std::optional<std::map<Phoneme, float>> phonemeSilenceSeconds;
+  std::optional<SpeakerId> speakerId;                              // set for multi-speaker voices
+  std::optional<std::map<Phoneme, float>> phonemeSilenceSeconds;   // "phoneme_silence": split phrases, add silence
+  float sentenceSilenceSeconds = 0.2f;                             // appended after every sentence
 };
 
 struct ModelConfig {
-  int numSpeakers = 1;
-  std::optional<std::map<std::string, SpeakerId>> speakerIdMap;
+  std::optional<std::map<std::string, SpeakerId>> speakerIdMap;   // "speaker_id_map"
+  int numSpeakers = 1;                                            // "num_speakers"
 };
 
+// ---- the engine handle (where the reference keeps Ort::Session / Ort::Env / Ort::SessionOptions) -----------------
 struct ModelSession {
   pb200_voice* engine = nullptr;
   int device = 0;
-  uint64_t noiseSeed = 0x9E3779B97F4A7C15ull;  // advanced per call: the reference's noise is unseeded
+  uint64_t noiseSeed = 0x9E3779B97F4A7C15ull;   // advanced per call: the reference's in-graph noise is unseeded
   ModelSession() = default;
+  ~ModelSession();
   ModelSession(const ModelSession&) = delete;
   ModelSession& operator=(const ModelSession&) = delete;
-  ~ModelSession();
 };
 
 struct SynthesisResult {
-  double inferSeconds = 0;
-  double audioSeconds = 0;
-  double realTimeFactor = 0;
+  double inferSeconds = 0;     // wall time of the engine call(s)
+  double audioSeconds = 0;     // samples / sampleRate
+  double realTimeFactor = 0;   // inferSeconds / audioSeconds
 };
 
 struct Voice {
@@ -102,6 +108,7 @@ struct Voice {
   ModelSession session;
 };
 
+// ---- API ---------------------------------------------------------------------------------------------------------
 bool isSingleCodepoint(std::string s);
 Phoneme getCodepoint(std::string s);
 std::string getVersion();
