@@ -124,6 +124,9 @@ int pb200_stage_times(const pb200_voice* v, float ms[5]);
  * as JSON {"stage": {"launches", "ms", "bytes", "flops"}} with the algorithmic bytes/flops of SURVEY §8d. */
 int pb200_set_profile(pb200_voice* v, int32_t on);
 int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap);
+/* Same records un-aggregated: a JSON array with one entry per conv launch of the last call, in launch order
+ * (tag, tensor-core flag, microseconds, layer shape, algorithmic bytes / FLOP).  Fails if cap is too small. */
+int pb200_profile_read_launches(pb200_voice* v, char* buf, int64_t cap);
 
 /* Select which layer families run on the tcgen05 tensor cores (split precision): bit 0 = generator (bf16x3),
  * bit 1 = flow (tf32x3), bit 2 = text encoder (tf32x3), bit 3 = duration predictor (tf32x3); cleared bits use the fp32

@@ -51,6 +51,7 @@ SYMBOLS = {
     "pb200_stage_times": (C.c_int, [C.c_void_p, _p(C.c_float)]),
     "pb200_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "pb200_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "pb200_profile_read_launches": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "pb200_set_mma": (C.c_int, [C.c_void_p, C.c_int32]),
     "pb200_debug_conv1d": (C.c_int, [C.c_int32, _p(C.c_float), C.c_int32, C.c_int32, C.c_int32, _p(C.c_float),
                                      _p(C.c_float), C.c_int32, C.c_int32, C.c_int32, C.c_float, _p(C.c_float),

@@ -203,6 +203,16 @@ int pb200_profile_read(pb200_voice* v, char* buf, int64_t cap) {
   });
 }
 
+int pb200_profile_read_launches(pb200_voice* v, char* buf, int64_t cap) {
+  return guarded([&] {
+    if (!v || !buf || cap <= 0) throw std::runtime_error("pb200_profile_read_launches: bad argument");
+    const std::string s = v->engine.profile_launches_json();
+    if (int64_t(s.size()) >= cap) throw std::runtime_error("pb200_profile_read_launches: buffer too small");
+    std::memcpy(buf, s.data(), s.size());
+    buf[s.size()] = 0;
+  });
+}
+
 int pb200_set_mma(pb200_voice* v, int32_t on) {
   return guarded([&] {
     if (!v) throw std::runtime_error("pb200_set_mma: null argument");

@@ -1094,6 +1094,31 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
   // ---- one tile per CTA (small problems / latency regime)
   a.kc = p.kc; a.stage_rows = p.stage_rows; a.tmem_cols = p.tmem_cols;
   a.a_slots = p.a_slots; a.w_slots = p.w_slots;
+  size_t smem_bytes = p.smem;
+  // Experimental (PIPER_B200_SMALL=1, off by default): the occupancy-first plan gives small layers a single
+  // activation slot and a 16-channel chunk, i.e. a chain of ci/16 dependent load -> convert -> MMA -> commit round
+  // trips (~2 us each: the ~30 us floor of the small encoder / duration-predictor launches in
+  // profiles/r01_layer_report.txt).  With fewer than ~3 CTAs per SM in the grid there is nothing co-resident to hide
+  // that chain, so take the largest double-buffered chunk that fits instead.  The weight layout does not depend on kc.
+  static int g_small = -1;
+  if (g_small < 0) {
+    const char* e = std::getenv("PIPER_B200_SMALL");
+    g_small = e ? std::atoi(e) : 0;
+  }
+  if (g_small && p.a_slots == 1) {
+    const long long ctas = (long long)((max_len + p.mt - 1) / p.mt) * B * p.n_tiles;
+    if (ctas <= 3 * 148) {
+      const int es = p.tf32 ? 4 : 2, kstep = p.tf32 ? 8 : 16;
+      for (int kc = a.ci; kc > p.kc; kc -= kstep) {
+        if (a.ci % kc) continue;
+        const size_t bytes = size_t(2) * 2 * kc * p.stage_rows * es + size_t(p.w_slots) * 2 * kc * p.n_tile * es;
+        if (bytes <= (size_t(200) << 10)) {
+          a.kc = kc; a.a_slots = 2; smem_bytes = bytes;
+          break;
+        }
+      }
+    }
+  }
   // never more chains than weight units, or an accumulator would be read without ever being written
   a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);
   mt = p.mt;
@@ -1104,11 +1129,11 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
   }
   dim3 grid((max_len + mt - 1) / mt, B, p.n_tiles);
   if (p.tf32) {
-    if (mt == 256) conv_mma_kernel<true, 256><<<grid, MMA_THREADS, p.smem, st>>>(a);
-    else conv_mma_kernel<true, 128><<<grid, MMA_THREADS, p.smem, st>>>(a);
+    if (mt == 256) conv_mma_kernel<true, 256><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
+    else conv_mma_kernel<true, 128><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
   } else {
-    if (mt == 256) conv_mma_kernel<false, 256><<<grid, MMA_THREADS, p.smem, st>>>(a);
-    else conv_mma_kernel<false, 128><<<grid, MMA_THREADS, p.smem, st>>>(a);
+    if (mt == 256) conv_mma_kernel<false, 256><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
+    else conv_mma_kernel<false, 128><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
   }
   count_launch();
 }

@@ -135,6 +135,7 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   const double co = double(a.rows) / a.up, lin = len_sum, lout = len_sum * a.up;
   r.bytes = 4.0 * (lin * a.ci + lout * (a.epi == EPI_GATE ? co / 2 : co) + double(a.ci) * a.rows * a.k + a.rows);
   r.flops = 2.0 * lout * a.ci * co * a.k;
+  r.ci = a.ci; r.rows = a.rows; r.k = a.k; r.dil = a.dil; r.up = a.up; r.max_len = max_len; r.len_sum = len_sum;
   CUDA_CHECK(cudaEventRecord(r.e0, stream_));
   go();
   CUDA_CHECK(cudaEventRecord(r.e1, stream_));
@@ -166,6 +167,23 @@ std::string Engine::profile_json() {
     first = false;
   }
   return out + "}";
+}
+
+std::string Engine::profile_launches_json() {
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  std::string out = "[";
+  for (size_t i = 0; i < recs_.size(); ++i) {
+    const ProfRec& r = recs_[i];
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    char buf[320];
+    snprintf(buf, sizeof buf,
+             "%s{\"tag\":\"%s\",\"mma\":%d,\"us\":%.3f,\"ci\":%d,\"rows\":%d,\"k\":%d,\"dil\":%d,\"up\":%d,"
+             "\"max_len\":%d,\"len_sum\":%.0f,\"bytes\":%.0f,\"flops\":%.0f}",
+             i ? "," : "", r.tag, r.mma ? 1 : 0, ms * 1e3, r.ci, r.rows, r.k, r.dil, r.up, r.max_len, r.len_sum, r.bytes, r.flops);
+    out += buf;
+  }
+  return out + "]";
 }
 
 void Engine::ensure_front(int B, int Tmax) {

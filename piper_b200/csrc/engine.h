@@ -90,6 +90,7 @@ class Engine {
   // per-launch CUDA-event timing of the conv kernel family, aggregated by pipeline stage (bench.py roofline)
   void set_profile(bool on) { profile_ = on; }
   std::string profile_json();
+  std::string profile_launches_json();   // every conv launch of the last call, in order
   void set_mma(int mask) { mma_mask_ = mask; }
   int mma() const { return mma_mask_; }
   // speaker ids for the next calls (multi-speaker voices); item b uses sids[min(b, n-1)], default speaker 0
@@ -151,7 +152,7 @@ class Engine {
   DeviceBuf ga_, gp_, gq_, gs_, audio_d_, audio16_d_, peak_d_;
   PinnedBuf ids_pin_, misc_pin_, audio_pin_, audio16_pin_, eps_pin_;
 
-  struct ProfRec { const char* tag; bool mma; cudaEvent_t e0, e1; double bytes, flops; };
+  struct ProfRec { const char* tag; bool mma; cudaEvent_t e0, e1; double bytes, flops; int ci, rows, k, dil, up, max_len; double len_sum; };
   bool profile_ = false;
   std::vector<cudaEvent_t> ev_pool_;
   size_t ev_used_ = 0;

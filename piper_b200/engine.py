@@ -223,6 +223,12 @@ class Voice:
         check(self._lib.pb200_profile_read(self._h, buf, len(buf)))
         return json.loads(buf.value.decode())
 
+    def profile_launches(self) -> list:
+        """Every conv launch of the last profiled call, in order (tag, us, shape, algorithmic bytes / FLOP)."""
+        buf = C.create_string_buffer(1 << 17)
+        check(self._lib.pb200_profile_read_launches(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def set_debug(self, on: bool):
         check(self._lib.pb200_set_debug(self._h, 1 if on else 0))
 

@@ -1,0 +1,65 @@
+"""Per-launch report of the headline step (GPU): every conv launch's CUDA-event time (median of a few steps) next to the
+analytical bounds of tools/perf_model.py for the same shape (HBM, tcgen05 issue, weight streaming).
+
+usage: python tools/layer_report.py [--arch medium] [--batch 32] > gpurun_out/layer_report.txt   (JSON beside it)
+"""
+import argparse, json, math, os, statistics, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import numpy as np
+import perf_model as pm
+from piper_b200 import engine, voicegen
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--arch", default="medium")
+ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--steps", type=int, default=5)
+a = ap.parse_args()
+
+v = engine.Voice(voicegen.cached_voice(a.arch), 0)
+ids = [voicegen.benchmark_ids(128, seed=1234 + b) for b in range(a.batch)]
+v.stage(ids, (0.667, 1.0, 0.8), seed=4242)
+for _ in range(3):
+    v.run_staged()
+v.set_profile(True)
+runs = []
+for _ in range(a.steps):
+    n, ms = v.run_staged()
+    runs.append(v.profile_launches())
+v.set_profile(False)
+n_l = len(runs[0])
+assert all(len(r) == n_l for r in runs)
+pm.B = a.batch
+rows = []
+for i in range(n_l):
+    r = dict(runs[0][i])
+    r["us"] = statistics.median(x[i]["us"] for x in runs)
+    if r["mma"]:
+        tf32 = not r["tag"].startswith("dec")
+        L = r["len_sum"] / a.batch
+        m = pm.layer(r["tag"], r["tag"], r["ci"], r["rows"], r["k"], r["dil"], L, tf32)
+        # tiles follow the longest item; bytes follow the recorded algorithmic figure
+        n_tile, n_tiles, mt = pm.plan(r["ci"], r["rows"], r["k"], r["dil"], tf32)
+        tiles = math.ceil(r["max_len"] / mt) * a.batch * n_tiles
+        scale = math.ceil(tiles / pm.SMS) / max(1, m["per_cta"])
+        r.update(n_tile=n_tile, n_tiles=n_tiles, mt=mt, tiles=tiles, t_hbm=r["bytes"] / pm.HBM * 1e6,
+                 t_mma=m["t_mma"] * scale * 1e6, t_w=m["t_w"] * scale * 1e6)
+        r["bound"] = max(r["t_hbm"], r["t_mma"], r["t_w"])
+    rows.append(r)
+print(f"{a.arch}, {a.batch} utterances: {n} samples in {ms:.3f} ms (profiled step), {n_l} conv launches")
+print(f"{'#':>3s} {'tag':8s} {'ci':>4s} {'rows':>5s} {'k':>2s} {'d':>2s} {'N':>4s} {'mt':>3s} {'tiles':>6s} | {'us':>7s} | {'t_hbm':>6s} {'t_mma':>6s} {'t_w':>6s} | {'us/bound':>8s}")
+fam = {}
+for i, r in enumerate(rows):
+    if r["mma"]:
+        print(f"{i:3d} {r['tag']:8s} {r['ci']:4d} {r['rows']:5d} {r['k']:2d} {r['dil']:2d} {r['n_tile']:4d} {r['mt']:3d} {r['tiles']:6d} | {r['us']:7.1f} | "
+              f"{r['t_hbm']:6.1f} {r['t_mma']:6.1f} {r['t_w']:6.1f} | {r['us'] / r['bound']:8.2f}")
+        f = fam.setdefault(r["tag"], [0.0, 0.0, 0])
+        f[0] += r["us"]; f[1] += r["bound"]; f[2] += 1
+    else:
+        print(f"{i:3d} {r['tag']:8s} {r['ci']:4d} {r['rows']:5d} {r['k']:2d} {r['dil']:2d}   (CUDA-core kernel)       | {r['us']:7.1f} |")
+print("\nfamily    launches   measured ms   bound ms   ratio")
+for k, (us, b, c) in fam.items():
+    print(f"{k:9s} {c:8d} {us / 1e3:13.3f} {b / 1e3:10.3f} {us / b:7.2f}")
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "layer_report.json"), "w"))
