@@ -1120,7 +1120,7 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
     }
   }
   // never more chains than weight units, or an accumulator would be read without ever being written
-  a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);
+  a.chains = std::min(p.chains, (a.ci / a.kc) * a.k);
   mt = p.mt;
   if (mt == 256 && (long long)((max_len + 255) / 256) * B * p.n_tiles < 148) {
     mt = 128;                                        // 128-row tiles double the CTA count
