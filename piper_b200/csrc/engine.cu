@@ -76,7 +76,7 @@ Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
   DeviceBuf* dbs[] = {&weights_, &weights_mma_, &ids_d_, &len_d_, &ylen_d_, &cum_d_, &logw_d_, &override_d_, &epsdp_d_, &epsoff_d_,
                       &off_d_, &sid_d_, &cond_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
-                      &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_};
+                      &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_, &mrf_w_};
   for (auto* d : dbs) d->release();
   PinnedBuf* pbs[] = {&ids_pin_, &misc_pin_, &audio_pin_, &audio16_pin_, &eps_pin_};
   for (auto* p : pbs) p->release();
@@ -517,6 +517,17 @@ void Engine::run_generator() {
     View P = view(gp_.as<float>(), ch, Lp_out), Q = view(gq_.as<float>(), ch, Lp_out);
     S = view(gs_.as<float>(), ch, Lp_out);
     if (debug_) save_tap("up" + std::to_string(st), A, ch, ylen_h_.data(), rate);
+    if ((mma_mask_ & 16) && !mrf_ready_) prepare_mrf_fused();
+    if ((mma_mask_ & 16) && mrf_plans_[st].ok) {
+      // experimental: the whole stage (all resblocks and the MRF average) in one launch
+      MrfFusedArgs f;
+      f.x = A; f.y = S; f.len = ylen; f.len_scale = rate; f.slope = 0.1f;
+      f.w = mrf_w_.as<uint8_t>() + mrf_w_off_[st];
+      f.bias = reinterpret_cast<const float*>(mrf_w_.as<uint8_t>() + mrf_b_off_[st]);
+      launch_mrf_fused(f, mrf_plans_[st], B, L, stream_);
+      if (debug_) save_tap("stage" + std::to_string(st), S, ch, ylen_h_.data(), rate);
+      continue;
+    }
     for (int j = 0; j < nk; ++j) {
       const ResBlockW& rb = voice_.resblocks[st][j];
       const int mrf = nk == 1 ? 2 : (j == 0 ? 0 : (j == nk - 1 ? 2 : 1));
@@ -549,6 +560,32 @@ void Engine::run_generator() {
   }
   launch_conv_post(S, W(voice_.post_w), voice_.post_c, voice_.post_k, 0.01f, audio_d_.as<float>(),
                    off_d_.as<long long>(), ylen, rate, B, F * rate, stream_);
+}
+
+void Engine::prepare_mrf_fused() {
+  const size_t n = voice_.ups.size();
+  mrf_plans_.assign(n, MrfFusedPlan{});
+  mrf_w_off_.assign(n, 0);
+  mrf_b_off_.assign(n, 0);
+  std::vector<uint8_t> host;
+  int ch = voice_.spec.up_initial;
+  for (size_t st = 0; st < n; ++st) {
+    ch = voice_.ups[st].rows / voice_.ups[st].up;
+    MrfFusedPlan& p = mrf_plans_[st];
+    if (!plan_mrf_fused(voice_.resblocks[st], voice_.spec.resblock, ch, p)) continue;
+    const size_t w_off = (host.size() + 127) & ~size_t(127);
+    const size_t b_off = w_off + p.w_bytes;
+    host.resize(b_off + size_t(p.n_bias) * 4);
+    pack_mrf_fused(voice_.blob.data(), voice_.resblocks[st], p, host.data() + w_off,
+                   reinterpret_cast<float*>(host.data() + b_off));
+    mrf_w_off_[st] = w_off;
+    mrf_b_off_[st] = b_off;
+  }
+  if (!host.empty()) {
+    mrf_w_.ensure(host.size());
+    CUDA_CHECK(cudaMemcpy(mrf_w_.p, host.data(), host.size(), cudaMemcpyHostToDevice));
+  }
+  mrf_ready_ = true;
 }
 
 void Engine::run_flow() {

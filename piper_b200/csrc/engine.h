@@ -126,6 +126,12 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[8] = {};
   DeviceBuf weights_, weights_mma_;
+  // experimental fused MRF stage (mask bit 16, mrf_fused.cu): packed lazily on first use
+  void prepare_mrf_fused();
+  bool mrf_ready_ = false;
+  std::vector<MrfFusedPlan> mrf_plans_;
+  std::vector<size_t> mrf_w_off_, mrf_b_off_;
+  DeviceBuf mrf_w_;
   int mma_mask_ = 15;  // generator bf16x3; flow, encoder, duration predictor tf32x3 with chained accumulators
 
   // request state

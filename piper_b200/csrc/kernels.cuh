@@ -80,6 +80,33 @@ struct MmaConvArgs {
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);
 void run_mma_bench(int N, int tf32, int n_acc, int iters, int shift, unsigned long long out[2]);
 
+// ---- EXPERIMENTAL, off by default: one whole MRF stage (three resblocks) of the generator per launch (mrf_fused.cu) ----
+constexpr int MRF_MAX_CHAINS = 3, MRF_MAX_STEPS = 6;
+struct MrfFusedPlan {
+  bool ok = false;
+  int n_chains = 0, n_steps = 0, pair = 1;      // pair: convs per residual unit (ResBlock2: 1, ResBlock1: 2)
+  int k[MRF_MAX_CHAINS] = {0, 0, 0};
+  int dil[MRF_MAX_CHAINS][MRF_MAX_STEPS] = {};
+  int hv = 0, to = 0;                           // rows dropped on each side of a 256-row tile / positions stored per tile
+  size_t w_bytes = 0;                           // packed tap tiles
+  int n_bias = 0;                               // floats
+};
+struct MrfFusedArgs {
+  View x, y;                                    // [B][32][L] fp32 in / out
+  const int* len = nullptr;
+  int len_scale = 1;
+  const uint8_t* w = nullptr;                   // pack_mrf_fused
+  const float* bias = nullptr;
+  float slope = 0.1f;
+  int n_chains = 0, n_steps = 0, pair = 1, hv = 0, to = 0;
+  int k[MRF_MAX_CHAINS] = {0, 0, 0};
+  int dil[MRF_MAX_CHAINS][MRF_MAX_STEPS] = {};
+  int tiles_per_item = 0, total_tiles = 0;
+};
+bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int channels, MrfFusedPlan& p);
+void pack_mrf_fused(const float* blob, const std::vector<ResBlockW>& stage, const MrfFusedPlan& p, uint8_t* w, float* bias);
+void launch_mrf_fused(MrfFusedArgs a, const MrfFusedPlan& p, int B, int max_len, cudaStream_t st);
+
 // ---- text encoder -----------------------------------------------------------------------------
 void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float scale, View x, const int* len, int B,
                   int Tmax, cudaStream_t st);
