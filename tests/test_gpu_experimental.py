@@ -1,0 +1,73 @@
+"""GPU tests of EXPERIMENTAL, off-by-default kernels.  Skipped unless PIPER_B200_EXPERIMENTAL=1: these paths were written
+without GPU access at the end of round 1 and are not part of the product path until they pass here.
+
+  PIPER_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from piper_b200 import voicegen
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PIPER_B200_EXPERIMENTAL") != "1", reason="experimental kernels are opt-in")]
+SCALES = (0.667, 1.0, 0.8)
+
+
+def _noise(inter, n_ids, seed):
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((2, n_ids)).astype(np.float32), rng.standard_normal((inter, 6 * n_ids + 16)).astype(np.float32)
+
+
+@pytest.mark.parametrize("arch,n_ph", [("tiny", 20), ("tiny-high", 20), ("medium", 64), ("high", 32)])
+def test_fused_mrf_stage_matches_layerwise_and_oracle(arch, n_ph):
+    """Engine mask bit 16 routes the 32-channel MRF stage through mrf_fused.cu: same taps as the layer-wise path (both
+    are bf16x3) and the same waveform bar against the oracle."""
+    from oracle.voice_loader import load_voice
+    from oracle.vits_oracle import Oracle
+    from piper_b200 import engine
+    path = voicegen.cached_voice(arch)
+    spec, w, attrs = load_voice(path)
+    orc = Oracle(spec, w, attrs)
+    ids = voicegen.benchmark_ids(n_ph, seed=3)
+    eps_dp, eps_z = _noise(spec.inter, len(ids), 77)
+    dump = {}
+    ref = orc.infer(ids, SCALES, eps_dp, eps_z, dump=dump)
+    v = engine.Voice(path, 0)
+    try:
+        stages = [i for i in range(len(spec.up_rates)) if dump[f"stage{i}"].shape[0] == 32]
+        assert stages, "no 32-channel stage in this architecture"
+        out = {}
+        for mask in (15, 31):
+            v.set_mma(mask)
+            v.set_debug(True)
+            audio, _ = v.synthesize(ids, SCALES, eps_dp, eps_z)
+            out[mask] = (audio.copy(), {i: v.tap(f"stage{i}") for i in stages})
+            v.set_debug(False)
+        for i in stages:
+            r = dump[f"stage{i}"].numpy()
+            e_layer = np.abs(out[15][1][i] - r).max()
+            e_fused = np.abs(out[31][1][i] - r).max()
+            assert e_fused <= max(2e-4 * max(1.0, np.abs(r).max()), 2 * e_layer), (i, e_layer, e_fused)
+        assert np.abs(out[31][0] - ref).max() <= 1e-3
+    finally:
+        v.close()
+
+
+def test_fused_mrf_ragged_batch():
+    """Ragged batch through the fused stage: each item equals its own batch-1 run (utterance-edge zero padding)."""
+    from piper_b200 import engine
+    v = engine.Voice(voicegen.cached_voice("medium"), 0)
+    try:
+        v.set_mma(31)
+        ids = [voicegen.benchmark_ids(n, seed=10 + n) for n in (5, 64, 23, 128, 1)]
+        flat, counts, _ = v.synthesize_batch(ids, SCALES, seed=99)
+        off = np.concatenate([[0], np.cumsum(counts)])
+        v.set_mma(15)
+        flat0, counts0, _ = v.synthesize_batch(ids, SCALES, seed=99)
+        assert np.array_equal(counts, counts0)
+        assert np.abs(flat - flat0).max() <= 2e-4
+        assert off[-1] == flat.shape[0]
+    finally:
+        v.close()
