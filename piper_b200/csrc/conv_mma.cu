@@ -556,7 +556,12 @@ struct PBarriers {
       w_empty[P_W_SLOTS], t_full[P_T_SLOTS], t_empty[P_T_SLOTS];
 };
 
-template <bool TF32, int MT>
+// UNI (experimental, PIPER_B200_UNI=1, off by default): the two TMA warps run their loops converged with only the copy
+// predicated on an elected lane, like the MMA warp, so the copy operands stay in uniform registers.  In the shipped
+// form (`if (lane == 0)`) every cp.async.bulk costs ~18 dependent instructions (vector address arithmetic, 3-4 R2UR, an
+// ELECT / BRA.U.ANY loop): ~150 cycles per activation ROW, which fits the launch times of every many-channel layer in
+// profiles/r01_layer_report.txt (tiles per CTA x C_in x ~76 ns) - see DESIGN.md section 8.
+template <bool TF32, int MT, bool UNI = false>
 __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const MmaConvArgs a) {
   constexpr int ES = TF32 ? 4 : 2;
   constexpr int E = 16 / ES;
@@ -611,7 +616,65 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
     return t0 < Lq;
   };
 
-  if (warp == 0) {
+  if (UNI && warp == 0) {
+    // ---------------------------------------------------------------------- raw activation rows via TMA, uniform issue
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int nt, b, t0, L, Lq;
+      bool ok = decode(tile, nt, b, t0, L, Lq);
+      L = __shfl_sync(0xffffffffu, L, 0);                              // loaded from global: make uniformity explicit
+      ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+      if (!ok) continue;
+      const int t_lo = t0 - a.pad;
+      const int t_base = t_lo & ~3;
+      const int g0 = max(t_lo, 0) & ~3;
+      const int g1 = min((min(t_lo + R, L) + 3) & ~3, a.x.cs);
+      const uint32_t row_bytes = (uint32_t)(g1 - g0) * 4;
+      const float* xb = a.x.p + (long long)b * a.x.bs + g0;
+      for (int kc = 0; kc < n_kc; ++kc, ++it) {
+        const int s = it % P_RAW_SLOTS;
+        if (it >= P_RAW_SLOTS) mbar_wait(&bar.raw_empty[s], ((it / P_RAW_SLOTS) - 1) & 1);
+        if (elect_one()) mbar_expect_tx(&bar.raw_full[s], row_bytes * (uint32_t)KC);
+        const uint32_t dst = smem_u32(RAW_ring + size_t(s) * raw_bytes) + (uint32_t)(g0 - t_base) * 4;
+        const float* src = xb + (long long)(kc * KC) * a.x.cs;
+        const uint32_t mb = smem_u32(&bar.raw_full[s]);
+        const uint32_t d_step = (uint32_t)RS * 4u;
+        const long long s_step = a.x.cs;
+        uint32_t d = dst;
+#pragma unroll 4
+        for (int c = 0; c < KC; ++c, d += d_step, src += s_step) {     // running addresses: ~4 uniform ops per copy
+          if (elect_one())
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                         "l"(src), "r"(row_bytes), "r"(mb)
+                         : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  } else if (UNI && warp == 1) {
+    // ---------------------------------------------------------------------- weight units via TMA, uniform issue
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int nt, b, t0, L, Lq;
+      bool ok = decode(tile, nt, b, t0, L, Lq);
+      ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+      if (!ok) continue;
+      const size_t g_row = size_t(a.n_tile) * 16, part_all = size_t(a.ci / E) * g_row;
+      const uint8_t* wsrc = a.w + size_t(nt) * a.k * 2 * part_all;
+      for (int u = 0; u < n_units; ++u, ++it) {
+        const int s = it % P_W_SLOTS;
+        if (it >= P_W_SLOTS) mbar_wait(&bar.w_empty[s], ((it / P_W_SLOTS) - 1) & 1);
+        const int kc = u / a.k, j = u - kc * a.k;
+        const uint8_t* hi = wsrc + size_t(j) * 2 * part_all + size_t(kc) * (KC / E) * g_row;
+        if (elect_one()) {
+          mbar_expect_tx(&bar.w_full[s], unit_bytes);
+          bulk_g2s(W_ring + size_t(s) * unit_bytes, hi, (uint32_t)w_part, &bar.w_full[s]);
+          bulk_g2s(W_ring + size_t(s) * unit_bytes + w_part, hi + part_all, (uint32_t)w_part, &bar.w_full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ raw activation rows via TMA
       uint32_t it = 0;
@@ -1083,7 +1146,21 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
       a.tmem_cols = pow2_cols(t_slots * (mt / 128) * n_acc * p.acc_cols);
       a.tiles_per_item = tpi; a.total_tiles = (int)total; a.batch = B;
       const int grid = (int)std::min<long long>(total, 148);
-      if (p.tf32) conv_mma_persist_kernel<true, 128><<<grid, P_THREADS, smem, st>>>(a);
+      static int g_uni = -1;                           // experimental uniform-issue TMA warps (see the kernel)
+      if (g_uni < 0) {
+        const char* e = std::getenv("PIPER_B200_UNI");
+        g_uni = e ? std::atoi(e) : 0;
+        if (g_uni) {
+          cudaFuncSetAttribute(conv_mma_persist_kernel<false, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(conv_mma_persist_kernel<false, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+          cudaFuncSetAttribute(conv_mma_persist_kernel<true, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        }
+      }
+      if (g_uni) {
+        if (p.tf32) conv_mma_persist_kernel<true, 128, true><<<grid, P_THREADS, smem, st>>>(a);
+        else if (mt == 256) conv_mma_persist_kernel<false, 256, true><<<grid, P_THREADS, smem, st>>>(a);
+        else conv_mma_persist_kernel<false, 128, true><<<grid, P_THREADS, smem, st>>>(a);
+      } else if (p.tf32) conv_mma_persist_kernel<true, 128><<<grid, P_THREADS, smem, st>>>(a);
       else if (mt == 256) conv_mma_persist_kernel<false, 256><<<grid, P_THREADS, smem, st>>>(a);
       else conv_mma_persist_kernel<false, 128><<<grid, P_THREADS, smem, st>>>(a);
       count_launch();

@@ -213,42 +213,56 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const __grid_co
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ stage input: 32 fp32 rows of the window
-      uint32_t ti = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        int b, t0, L;
-        if (!decode(tile, b, t0, L)) continue;
-        const int t_lo = t0 - a.hv - F_G0;                               // position of operand row 0
-        const int t_base = t_lo & ~3;                                    // shared-memory column 0 <-> position t_base
-        const int g0 = max(t_lo, 0) & ~3;
-        const int g1 = min((min(t_lo + F_R0, L) + 3) & ~3, a.x.cs);
-        const uint32_t row_bytes = (uint32_t)(g1 - g0) * 4;
-        if (ti >= 1) mbar_wait(&bar.raw_free, (ti - 1) & 1);
-        mbar_expect_tx(&bar.raw_full, row_bytes * (uint32_t)F_C);
-        const float* xb = a.x.p + (long long)b * a.x.bs + g0;
-        float* dst = xs + (g0 - t_base);
-        for (int c = 0; c < F_C; ++c) bulk_g2s(dst + c * F_XS, xb + (long long)c * a.x.cs, row_bytes, &bar.raw_full);
-        ++ti;
+    // ---------------------------------------------------------------------- stage input: 32 fp32 rows of the window.
+    // Whole warp converged, copies predicated on an elected lane: operands stay in uniform registers (conv_mma.cu, UNI)
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int b, t0, L;
+      bool ok = decode(tile, b, t0, L);
+      L = __shfl_sync(0xffffffffu, L, 0);
+      ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+      if (!ok) continue;
+      const int t_lo = t0 - a.hv - F_G0;                               // position of operand row 0
+      const int t_base = t_lo & ~3;                                    // shared-memory column 0 <-> position t_base
+      const int g0 = max(t_lo, 0) & ~3;
+      const int g1 = min((min(t_lo + F_R0, L) + 3) & ~3, a.x.cs);
+      const uint32_t row_bytes = (uint32_t)(g1 - g0) * 4;
+      if (ti >= 1) mbar_wait(&bar.raw_free, (ti - 1) & 1);
+      if (elect_one()) mbar_expect_tx(&bar.raw_full, row_bytes * (uint32_t)F_C);
+      const float* src = a.x.p + (long long)b * a.x.bs + g0;
+      uint32_t d = smem_u32(xs + (g0 - t_base));
+      const uint32_t mb = smem_u32(&bar.raw_full);
+      const long long s_step = a.x.cs;
+#pragma unroll 4
+      for (int c = 0; c < F_C; ++c, d += F_XS * 4, src += s_step) {
+        if (elect_one())
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                       "l"(src), "r"(row_bytes), "r"(mb)
+                       : "memory");
       }
+      __syncwarp();
+      ++ti;
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ weight taps, in the order the MMAs use them
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        int b, t0, L;
-        if (!decode(tile, b, t0, L)) continue;
-        const uint8_t* src = a.w;
-        for (int s = 0; s < n_steps; ++s)
-          for (int c = 0; c < n_chains; ++c)
-            for (int j = 0; j < a.k[c]; ++j, ++it, src += F_TAP_BYTES) {
-              const int slot = it % F_W_SLOTS;
-              if (it >= F_W_SLOTS) mbar_wait(&bar.w_empty[slot], ((it / F_W_SLOTS) - 1) & 1);
+    // ---------------------------------------------------------------------- weight taps, in the order the MMAs use them
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      int b, t0, L;
+      bool ok = decode(tile, b, t0, L);
+      ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+      if (!ok) continue;
+      const uint8_t* src = a.w;
+      for (int s = 0; s < n_steps; ++s)
+        for (int c = 0; c < n_chains; ++c)
+          for (int j = 0; j < a.k[c]; ++j, ++it, src += F_TAP_BYTES) {
+            const int slot = it % F_W_SLOTS;
+            if (it >= F_W_SLOTS) mbar_wait(&bar.w_empty[slot], ((it / F_W_SLOTS) - 1) & 1);
+            if (elect_one()) {
               mbar_expect_tx(&bar.w_full[slot], F_TAP_BYTES);
               bulk_g2s(Wr + slot * F_TAP_BYTES, src, F_TAP_BYTES, &bar.w_full[slot]);
             }
-      }
+            __syncwarp();
+          }
     }
   } else if (warp == 2) {
     // -------------------------------------------------------------------- MMA issue (whole warp converged; only the

@@ -62,12 +62,54 @@ def test_fused_mrf_ragged_batch():
     try:
         v.set_mma(31)
         ids = [voicegen.benchmark_ids(n, seed=10 + n) for n in (5, 64, 23, 128, 1)]
-        flat, counts, _ = v.synthesize_batch(ids, SCALES, seed=99)
-        off = np.concatenate([[0], np.cumsum(counts)])
+        wavs, _ = v.synthesize_batch(ids, SCALES, seed=99)
         v.set_mma(15)
-        flat0, counts0, _ = v.synthesize_batch(ids, SCALES, seed=99)
-        assert np.array_equal(counts, counts0)
-        assert np.abs(flat - flat0).max() <= 2e-4
-        assert off[-1] == flat.shape[0]
+        wavs0, _ = v.synthesize_batch(ids, SCALES, seed=99)
+        assert [len(a) for a in wavs] == [len(a) for a in wavs0]
+        for a, b in zip(wavs, wavs0):
+            assert np.abs(a - b).max() <= 2e-4
     finally:
         v.close()
+
+
+_CHILD = r"""
+import json, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+from oracle.voice_loader import load_voice
+from oracle.vits_oracle import Oracle
+from piper_b200 import engine, voicegen
+out = {{}}
+for arch, n_ph, batch in (("tiny", 20, 1), ("medium", 64, 1), ("medium", 128, 32)):
+    path = voicegen.cached_voice(arch)
+    spec, w, attrs = load_voice(path)
+    v = engine.Voice(path, 0)
+    ids = [voicegen.benchmark_ids(n_ph, seed=3 + b) for b in range(batch)]
+    rng = np.random.default_rng(77)
+    eps_dp = [rng.standard_normal((2, len(i))).astype(np.float32) for i in ids]
+    eps_z = [rng.standard_normal((spec.inter, 6 * len(i) + 16)).astype(np.float32) for i in ids]
+    wavs, _ = v.synthesize_batch(ids, (0.667, 1.0, 0.8), eps_dp=eps_dp, eps_z=np.stack(eps_z))
+    worst = 0.0
+    for b in sorted(set([0, batch - 1])):
+        ref = Oracle(spec, w, attrs).infer(ids[b], (0.667, 1.0, 0.8), eps_dp[b], eps_z[b])
+        got = wavs[b]
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        worst = max(worst, float(np.abs(got - ref).max()))
+    out[f"{{arch}}/{{batch}}"] = worst
+    v.close()
+print("RESULT " + json.dumps(out))
+"""
+
+
+@pytest.mark.parametrize("env", [{"PIPER_B200_UNI": "1"}, {"PIPER_B200_SMALL": "1"}, {"PIPER_B200_UNI": "1", "PIPER_B200_SMALL": "1"}])
+def test_env_gated_variants_keep_parity(env):
+    """PIPER_B200_UNI (uniform-issue TMA warps of the persistent conv kernel) and PIPER_B200_SMALL (double-buffered plan
+    for small one-tile-per-CTA launches) are read once per process, so the check runs in a child process."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-c", _CHILD.format(root=root)], capture_output=True, text=True, env=e, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    for k, err in json.loads(line[7:]).items():
+        assert err <= 1e-3, (env, k, err)
