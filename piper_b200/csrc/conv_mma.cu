@@ -121,6 +121,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Watchdog form for EXPERIMENTAL kernel variants: a protocol bug becomes a trap (launch failure) after ~2 s instead of
+// a hung GPU.  BOUNDED = false is exactly mbar_wait.
+template <bool BOUNDED>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* mbar, uint32_t parity) {
+  if (!BOUNDED) {
+    mbar_wait(mbar, parity);
+    return;
+  }
+  const uint32_t a = smem_u32(mbar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
@@ -633,7 +656,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
       const float* xb = a.x.p + (long long)b * a.x.bs + g0;
       for (int kc = 0; kc < n_kc; ++kc, ++it) {
         const int s = it % P_RAW_SLOTS;
-        if (it >= P_RAW_SLOTS) mbar_wait(&bar.raw_empty[s], ((it / P_RAW_SLOTS) - 1) & 1);
+        if (it >= P_RAW_SLOTS) mbar_wait_t<UNI>(&bar.raw_empty[s], ((it / P_RAW_SLOTS) - 1) & 1);
         if (elect_one()) mbar_expect_tx(&bar.raw_full[s], row_bytes * (uint32_t)KC);
         const uint32_t dst = smem_u32(RAW_ring + size_t(s) * raw_bytes) + (uint32_t)(g0 - t_base) * 4;
         const float* src = xb + (long long)(kc * KC) * a.x.cs;
@@ -663,7 +686,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
       const uint8_t* wsrc = a.w + size_t(nt) * a.k * 2 * part_all;
       for (int u = 0; u < n_units; ++u, ++it) {
         const int s = it % P_W_SLOTS;
-        if (it >= P_W_SLOTS) mbar_wait(&bar.w_empty[s], ((it / P_W_SLOTS) - 1) & 1);
+        if (it >= P_W_SLOTS) mbar_wait_t<UNI>(&bar.w_empty[s], ((it / P_W_SLOTS) - 1) & 1);
         const int kc = u / a.k, j = u - kc * a.k;
         const uint8_t* hi = wsrc + size_t(j) * 2 * part_all + size_t(kc) * (KC / E) * g_row;
         if (elect_one()) {
@@ -689,7 +712,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
         const float* xb = a.x.p + (long long)b * a.x.bs + g0;
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
           const int s = it % P_RAW_SLOTS;
-          if (it >= P_RAW_SLOTS) mbar_wait(&bar.raw_empty[s], ((it / P_RAW_SLOTS) - 1) & 1);
+          if (it >= P_RAW_SLOTS) mbar_wait_t<UNI>(&bar.raw_empty[s], ((it / P_RAW_SLOTS) - 1) & 1);
           mbar_expect_tx(&bar.raw_full[s], row_bytes * (uint32_t)KC);
           uint8_t* dst = RAW_ring + size_t(s) * raw_bytes + (size_t)(g0 - t_base) * 4;
           for (int c = 0; c < KC; ++c)
@@ -708,7 +731,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
         const uint8_t* wsrc = a.w + size_t(nt) * a.k * 2 * part_all;
         for (int u = 0; u < n_units; ++u, ++it) {
           const int s = it % P_W_SLOTS;
-          if (it >= P_W_SLOTS) mbar_wait(&bar.w_empty[s], ((it / P_W_SLOTS) - 1) & 1);
+          if (it >= P_W_SLOTS) mbar_wait_t<UNI>(&bar.w_empty[s], ((it / P_W_SLOTS) - 1) & 1);
           const int kc = u / a.k, j = u - kc * a.k;
           const uint8_t* hi = wsrc + size_t(j) * 2 * part_all + size_t(kc) * (KC / E) * g_row;
           mbar_expect_tx(&bar.w_full[s], unit_bytes);
@@ -734,20 +757,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
         if (!ok) continue;
         const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
         const int ts = t_it % t_slots;
-        if (t_it >= (uint32_t)t_slots) mbar_wait(&bar.t_empty[ts], ((t_it / t_slots) - 1) & 1);
+        if (t_it >= (uint32_t)t_slots) mbar_wait_t<UNI>(&bar.t_empty[ts], ((t_it / t_slots) - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t d_set = tmem_du + (uint32_t)(ts * set_cols);
         uint32_t started = 0;
         int u = 0;
         for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
           const int as = a_it % P_A_SLOTS;
-          mbar_wait(&bar.a_full[as], (a_it / P_A_SLOTS) & 1);
+          mbar_wait_t<UNI>(&bar.a_full[as], (a_it / P_A_SLOTS) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
           const uint32_t a_hi = smem_u32(A_ring + size_t(as) * 2 * a_part);
           const uint32_t ah_base = desc_lo(a_hi, a_lbo), al_base = desc_lo(a_hi + a_part, a_lbo);
           for (int j = 0; j < a.k; ++j, ++u, ++w_it) {
             const int ws = w_it % P_W_SLOTS;
-            mbar_wait(&bar.w_full[ws], (w_it / P_W_SLOTS) & 1);
+            mbar_wait_t<UNI>(&bar.w_full[ws], (w_it / P_W_SLOTS) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int chain = (u * a.chains) / n_units;
             const int corr = a.sep_corr ? a.chains : chain;
@@ -783,8 +806,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
       const int off = t_lo - (t_lo & ~3);                               // smem column of stage row 0
       for (int kc = 0; kc < n_kc; ++kc, ++raw_it, ++a_it) {
         const int rs = raw_it % P_RAW_SLOTS, as = a_it % P_A_SLOTS;
-        mbar_wait(&bar.raw_full[rs], (raw_it / P_RAW_SLOTS) & 1);
-        if (a_it >= P_A_SLOTS) mbar_wait(&bar.a_empty[as], ((a_it / P_A_SLOTS) - 1) & 1);
+        mbar_wait_t<UNI>(&bar.raw_full[rs], (raw_it / P_RAW_SLOTS) & 1);
+        if (a_it >= P_A_SLOTS) mbar_wait_t<UNI>(&bar.a_empty[as], ((a_it / P_A_SLOTS) - 1) & 1);
         const float* raw = reinterpret_cast<const float*>(RAW_ring + size_t(rs) * raw_bytes) + off;
         uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
         uint8_t* A_lo = A_hi + a_part;
@@ -839,7 +862,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
       if (!decode(tile, nt, b, t0, L, Lq)) continue;
       const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
       const int ts = t_it % t_slots;
-      mbar_wait(&bar.t_full[ts], (t_it / t_slots) & 1);
+      mbar_wait_t<UNI>(&bar.t_full[ts], (t_it / t_slots) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
       float* yb = a.y.p ? a.y.p + (long long)b * a.y.bs : nullptr;

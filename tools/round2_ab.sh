@@ -9,12 +9,12 @@ set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 echo "== experimental parity tests" > gpurun_out/ab_tests.log
-PIPER_B200_EXPERIMENTAL=1 timeout 1200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -x --timeout 600 >> gpurun_out/ab_tests.log 2>&1
+PIPER_B200_EXPERIMENTAL=1 timeout -k 10 1200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -x --timeout 600 >> gpurun_out/ab_tests.log 2>&1
 echo "rc=$?" >> gpurun_out/ab_tests.log
 tail -15 gpurun_out/ab_tests.log
 run() {  # name, env...
   local name=$1; shift
-  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_$name.json 2> gpurun_out/ab_bench_$name.err
+  env "$@" timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_$name.json 2> gpurun_out/ab_bench_$name.err
   python - "$name" <<'PY'
 import json, sys
 try:
@@ -28,5 +28,5 @@ run base PIPER_B200_NOP=1
 run uni PIPER_B200_UNI=1
 run uni_small PIPER_B200_UNI=1 PIPER_B200_SMALL=1
 run uni_fused PIPER_B200_UNI=1 PIPER_B200_MMA=31
-PIPER_B200_UNI=1 timeout 200 python tools/layer_report.py > gpurun_out/ab_layer_report_uni.txt 2>&1
+PIPER_B200_UNI=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_uni.txt 2>&1
 tail -9 gpurun_out/ab_layer_report_uni.txt
