@@ -103,6 +103,16 @@ struct MrfFusedArgs {
   int dil[MRF_MAX_CHAINS][MRF_MAX_STEPS] = {};
   int tiles_per_item = 0, total_tiles = 0;
 };
+// plan -> launch arguments (shared by the CUDA launcher and the CPU model of the kernel in tests/sim)
+inline void mrf_fill_args(MrfFusedArgs& a, const MrfFusedPlan& p, int B, int max_len) {
+  a.n_chains = p.n_chains; a.n_steps = p.n_steps; a.pair = p.pair; a.hv = p.hv; a.to = p.to;
+  for (int c = 0; c < MRF_MAX_CHAINS; ++c) {
+    a.k[c] = p.k[c];
+    for (int s = 0; s < MRF_MAX_STEPS; ++s) a.dil[c][s] = p.dil[c][s];
+  }
+  a.tiles_per_item = (max_len + p.to - 1) / p.to;
+  a.total_tiles = a.tiles_per_item * B;
+}
 bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int channels, MrfFusedPlan& p);
 void pack_mrf_fused(const float* blob, const std::vector<ResBlockW>& stage, const MrfFusedPlan& p, uint8_t* w, float* bias);
 void launch_mrf_fused(MrfFusedArgs a, const MrfFusedPlan& p, int B, int max_len, cudaStream_t st);

@@ -1,0 +1,67 @@
+"""The experimental fused MRF kernel's own body (piper_b200/csrc/mrf_fused_body.inl), compiled against a CPU model of the
+hardware primitives (tests/sim/mrf_sim.cpp: every CTA thread a std::thread, blocking mbarriers, TMEM array, tcgen05.mma
+decoded from its descriptors), against the oracle's generator stage.  No GPU involved: this checks index arithmetic,
+operand layouts, the TMEM column map, TMA alignment and the barrier protocol - not the hardware's asynchrony."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle.voice_loader import load_voice
+from oracle.vits_oracle import Oracle
+from piper_b200 import _lib, voicegen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "sim", "libmrf_sim.so")
+
+
+def _plan_and_taps(path, stage):
+    lib = _lib.load()
+    plan = (C.c_int32 * 32)()
+    wb, nb = C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.pb200_debug_mrf_pack(path.encode(), stage, plan, None, C.byref(wb), None, C.byref(nb)))
+    w = np.zeros(wb.value + 64, np.uint8)
+    w = w[(-w.ctypes.data) % 64:][:wb.value]                      # 64-byte aligned like the device buffer
+    b = np.zeros(nb.value, np.float32)
+    _lib.check(lib.pb200_debug_mrf_pack(path.encode(), stage, plan, w.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(wb),
+                                        b.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nb)))
+    return plan, w, b
+
+
+@pytest.mark.parametrize("arch,stage,n_phonemes,grid", [("tiny", 0, (12, 3, 7), 2), ("tiny-high", 0, (9, 2), 3)])
+def test_kernel_body_on_cpu_model_matches_oracle(lib_built, arch, stage, n_phonemes, grid):
+    if not os.path.exists(SIM):
+        pytest.skip("tests/sim/libmrf_sim.so not built (make -C piper_b200/csrc)")
+    sim = C.CDLL(SIM)
+    path = voicegen.cached_voice(arch)
+    plan, w, bias = _plan_and_taps(path, stage)
+    assert plan[0] == 1
+    spec, wd, attrs = load_voice(path)
+    orc = Oracle(spec, wd, attrs)
+    xs, refs = [], []
+    for i, n in enumerate(n_phonemes):
+        dump = {}
+        orc.infer(voicegen.benchmark_ids(n, seed=20 + i), (0.667, 1.0, 0.8), dump=dump)
+        xs.append(dump[f"up{stage}"].numpy())
+        refs.append(dump[f"stage{stage}"].numpy())
+    B = len(xs)
+    lens = np.asarray([x.shape[1] for x in xs], np.int32)
+    assert len(set(lens.tolist())) > 1 and lens.max() > plan[5]     # ragged, and more than one tile per item
+    cs = (int(lens.max()) + 3) & ~3
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((B, 32, cs)).astype(np.float32) * 50.0    # stale data past each item's length must not matter
+    for b in range(B):
+        x[b, :, :lens[b]] = xs[b]
+    y = np.full((B, 32, cs), 7e7, np.float32)
+    err = C.create_string_buffer(512)
+    rc = sim.mrf_sim_run(x.ctypes.data_as(C.POINTER(C.c_float)), y.ctypes.data_as(C.POINTER(C.c_float)),
+                         lens.ctypes.data_as(C.POINTER(C.c_int32)), B, C.c_longlong(32 * cs), cs, 1,
+                         w.ctypes.data_as(C.POINTER(C.c_uint8)), bias.ctypes.data_as(C.POINTER(C.c_float)), plan,
+                         int(lens.max()), grid, err, len(err))
+    assert rc == 0, err.value.decode()
+    for b in range(B):
+        got, ref = y[b, :, :lens[b]], refs[b]
+        e = float(np.abs(got - ref).max())
+        assert e <= 1e-4 * max(1.0, float(np.abs(ref).max())), (b, e)
+        assert np.all(y[b, :, lens[b]:] == 7e7), "the kernel stored outside the utterance"
