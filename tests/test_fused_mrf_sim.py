@@ -32,7 +32,9 @@ def _plan_and_taps(path, stage):
 @pytest.mark.parametrize("arch,stage,n_phonemes,grid", [("tiny", 0, (12, 3, 7), 2), ("tiny-high", 0, (9, 2), 3)])
 def test_kernel_body_on_cpu_model_matches_oracle(lib_built, arch, stage, n_phonemes, grid):
     if not os.path.exists(SIM):
-        pytest.skip("tests/sim/libmrf_sim.so not built (make -C piper_b200/csrc)")
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "piper_b200", "csrc"), "../../tests/sim/libmrf_sim.so"], check=True,
+                       stdout=subprocess.DEVNULL)
     sim = C.CDLL(SIM)
     path = voicegen.cached_voice(arch)
     plan, w, bias = _plan_and_taps(path, stage)
