@@ -29,7 +29,9 @@ def _plan_and_taps(path, stage):
     return plan, w, b
 
 
-@pytest.mark.parametrize("arch,stage,n_phonemes,grid", [("tiny", 0, (12, 3, 7), 2), ("tiny-high", 0, (9, 2), 3)])
+@pytest.mark.parametrize("arch,stage,n_phonemes,grid", [("tiny", 0, (12, 3, 7), 2), ("tiny-high", 0, (9, 2), 3),
+                                                        ("tiny", 0, (1, 0, 12), 1),      # items shorter than one tile, one CTA
+                                                        ("tiny", 0, (2, 12), 64)])       # more CTAs than tiles
 def test_kernel_body_on_cpu_model_matches_oracle(lib_built, arch, stage, n_phonemes, grid):
     if not os.path.exists(SIM):
         import subprocess
@@ -49,7 +51,7 @@ def test_kernel_body_on_cpu_model_matches_oracle(lib_built, arch, stage, n_phone
         refs.append(dump[f"stage{stage}"].numpy())
     B = len(xs)
     lens = np.asarray([x.shape[1] for x in xs], np.int32)
-    assert len(set(lens.tolist())) > 1 and lens.max() > plan[5]     # ragged, and more than one tile per item
+    assert len(set(lens.tolist())) > 1 and lens.max() > plan[5]     # ragged, and more than one tile for the longest item
     cs = (int(lens.max()) + 3) & ~3
     rng = np.random.default_rng(0)
     x = rng.standard_normal((B, 32, cs)).astype(np.float32) * 50.0    # stale data past each item's length must not matter
