@@ -41,6 +41,7 @@
 #include <stdexcept>
 
 #define MRF_FN __device__ __forceinline__
+#include "tc_policy_dev.cuh"
 #include "mrf_fused_body.inl"
 
 namespace pb200 {
@@ -48,111 +49,6 @@ void count_launch();
 
 namespace {
 using namespace mrf;
-
-// ---- tcgen05 / TMA / mbarrier primitives (same forms as conv_mma.cu, where they have been exercised on hardware) ----
-struct DevPrim {
-  using Mbar = uint64_t;
-  struct Ctx {
-    __device__ __forceinline__ int tid() const { return threadIdx.x; }
-    __device__ __forceinline__ int block() const { return blockIdx.x; }
-    __device__ __forceinline__ int grid() const { return gridDim.x; }
-  };
-  static __device__ __forceinline__ uint32_t saddr(Ctx&, const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-  static __device__ __forceinline__ int bcast0(Ctx&, int v) { return __shfl_sync(0xffffffffu, v, 0); }
-  static __device__ __forceinline__ void syncwarp() { __syncwarp(); }
-  static __device__ __forceinline__ void syncthreads(Ctx&) { __syncthreads(); }
-  static __device__ __forceinline__ bool elect_one(Ctx&) {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-        "elect.sync rx|px, %1;\n\t"
-        "@px mov.s32 %0, 1;\n\t}\n"
-        : "+r"(pred)
-        : "r"(0xFFFFFFFFu));
-    return pred != 0;
-  }
-  static __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-  static __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-  static __device__ __forceinline__ void fence_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-  static __device__ __forceinline__ void fence_tc_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-  static __device__ __forceinline__ void mbar_init(Ctx& c, Mbar* m, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(saddr(c, m)), "r"(count) : "memory");
-  }
-  static __device__ __forceinline__ void mbar_arrive(Ctx& c, Mbar* m) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(saddr(c, m)) : "memory");
-  }
-  static __device__ __forceinline__ void mbar_expect_tx(Ctx& c, Mbar* m, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(saddr(c, m)), "r"(bytes) : "memory");
-  }
-  // bounded: this kernel is experimental - a protocol bug must end as a trap (launch failure), not as a hung GPU
-  static __device__ __forceinline__ void mbar_wait(Ctx& c, Mbar* m, uint32_t parity) {
-    const uint32_t a = saddr(c, m);
-    const long long t0 = clock64();
-    for (;;) {
-      uint32_t done;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}\n"
-          : "=r"(done)
-          : "r"(a), "r"(parity)
-          : "memory");
-      if (done) return;
-      if (clock64() - t0 > 4000000000LL) __trap();
-    }
-  }
-  // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
-  static __device__ __forceinline__ void bulk_g2s(Ctx& c, uint32_t dst_saddr, const void* gsrc, uint32_t bytes, Mbar* m) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_saddr),
-                 "l"(gsrc), "r"(bytes), "r"(saddr(c, m))
-                 : "memory");
-  }
-  static __device__ __forceinline__ void tmem_alloc(Ctx& c, uint32_t* slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(saddr(c, slot)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-  }
-  static __device__ __forceinline__ void tmem_dealloc(Ctx&, uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
-  }
-  static __device__ __forceinline__ void mma_bf16(Ctx&, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-    constexpr uint32_t HI = (128u >> 4) | (1u << 14);     // SBO = 128 bytes, descriptor version 1
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(HI)
-        : "memory");
-  }
-  static __device__ __forceinline__ void mma_commit(Ctx& c, Mbar* m) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(saddr(c, m)) : "memory");
-  }
-  static __device__ __forceinline__ void tmem_ld16(Ctx&, uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-  }
-  static __device__ __forceinline__ void tmem_st16(Ctx&, uint32_t taddr, const float* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-        : "memory");
-  }
-  static __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-  static __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-  static __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // .x = a (low half), .y = b
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
-};
 
 __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const __grid_constant__ MrfFusedArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];

@@ -1,0 +1,242 @@
+// CPU functional model of the primitive policy (the counterpart of piper_b200/csrc/tc_policy_dev.cuh) - test
+// infrastructure.  See tests/sim/mrf_sim.cpp for what the model covers and what it cannot.
+#pragma once
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace simtc {
+
+struct SimAbort : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct SimCta;
+struct SimMbar {
+  std::mutex m;
+  std::condition_variable cv;
+  int count = 0, pending = 0;
+  long long tx = 0;
+  uint32_t phase = 0;
+  const char* name = "?";
+};
+
+struct CtaBarrier {   // __syncthreads for n threads, reusable
+  std::mutex m; std::condition_variable cv; int n = 0, waiting = 0; unsigned gen = 0;
+  void arrive_and_wait(std::atomic<bool>& abort) {
+    std::unique_lock<std::mutex> l(m);
+    const unsigned g = gen;
+    if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return; }
+    while (gen == g) {
+      if (cv.wait_for(l, std::chrono::seconds(20)) == std::cv_status::timeout || abort.load())
+        if (gen == g) { abort = true; throw SimAbort("__syncthreads never completed"); }
+    }
+  }
+};
+
+struct SimCta {
+  uint8_t* smem = nullptr;            // 128-byte aligned, smem_bytes long
+  int smem_bytes = 0;
+  int control_warps = 3;              // warps that run converged on hardware (TMA x 2, MMA): only lane 0 blocks in the model
+  float tmem[128][512];
+  uint32_t tmem_base = 0xdeadbeef;
+  uint32_t tmem_cols = 0;
+  CtaBarrier sync;
+  std::atomic<bool> abort{false};
+  std::mutex err_m;
+  std::string err;
+  void fail(const std::string& e) {
+    std::lock_guard<std::mutex> l(err_m);
+    if (err.empty()) err = e;
+    abort = true;
+  }
+};
+
+inline uint16_t f2bf(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return uint16_t((u >> 16) | 0x40);
+  return uint16_t((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+inline float bf2f(uint16_t h) { uint32_t u = uint32_t(h) << 16; float f; memcpy(&f, &u, 4); return f; }
+
+struct SimPrim {
+  static constexpr bool kSim = true;
+  using Mbar = SimMbar;
+  struct Ctx {
+    int tid_, block_, grid_;
+    SimCta* cta;
+    int tid() const { return tid_; }
+    int block() const { return block_; }
+    int grid() const { return grid_; }
+  };
+  static void check(Ctx& c, bool ok, const char* what) {
+    if (!ok) { c.cta->fail(std::string("check failed: ") + what + " (tid " + std::to_string(c.tid_) + ")"); throw SimAbort(what); }
+  }
+  static uint32_t saddr(Ctx& c, const void* p) {
+    const long long off = (const uint8_t*)p - c.cta->smem;
+    check(c, off >= 0 && off < c.cta->smem_bytes, "pointer outside shared memory");
+    return (uint32_t)off;
+  }
+  static int bcast0(Ctx&, int v) { return v; }           // values broadcast in the kernel are warp-uniform by construction
+  static void syncwarp() {}
+  static void syncthreads(Ctx& c) { c.cta->sync.arrive_and_wait(c.cta->abort); }
+  static bool elect_one(Ctx& c) { return (c.tid_ & 31) == 0; }
+  static void fence_mbar_init() {}
+  static void fence_async_proxy() {}
+  static void fence_tc_before() {}
+  static void fence_tc_after() {}
+
+  static void mbar_init(Ctx&, Mbar* m, uint32_t count) { m->count = m->pending = (int)count; m->tx = 0; m->phase = 0; }
+  static void complete_locked(Mbar* m) {
+    if (m->pending == 0 && m->tx == 0) { m->phase ^= 1u; m->pending = m->count; m->cv.notify_all(); }
+  }
+  static void mbar_arrive(Ctx& c, Mbar* m) {
+    std::lock_guard<std::mutex> l(m->m);
+    check(c, m->pending > 0, "more arrivals than the barrier expects in one phase");
+    --m->pending;
+    complete_locked(m);
+  }
+  static void mbar_expect_tx(Ctx& c, Mbar* m, uint32_t bytes) {
+    std::lock_guard<std::mutex> l(m->m);
+    check(c, m->pending > 0, "more arrivals than the barrier expects in one phase");
+    m->tx += bytes;
+    --m->pending;
+    complete_locked(m);
+  }
+  static void complete_tx(Mbar* m, uint32_t bytes) {
+    std::lock_guard<std::mutex> l(m->m);
+    m->tx -= bytes;
+    complete_locked(m);
+  }
+  static void mbar_wait(Ctx& c, Mbar* m, uint32_t parity) {
+    // Control warps (TMA x 2, MMA) run converged on hardware: all 32 lanes observe a barrier phase together and only the
+    // elected lane acts.  std::threads are not in lockstep - a lane that reaches a parity wait late could find the phase
+    // flipped twice and wait forever - so in the model only the elected lane of a control warp blocks.
+    if ((c.tid_ >> 5) < c.cta->control_warps && (c.tid_ & 31) != 0) return;
+    std::unique_lock<std::mutex> l(m->m);
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(20);
+    while (m->phase == parity) {                          // the phase with this parity has not completed yet
+      if (c.cta->abort.load()) throw SimAbort("aborted");
+      if (m->cv.wait_until(l, std::chrono::steady_clock::now() + std::chrono::milliseconds(200)) == std::cv_status::timeout &&
+          std::chrono::steady_clock::now() > deadline) {
+        l.unlock();
+        c.cta->fail("deadlock: thread " + std::to_string(c.tid_) + " (warp " + std::to_string(c.tid_ >> 5) +
+                    ") waited 20 s on an mbarrier, parity " + std::to_string(parity));
+        throw SimAbort("deadlock");
+      }
+    }
+  }
+  static void bulk_g2s(Ctx& c, uint32_t dst, const void* src, uint32_t bytes, Mbar* m) {
+    check(c, (dst & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (bytes & 15) == 0 && bytes > 0,
+          "cp.async.bulk needs 16-byte aligned addresses and size");
+    check(c, dst + bytes <= (uint32_t)c.cta->smem_bytes, "cp.async.bulk writes past shared memory");
+    memcpy(c.cta->smem + dst, src, bytes);
+    complete_tx(m, bytes);
+  }
+  static void tmem_alloc(Ctx& c, uint32_t* slot, uint32_t cols) {
+    check(c, cols >= 32 && cols <= 512 && (cols & (cols - 1)) == 0, "tmem columns must be a power of two in [32, 512]");
+    c.cta->tmem_cols = cols;
+    *slot = 0;
+  }
+  static void tmem_dealloc(Ctx&, uint32_t, uint32_t) {}
+  // D[128][N] (+)= A[128][K] * B[N][K]^T with K = 32 bytes of elements; operands K-major, no swizzle:
+  //   element (row, k) at  start + (k / E) * LBO + (row / 8) * 128 + (row % 8) * 16 + (k % E) * elem_bytes,  E = 16 / elem_bytes
+  template <bool TF32>
+  static void mma_any(Ctx& c, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+    constexpr int ES = TF32 ? 4 : 2, E = 16 / ES, K = 2 * E;
+    const uint32_t a0 = (a_lo & 0x3FFFu) << 4, albo = ((a_lo >> 16) & 0x3FFFu) << 4;
+    const uint32_t b0 = (b_lo & 0x3FFFu) << 4, blbo = ((b_lo >> 16) & 0x3FFFu) << 4;
+    const int N = int((idesc >> 17) & 0x3Fu) << 3, M = int((idesc >> 24) & 0x1Fu) << 4;
+    check(c, M == 128 && N >= 16 && N <= 256 && N % 16 == 0, "instruction descriptor shape");
+    const uint32_t fmt = TF32 ? 2u : 1u;
+    check(c, ((idesc >> 4) & 3u) == 1 && ((idesc >> 7) & 7u) == fmt && ((idesc >> 10) & 7u) == fmt, "instruction descriptor formats");
+    const uint32_t col0 = tmem_d & 0xFFFFu;
+    check(c, (tmem_d >> 16) == 0 && col0 + N <= c.cta->tmem_cols, "accumulator address outside the TMEM allocation");
+    auto elem = [&](uint32_t start, uint32_t lbo, int row, int k) -> float {
+      const uint32_t addr = start + uint32_t(k / E) * lbo + uint32_t(row / 8) * 128u + uint32_t(row % 8) * 16u + uint32_t(k % E) * ES;
+      if (addr + ES > (uint32_t)c.cta->smem_bytes) { c.cta->fail("tcgen05.mma operand outside shared memory"); throw SimAbort("operand"); }
+      if (TF32) {
+        uint32_t u; memcpy(&u, c.cta->smem + addr, 4);
+        u &= 0xFFFFE000u;                                  // the tensor core reads 19 bits of a tf32 operand
+        float f; memcpy(&f, &u, 4);
+        return f;
+      }
+      uint16_t h; memcpy(&h, c.cta->smem + addr, 2);
+      return bf2f(h);
+    };
+    std::vector<float> B(size_t(N) * K);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) B[size_t(n) * K + k] = elem(b0, blbo, n, k);
+    for (int m = 0; m < 128; ++m) {
+      float A[16];
+      for (int k = 0; k < K; ++k) A[k] = elem(a0, albo, m, k);
+      for (int n = 0; n < N; ++n) {
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s += A[k] * B[size_t(n) * K + k];
+        float& d = c.cta->tmem[m][col0 + n];
+        d = acc ? d + s : s;
+      }
+    }
+  }
+  static void mma_bf16(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) { mma_any<false>(c, d, a, b, idesc, acc); }
+  static void mma_tf32(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) { mma_any<true>(c, d, a, b, idesc, acc); }
+  static float to_tf32(float v) {                          // cvt.rna.tf32.f32: nearest, ties away from zero
+    uint32_t u; memcpy(&u, &v, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return v;
+    u = (u + 0x1000u) & 0xffffe000u;
+    float f; memcpy(&f, &u, 4);
+    return f;
+  }
+  static float ldg(const float* p) { return *p; }
+  static void mma_commit(Ctx& c, Mbar* m) { mbar_arrive(c, m); }   // the model executes MMAs synchronously
+  static void tmem_ld16(Ctx& c, uint32_t taddr, float (&v)[16]) {
+    const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFFu;
+    check(c, lane0 == 32u * ((c.tid_ >> 5) & 3), "tcgen05.ld outside the warp's TMEM lane quadrant (warp id % 4)");
+    check(c, col + 16 <= c.cta->tmem_cols, "tcgen05.ld column range");
+    for (int i = 0; i < 16; ++i) v[i] = c.cta->tmem[lane0 + (c.tid_ & 31)][col + i];
+  }
+  static void tmem_st16(Ctx& c, uint32_t taddr, const float* v) {
+    const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFFu;
+    check(c, lane0 == 32u * ((c.tid_ >> 5) & 3), "tcgen05.st outside the warp's TMEM lane quadrant (warp id % 4)");
+    check(c, col + 16 <= c.cta->tmem_cols, "tcgen05.st column range");
+    for (int i = 0; i < 16; ++i) c.cta->tmem[lane0 + (c.tid_ & 31)][col + i] = v[i];
+  }
+  static void tmem_wait_st() {}
+  static float bf16_round(float v) { return bf2f(f2bf(v)); }
+  static uint32_t pack_bf16(float a, float b) { return uint32_t(f2bf(a)) | (uint32_t(f2bf(b)) << 16); }
+};
+
+
+// Run `threads` std::threads of one CTA over `body(ctx)`; returns the first error ("" if none).
+template <class Body>
+inline std::string run_cta(SimCta& cta, int threads, int block, int grid, Body body) {
+  cta.sync.n = threads;
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t)
+    th.emplace_back([&, t] {
+      SimPrim::Ctx cx{t, block, grid, &cta};
+      try {
+        body(cx);
+      } catch (const SimAbort&) {
+      } catch (const std::exception& e) {
+        cta.fail(e.what());
+      }
+    });
+  for (auto& t : th) t.join();
+  return cta.err;
+}
+
+struct SmemBuf {                       // 128-byte aligned shared-memory image filled with stale garbage
+  std::vector<uint8_t> raw;
+  uint8_t* p = nullptr;
+  explicit SmemBuf(size_t bytes) : raw(bytes + 128, 0xCD) { p = raw.data() + ((128 - reinterpret_cast<uintptr_t>(raw.data()) % 128) % 128); }
+};
+
+}  // namespace simtc
