@@ -1,0 +1,430 @@
+// EXPERIMENTAL - OFF BY DEFAULT (PIPER_B200_V2=1).  Second-generation persistent tensor-core convolution, written against
+// the primitive policy P (tc_policy_dev.cuh on the GPU, tests/sim/sim_prim.h on the CPU) so that its logic is checked by
+// tests/test_conv2_sim.py without a GPU.  NOT yet run on hardware.  Same GEMM view, data layout, ragged-batch rules and
+// fused epilogues as conv_mma_persist_kernel (conv_mma.cu); what changes, from the round-1 measurements:
+//
+//   * both TMA warps run converged and issue from an elected lane, so copy operands live in uniform registers (the
+//     shipped kernel spends ~150 cycles per activation-row copy building addresses in vector registers)
+//   * the two weight halves are stacked along N, [W_hi ; W_lo], so a k-step is TWO instructions instead of three:
+//         D[:, 0..N)   += A_hi W_hi^T   and   D[:, N..2N) += A_hi W_lo^T      one tcgen05.mma, N' = 2N
+//         D[:, N..2N)  += A_lo W_hi^T                                          one tcgen05.mma, N' = N
+//     (the SS-form instruction is paced by reading its operands from shared memory; A is read twice instead of three
+//     times).  Each K-chain therefore owns a (main | correction) accumulator pair; the epilogue adds all of them in
+//     fp32 round-to-nearest, which keeps the chained / separated accumulation that tf32x3 layers need.
+//   * a weight unit is ONE bulk copy (the stacked layout is contiguous per channel chunk and tap).
+#pragma once
+
+namespace pb200 {
+namespace conv2 {
+
+constexpr int C2_CONV_WARP0 = 3, C2_CONV_THREADS = 128;
+constexpr int C2_EPI_WARP0 = 7, C2_EPI_THREADS = 256;
+constexpr int C2_THREADS = 32 * 15;
+constexpr int C2_RAW_SLOTS = 2, C2_A_SLOTS = 2, C2_W_SLOTS = 4, C2_T_SLOTS = 2;
+
+template <class Mbar>
+struct Barriers {
+  Mbar raw_full[C2_RAW_SLOTS], raw_empty[C2_RAW_SLOTS], a_full[C2_A_SLOTS], a_empty[C2_A_SLOTS], w_full[C2_W_SLOTS],
+      w_empty[C2_W_SLOTS], t_full[C2_T_SLOTS], t_empty[C2_T_SLOTS];
+};
+
+MRF_FN uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+MRF_FN constexpr uint32_t make_idesc(bool tf32, int M, int N) {
+  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+MRF_FN int imax(int a, int b) { return a > b ? a : b; }
+MRF_FN int imin(int a, int b) { return a < b ? a : b; }
+
+// WaveNet gate tanh(a) * sigmoid(b) (commons.py:99-106), one out-of-line copy on the GPU (instruction footprint)
+MRF_NOINLINE float wn_gate(float a, float b) { return tanhf(a) * (1.f / (1.f + expf(-b))); }
+
+template <int UP>
+MRF_FN void store_upsampled(const float (&v)[16], float* yb, int cs, int row0, int t, int up_pad, int Lout) {
+#pragma unroll
+  for (int i = 0; i < 16; i += UP) {
+    const int co = (row0 + i) / UP;
+    const int to = t * UP - up_pad;
+    float* dst = yb + (long long)co * cs + to;
+    if (to >= 0 && to + UP <= Lout) {
+      if (UP % 4 == 0 && (to & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < UP; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[i + j], v[i + j + 1], v[i + j + 2], v[i + j + 3]);
+      } else if (UP % 2 == 0 && (to & 1) == 0) {
+#pragma unroll
+        for (int j = 0; j < UP; j += 2) *reinterpret_cast<float2*>(dst + j) = make_float2(v[i + j], v[i + j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < UP; ++j) dst[j] = v[i + j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < UP; ++j)
+        if (to + j >= 0 && to + j < Lout) dst[j] = v[i + j];
+    }
+  }
+}
+
+template <class P, bool TF32, int MT>
+MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem, Barriers<typename P::Mbar>& bar,
+                       uint32_t* tmem_base_s) {
+  constexpr int ES = TF32 ? 4 : 2;
+  constexpr int E = 16 / ES;
+  constexpr int KSTEP = 2 * E;
+  constexpr int MH = MT / 128;
+
+  const int tid = cx.tid(), lane = tid & 31, warp = P::bcast0(cx, tid >> 5);
+  const int block = cx.block(), grid = cx.grid();
+  const int KC = a.kc, R = a.stage_rows, RS = a.raw_stride, NT = a.n_tile;
+  const int raw_bytes = KC * RS * 4, a_part = KC * R * ES;
+  const uint32_t unit_bytes = (uint32_t)(KC / E) * 2u * (uint32_t)NT * 16u;       // one (chunk, tap): stacked hi | lo rows
+  uint8_t* RAW_ring = smem;
+  uint8_t* A_ring = RAW_ring + size_t(C2_RAW_SLOTS) * raw_bytes;
+  uint8_t* W_ring = A_ring + size_t(C2_A_SLOTS) * 2 * a_part;
+  const int n_kc = a.ci / KC;
+  const int n_units = n_kc * a.k;
+  const int tpi = a.tiles_per_item, total = a.total_tiles;
+  const int t_slots = a.t_slots;                       // 1 or 2 TMEM accumulator sets
+  const int pair_cols = 2 * NT;                        // (main | correction) of one chain
+  const int set_cols = MH * a.mh_stride;               // mh_stride = chains * pair_cols
+
+  if (warp == 2) P::tmem_alloc(cx, tmem_base_s, (uint32_t)a.tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < C2_RAW_SLOTS; ++i) { P::mbar_init(cx, &bar.raw_full[i], 1); P::mbar_init(cx, &bar.raw_empty[i], C2_CONV_THREADS); }
+    for (int i = 0; i < C2_A_SLOTS; ++i) { P::mbar_init(cx, &bar.a_full[i], C2_CONV_THREADS); P::mbar_init(cx, &bar.a_empty[i], 1); }
+    for (int i = 0; i < C2_W_SLOTS; ++i) { P::mbar_init(cx, &bar.w_full[i], 1); P::mbar_init(cx, &bar.w_empty[i], 1); }
+    for (int i = 0; i < C2_T_SLOTS; ++i) { P::mbar_init(cx, &bar.t_full[i], 1); P::mbar_init(cx, &bar.t_empty[i], C2_EPI_THREADS); }
+    P::fence_mbar_init();
+  }
+  P::fence_tc_before();
+  P::syncthreads(cx);
+  P::fence_tc_after();
+  const uint32_t tmem_d = *tmem_base_s;
+
+  // tile id -> (output-row tile, item, time block); every role walks the same list and skips the same tiles
+  auto decode = [&](int tile, int& nt, int& b, int& t0, int& L, int& Lq) {
+    const int tb = tile % tpi;
+    const int rest = tile / tpi;
+    b = rest % a.batch;
+    nt = rest / a.batch;
+    t0 = tb * MT;
+    L = a.len[b] * a.len_scale;
+    Lq = L + a.q_extra;
+    return t0 < Lq;
+  };
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------------- raw activation rows via TMA, uniform issue
+    uint32_t it = 0;
+    for (int tile = block; tile < total; tile += grid) {
+      int nt, b, t0, L, Lq;
+      bool ok = decode(tile, nt, b, t0, L, Lq);
+      L = P::bcast0(cx, L);                                            // loaded from global: make uniformity explicit
+      ok = P::bcast0(cx, (int)ok) != 0;
+      if (!ok) continue;
+      const int t_lo = t0 - a.pad;
+      const int t_base = t_lo & ~3;                                    // smem column 0 <-> time t_base
+      const int g0 = imax(t_lo, 0) & ~3;                               // first / one-past-last float fetched
+      const int g1 = imin((imin(t_lo + R, L) + 3) & ~3, a.x.cs);
+      const bool any = g1 > g0;                                        // a tile that lies wholly in the ConvTranspose tail
+      const uint32_t row_bytes = any ? (uint32_t)(g1 - g0) * 4 : 0u;   // reads nothing: every row is masked to zero
+      const float* xb = a.x.p + (long long)b * a.x.bs + g0;
+      for (int kc = 0; kc < n_kc; ++kc, ++it) {
+        const int s = it % C2_RAW_SLOTS;
+        if (it >= C2_RAW_SLOTS) P::mbar_wait(cx, &bar.raw_empty[s], ((it / C2_RAW_SLOTS) - 1) & 1);
+        if (P::elect_one(cx)) P::mbar_expect_tx(cx, &bar.raw_full[s], row_bytes * (uint32_t)KC);
+        uint32_t d = P::saddr(cx, RAW_ring + size_t(s) * raw_bytes) + (uint32_t)(g0 - t_base) * 4;
+        const float* src = xb + (long long)(kc * KC) * a.x.cs;
+        const uint32_t d_step = (uint32_t)RS * 4u;
+        const long long s_step = a.x.cs;
+        if (any) {
+#pragma unroll 4
+          for (int c = 0; c < KC; ++c, d += d_step, src += s_step) {
+            if (P::elect_one(cx)) P::bulk_g2s(cx, d, src, row_bytes, &bar.raw_full[s]);
+          }
+        }
+        P::syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------------- weight units via TMA: one copy per unit
+    uint32_t it = 0;
+    const size_t nt_bytes = size_t(a.k) * (a.ci / E) * 2 * NT * 16;    // all taps and chunks of one output-row tile
+    for (int tile = block; tile < total; tile += grid) {
+      int nt, b, t0, L, Lq;
+      bool ok = decode(tile, nt, b, t0, L, Lq);
+      ok = P::bcast0(cx, (int)ok) != 0;
+      if (!ok) continue;
+      const uint8_t* wsrc = a.w + size_t(nt) * nt_bytes;
+      for (int u = 0; u < n_units; ++u, ++it) {
+        const int s = it % C2_W_SLOTS;
+        if (it >= C2_W_SLOTS) P::mbar_wait(cx, &bar.w_empty[s], ((it / C2_W_SLOTS) - 1) & 1);
+        const int kc = u / a.k, j = u - kc * a.k;
+        const uint8_t* src = wsrc + (size_t(j) * (a.ci / E) + size_t(kc) * (KC / E)) * 2 * NT * 16;
+        if (P::elect_one(cx)) {
+          P::mbar_expect_tx(cx, &bar.w_full[s], unit_bytes);
+          P::bulk_g2s(cx, P::saddr(cx, W_ring + size_t(s) * unit_bytes), src, unit_bytes, &bar.w_full[s]);
+        }
+        P::syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------------------------------------------------------------- MMA issue: whole warp converged, the
+    // tcgen05 instructions predicated on one elected lane so that every operand stays warp-uniform
+    const uint32_t tmem_du = (uint32_t)P::bcast0(cx, (int)tmem_d);
+    const uint32_t a_lbo = (uint32_t)R * 16, w_lbo = 2u * (uint32_t)NT * 16;
+    const uint32_t idesc2 = make_idesc(TF32, 128, 2 * NT), idesc1 = make_idesc(TF32, 128, NT);
+    const uint32_t a_step = 2u * (uint32_t)R, w_step = 4u * (uint32_t)NT;          // 16-byte units per k-step
+    uint32_t a_it = 0, w_it = 0, t_it = 0;
+    for (int tile = block; tile < total; tile += grid) {
+      int nt, b, t0, L, Lq;
+      bool ok = decode(tile, nt, b, t0, L, Lq);
+      Lq = P::bcast0(cx, Lq);
+      ok = P::bcast0(cx, (int)ok) != 0;
+      if (!ok) continue;
+      const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
+      const int ts = t_it % t_slots;
+      if (t_it >= (uint32_t)t_slots) P::mbar_wait(cx, &bar.t_empty[ts], ((t_it / t_slots) - 1) & 1);
+      P::fence_tc_after();
+      const uint32_t d_set = tmem_du + (uint32_t)(ts * set_cols);
+      uint32_t started = 0;
+      int u = 0;
+      for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
+        const int as = a_it % C2_A_SLOTS;
+        P::mbar_wait(cx, &bar.a_full[as], (a_it / C2_A_SLOTS) & 1);
+        P::fence_tc_after();
+        const uint32_t a_hi = P::saddr(cx, A_ring + size_t(as) * 2 * a_part);
+        const uint32_t ah_base = desc_lo(a_hi, a_lbo), al_base = desc_lo(a_hi + a_part, a_lbo);
+        for (int j = 0; j < a.k; ++j, ++u, ++w_it) {
+          const int ws = w_it % C2_W_SLOTS;
+          P::mbar_wait(cx, &bar.w_full[ws], (w_it / C2_W_SLOTS) & 1);
+          P::fence_tc_after();
+          const int chain = (u * a.chains) / n_units;
+          uint32_t acc = (started >> chain) & 1u;
+          started |= 1u << chain;
+          const uint32_t d_pair = d_set + (uint32_t)(chain * pair_cols);
+          const uint32_t row = (uint32_t)(j * a.dil);
+          uint32_t ah = ah_base + row, al = al_base + row;
+          uint32_t wb = desc_lo(P::saddr(cx, W_ring + size_t(ws) * unit_bytes), w_lbo);
+#pragma unroll 1
+          for (int kb = 0; kb < KC / KSTEP; ++kb) {
+            if (P::elect_one(cx)) {
+              if (TF32) {
+                P::mma_tf32(cx, d_pair, ah, wb, idesc2, acc);                            // main | hi*lo
+                P::mma_tf32(cx, d_pair + (uint32_t)NT, al, wb, idesc1, 1u);              //        lo*hi
+              } else {
+                P::mma_bf16(cx, d_pair, ah, wb, idesc2, acc);
+                P::mma_bf16(cx, d_pair + (uint32_t)NT, al, wb, idesc1, 1u);
+              }
+            }
+            if (MH == 2 && mh_live == 2) {
+              if (P::elect_one(cx)) {
+                if (TF32) {
+                  P::mma_tf32(cx, d_pair + (uint32_t)a.mh_stride, ah + 128u, wb, idesc2, acc);
+                  P::mma_tf32(cx, d_pair + (uint32_t)(a.mh_stride + NT), al + 128u, wb, idesc1, 1u);
+                } else {
+                  P::mma_bf16(cx, d_pair + (uint32_t)a.mh_stride, ah + 128u, wb, idesc2, acc);
+                  P::mma_bf16(cx, d_pair + (uint32_t)(a.mh_stride + NT), al + 128u, wb, idesc1, 1u);
+                }
+              }
+            }
+            P::syncwarp();
+            acc = 1u;
+            ah += a_step; al += a_step; wb += w_step;
+          }
+          if (P::elect_one(cx)) P::mma_commit(cx, &bar.w_empty[ws]);
+          P::syncwarp();
+        }
+        if (P::elect_one(cx)) P::mma_commit(cx, &bar.a_empty[as]);
+        P::syncwarp();
+      }
+      if (P::elect_one(cx)) P::mma_commit(cx, &bar.t_full[ts]);
+      P::syncwarp();
+      ++t_it;
+    }
+  } else if (warp < C2_EPI_WARP0) {
+    // ---------------------------------------------------------------------- converters
+    const int ctid = tid - C2_CONV_WARP0 * 32;
+    uint32_t raw_it = 0, a_it = 0;
+    for (int tile = block; tile < total; tile += grid) {
+      int nt, b, t0, L, Lq;
+      if (!decode(tile, nt, b, t0, L, Lq)) continue;
+      const int t_lo = t0 - a.pad;
+      const int off = t_lo - (t_lo & ~3);                               // smem column of stage row 0
+      for (int kc = 0; kc < n_kc; ++kc, ++raw_it, ++a_it) {
+        const int rs = raw_it % C2_RAW_SLOTS, as = a_it % C2_A_SLOTS;
+        P::mbar_wait(cx, &bar.raw_full[rs], (raw_it / C2_RAW_SLOTS) & 1);
+        if (a_it >= C2_A_SLOTS) P::mbar_wait(cx, &bar.a_empty[as], ((a_it / C2_A_SLOTS) - 1) & 1);
+        const float* raw = reinterpret_cast<const float*>(RAW_ring + size_t(rs) * raw_bytes) + off;
+        uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
+        uint8_t* A_lo = A_hi + a_part;
+        for (int g = 0; g < KC / E; ++g) {
+          const float* rg = raw + (size_t)(g * E) * RS;
+          for (int r = ctid; r < R; r += C2_CONV_THREADS) {
+            const int t = t_lo + r;
+            const bool live = t >= 0 && t < L;                          // outside the utterance: zeros, whatever the
+            float v[E];                                                 // (unwritten / stale) smem holds
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+              float x = live ? rg[(size_t)e * RS + r] : 0.f;
+              if (a.pre == PRE_LRELU) x = x > 0.f ? x : x * a.slope;
+              v[e] = x;
+            }
+            const int o = (g * R + r) * 16;
+            if (TF32) {
+              float h[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = P::to_tf32(v[e % E]);
+              *reinterpret_cast<float4*>(A_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(A_lo + o) =
+                  make_float4(v[0] - h[0], v[1 % E] - h[1], v[2 % E] - h[2], v[3 % E] - h[3]);
+            } else {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                const float ph = P::bf16_round(v[e % E]), qh = P::bf16_round(v[(e + 1) % E]);
+                hi[e >> 1] = P::pack_bf16(ph, qh);
+                lo[e >> 1] = P::pack_bf16(v[e % E] - ph, v[(e + 1) % E] - qh);
+              }
+              *reinterpret_cast<uint4*>(A_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(A_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
+        }
+        P::fence_async_proxy();
+        P::mbar_arrive(cx, &bar.a_full[as]);
+        P::mbar_arrive(cx, &bar.raw_empty[rs]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------- epilogue
+    const int ew = warp - C2_EPI_WARP0;                 // 0..7
+    const int q = warp & 3, half = ew >> 2;             // TMEM lane quadrant is fixed by warp id % 4
+    uint32_t t_it = 0;
+    const int n_chunks = NT / 16;
+    const int n_acc = 2 * a.chains;                     // (main | correction) per chain, NT columns apart
+    for (int tile = block; tile < total; tile += grid) {
+      int nt, b, t0, L, Lq;
+      if (!decode(tile, nt, b, t0, L, Lq)) continue;
+      const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
+      const int ts = t_it % t_slots;
+      P::mbar_wait(cx, &bar.t_full[ts], (t_it / t_slots) & 1);
+      P::fence_tc_after();
+      const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
+      float* yb = a.y.p ? a.y.p + (long long)b * a.y.bs : nullptr;
+      float* y2b = a.y2.p ? a.y2.p + (long long)b * a.y2.bs : nullptr;
+      const float* rb = a.r.p ? a.r.p + (long long)b * a.r.bs : nullptr;
+      const int n0 = nt * NT;
+      // this thread's share of the tile: chunks c = half, half+2, ... of each live row half
+      const int my_chunks = (n_chunks - half + 1) / 2;
+      const int work = mh_live * my_chunks;
+      for (int wi = 0; wi < work; ++wi) {
+        const int mh = wi / my_chunks, c = half + 2 * (wi - mh * my_chunks);
+        const int t = t0 + mh * 128 + q * 32 + lane;
+        float v[16];
+        const uint32_t tbase = d_set + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * a.mh_stride + c * 16);
+        P::tmem_ld16(cx, tbase, v);
+        for (int ai = 1; ai < n_acc; ++ai) {             // fp32 round-to-nearest combine of the partial sums
+          float p[16];
+          P::tmem_ld16(cx, tbase + (uint32_t)(ai * NT), p);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += p[i];
+        }
+        if (wi == work - 1) {                            // all of this thread's TMEM reads are done: release the set
+          P::fence_tc_before();
+          P::mbar_arrive(cx, &bar.t_empty[ts]);
+        }
+        if (t >= Lq) continue;
+        const int row0 = n0 + c * 16;
+        if (a.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias + row0 + i);
+        }
+        if (a.bias_item) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias_item + (long long)b * a.bias_item_stride + row0 + i);
+        }
+        if (a.epi == EPI_GATE) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 2)
+            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = wn_gate(v[i], v[i + 1]);
+          continue;
+        }
+        if (a.epi == EPI_RES || a.epi == EPI_MRF || a.epi == EPI_SUBFROM) {
+          float rv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rv[i] = rb[(long long)(row0 + i) * a.r.cs + t];   // 16 loads in flight
+          if (a.epi == EPI_SUBFROM) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = rv[i] - v[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += rv[i];
+          }
+        }
+        if (a.epi == EPI_UPSAMPLE && (a.up == 8 || a.up == 4 || a.up == 2)) {
+          if (a.up == 8) store_upsampled<8>(v, yb, a.y.cs, row0, t, a.up_pad, L * 8);
+          else if (a.up == 4) store_upsampled<4>(v, yb, a.y.cs, row0, t, a.up_pad, L * 4);
+          else store_upsampled<2>(v, yb, a.y.cs, row0, t, a.up_pad, L * 2);
+          continue;
+        }
+        if (a.epi == EPI_MRF) {
+          if (a.mrf == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = v[i];
+          } else {
+            float ov[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = y2b[(long long)(row0 + i) * a.y2.cs + t];
+            const float n_f = (float)a.mrf_n;
+            if (a.mrf == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = ov[i] + v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = (ov[i] + v[i]) / n_f;
+            }
+          }
+          continue;
+        }
+        switch (a.epi) {
+          case EPI_RELU:
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i] > 0.f ? v[i] : 0.f;
+            break;
+          case EPI_WN:
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + i;
+              if (row < a.split) yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + v[i];
+              else {
+                float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
+                *o = a.first ? v[i] : *o + v[i];
+              }
+            }
+            break;
+          case EPI_UPSAMPLE:                              // generic stride (the common ones took the vector path above)
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + i;
+              const int co = row / a.up, phi = row - co * a.up;
+              const int to = t * a.up + phi - a.up_pad;
+              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = v[i];
+            }
+            break;
+          default:                                        // EPI_BIAS, and EPI_RES / EPI_SUBFROM after the residual fold
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i];
+            break;
+        }
+      }
+      ++t_it;
+    }
+  }
+  P::fence_tc_before();
+  P::syncthreads(cx);
+  if (warp == 2) P::tmem_dealloc(cx, tmem_d, (uint32_t)a.tmem_cols);
+}
+
+}  // namespace conv2
+}  // namespace pb200

@@ -1,0 +1,128 @@
+// Host side of the experimental second-generation tensor-core convolution (conv2_body.inl): tiling plan, stacked weight
+// packing and launch-argument fill.  Plain C++ (no CUDA calls): shared by conv_mma2.cu and the CPU model in tests/sim.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace pb200 {
+namespace conv2 {
+
+struct Plan {
+  bool ok = false, tf32 = false;
+  int n_tile = 0, n_tiles = 0, mt = 128, kc = 0, stage_rows = 0, raw_stride = 0, t_slots = 1, tmem_cols = 0, chains = 1;
+  int mh_stride = 0;
+  size_t smem = 0, w_bytes = 0;
+};
+
+inline int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+// Output-row tile N (<= 128 so that the stacked instruction has N' = 2N <= 256), K-chains (2 for tf32x3, DESIGN.md
+// section 3), tile height, TMEM double-buffering and the largest channel chunk that fits 196 KB of shared memory.
+inline bool plan(int ci, int rows, int k, int dil, bool tf32, Plan& p) {
+  p = Plan{};
+  p.tf32 = tf32;
+  const int es = tf32 ? 4 : 2, kstep = tf32 ? 8 : 16;
+  if (ci % kstep != 0 || rows % 16 != 0 || rows < 16) return false;
+  p.chains = tf32 ? 2 : 1;
+  // candidates: (n_tile, mt) with the accumulator sets of one tile within 512 columns; prefer two TMEM sets
+  // (epilogue overlaps the next tile), then the wider row tile (fewer activation re-reads), then the taller tile
+  int best_score = -1;
+  for (int nt = 1; nt <= 64; ++nt) {
+    if (rows % nt || (rows / nt) % 16 || rows / nt > 128) continue;
+    const int n_tile = rows / nt;
+    if (tf32 && n_tile > 64 && !(ci * k >= 900 && rows >= 256)) continue;   // as conv_mma.cu: wide tiles only for long reductions
+    for (int mt : {256, 128}) {
+      if (tf32 && mt != 128) continue;
+      const int set_cols = mt / 128 * p.chains * 2 * n_tile;
+      if (set_cols > 512) continue;
+      const int slots = 2 * set_cols <= 512 ? 2 : 1;
+      const int score = slots * 100000 + n_tile * 100 + mt / 128;
+      if (score > best_score) {
+        best_score = score;
+        p.n_tile = n_tile; p.n_tiles = nt; p.mt = mt; p.t_slots = slots;
+      }
+    }
+  }
+  if (best_score < 0) return false;
+  p.mh_stride = p.chains * 2 * p.n_tile;
+  p.tmem_cols = pow2_cols(p.t_slots * (p.mt / 128) * p.mh_stride);
+  p.stage_rows = (p.mt + (k - 1) * dil + 7) & ~7;
+  if (p.stage_rows * 16 >= (1 << 18)) return false;
+  p.raw_stride = p.stage_rows + 8;
+  for (int c = ci; c >= kstep; c -= kstep) {
+    if (ci % c) continue;
+    const size_t bytes = size_t(2) * c * p.raw_stride * 4 + size_t(2) * 2 * c * p.stage_rows * es + size_t(4) * c * 2 * p.n_tile * es;
+    if (bytes <= (size_t(196) << 10)) {
+      p.kc = c;
+      p.smem = bytes;
+      break;
+    }
+  }
+  if (!p.kc) return false;
+  p.w_bytes = size_t(rows / p.n_tile) * k * ci * 2 * p.n_tile * es;
+  p.ok = true;
+  return true;
+}
+
+inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return uint16_t((u >> 16) | 0x40);
+  return uint16_t((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = uint32_t(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline float f32_to_tf32_rna(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// wsrc: the engine's fp32 layout [ci][k][rows_p] (row fastest).  out: [n tile][tap][ci / E][W_hi rows | W_lo rows][E].
+inline void pack(const float* wsrc, int ci, int k, int rows_p, const Plan& p, uint8_t* out) {
+  const int es = p.tf32 ? 4 : 2, E = 16 / es, NT = p.n_tile;
+  for (int nt = 0; nt < p.n_tiles; ++nt)
+    for (int j = 0; j < k; ++j) {
+      uint8_t* base = out + (size_t(nt) * k + j) * (ci / E) * 2 * NT * 16;
+      for (int cin = 0; cin < ci; ++cin)
+        for (int n = 0; n < NT; ++n) {
+          const float v = wsrc[(size_t(cin) * k + j) * rows_p + nt * NT + n];
+          uint8_t* g = base + size_t(cin / E) * 2 * NT * 16;
+          const size_t hi_pos = size_t(n) * E + (cin % E), lo_pos = size_t(NT + n) * E + (cin % E);
+          if (p.tf32) {
+            const float hi = f32_to_tf32_rna(v), lo = v - hi;
+            memcpy(g + hi_pos * 4, &hi, 4);
+            memcpy(g + lo_pos * 4, &lo, 4);
+          } else {
+            const uint16_t hi = f32_to_bf16_rn(v), lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
+            memcpy(g + hi_pos * 2, &hi, 2);
+            memcpy(g + lo_pos * 2, &lo, 2);
+          }
+        }
+    }
+}
+
+// plan -> the tiling fields of the launch arguments; returns the grid size (0: nothing to do)
+inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len) {
+  a.n_tile = p.n_tile; a.acc_cols = p.n_tile; a.chains = p.chains; a.mh_stride = p.mh_stride; a.sep_corr = 0;
+  a.kc = p.kc; a.stage_rows = p.stage_rows; a.raw_stride = p.raw_stride; a.t_slots = p.t_slots; a.tmem_cols = p.tmem_cols;
+  a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);          // never more chains than weight units
+  a.tiles_per_item = (max_len + p.mt - 1) / p.mt;
+  a.total_tiles = a.tiles_per_item * B * p.n_tiles;
+  a.batch = B;
+  return std::min(a.total_tiles, 148);
+}
+
+}  // namespace conv2
+}  // namespace pb200

@@ -78,6 +78,8 @@ Engine::~Engine() {
                       &off_d_, &sid_d_, &cond_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
                       &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_, &mrf_w_};
   for (auto* d : dbs) d->release();
+  for (auto& kv : v2_layers_)
+    if (kv.second.w_dev) cudaFree(kv.second.w_dev);
   PinnedBuf* pbs[] = {&ids_pin_, &misc_pin_, &audio_pin_, &audio16_pin_, &eps_pin_};
   for (auto* p : pbs) p->release();
   for (auto& ev : ev_)
@@ -113,7 +115,18 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
     m.pre = a.pre; m.slope = a.slope; m.epi = a.epi; m.split = a.split; m.first = a.first;
     m.up = a.up; m.up_pad = a.up_pad; m.mrf = a.mrf; m.mrf_n = a.mrf_n;
   }
+  if (v2_ < 0) {
+    const char* e = std::getenv("PIPER_B200_V2");
+    v2_ = e ? std::atoi(e) : 0;
+  }
   auto go = [&] {
+    if (mma && v2_) {                                  // experimental kernel first; it declines small launches
+      if (const Conv2Layer* l = v2_layer(*w, a)) {
+        MmaConvArgs m2 = m;
+        m2.w = static_cast<const uint8_t*>(l->w_dev);
+        if (launch_conv2(m2, *l, B_, max_len, stream_)) return;
+      }
+    }
     if (mma) launch_conv_mma(m, w->plan, B_, max_len, stream_);
     else launch_conv1d(a, B_, max_len, stream_);
   };
@@ -140,6 +153,21 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   go();
   CUDA_CHECK(cudaEventRecord(r.e1, stream_));
   recs_.push_back(r);
+}
+
+const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a) {
+  auto it = v2_layers_.find(&w);
+  if (it == v2_layers_.end()) {
+    Conv2Layer l;
+    if (conv2_plan(a.ci, a.rows, a.k, a.dil, w.plan.tf32, l)) {
+      std::vector<uint8_t> host(l.w_bytes);
+      conv2_pack(voice_.blob.data() + w.w, a.ci, a.k, a.rows_p, l, host.data());
+      CUDA_CHECK(cudaMalloc(&l.w_dev, l.w_bytes));
+      CUDA_CHECK(cudaMemcpy(l.w_dev, host.data(), l.w_bytes, cudaMemcpyHostToDevice));
+    }
+    it = v2_layers_.emplace(&w, l).first;
+  }
+  return it->second.w_dev ? &it->second : nullptr;
 }
 
 void Engine::profile_begin() {

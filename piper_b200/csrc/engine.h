@@ -126,6 +126,10 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[8] = {};
   DeviceBuf weights_, weights_mma_;
+  // experimental second-generation conv kernel (PIPER_B200_V2=1, conv_mma2.cu): per-layer plan + stacked weights, lazily
+  int v2_ = -1;
+  std::map<const ConvW*, Conv2Layer> v2_layers_;
+  const Conv2Layer* v2_layer(const ConvW& w, const ConvArgs& a);
   // experimental fused MRF stage (mask bit 16, mrf_fused.cu): packed lazily on first use
   void prepare_mrf_fused();
   bool mrf_ready_ = false;

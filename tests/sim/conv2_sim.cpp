@@ -1,0 +1,73 @@
+// CPU functional model run of the experimental second-generation tensor-core convolution: the SAME kernel body as the
+// GPU build (piper_b200/csrc/conv2_body.inl) against the primitive model in sim_prim.h, with the host plan / pack /
+// argument fill of conv2_host.h.  Test infrastructure only (tests/test_conv2_sim.py).
+#include "../../piper_b200/csrc/conv2_host.h"
+
+#include <cmath>
+
+#include "sim_prim.h"
+
+#define MRF_FN inline
+#define MRF_NOINLINE inline
+#include "../../piper_b200/csrc/conv2_body.inl"
+
+using namespace pb200;
+using namespace simtc;
+
+// One convolution layer on a ragged batch.  x [B][ci][cs_x], w [rows][ci][k] fp32 (rows = output rows: C_out, or
+// C_out * up for a lowered ConvTranspose), y / y2 / r as the epilogue needs.  desc = {ci, rows, k, dil, pad, q_extra, pre,
+// epi, split, first, up, up_pad, mrf, mrf_n, tf32, len_scale, cs_x, cs_y, cs_y2, cs_r, C_y, C_y2, C_r, grid}.
+// info (out) = {n_tile, n_tiles, mt, kc, t_slots, chains, total_tiles, smem bytes}.
+extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, const float* bias_item, int bias_item_stride,
+                             float* y, float* y2, const float* r, const int* len, int B, const int* desc, float slope, int max_len,
+                             int* info, char* err, int errcap) {
+  try {
+    const int ci = desc[0], rows = desc[1], k = desc[2], dil = desc[3];
+    const bool tf32 = desc[14] != 0;
+    conv2::Plan p;
+    if (!conv2::plan(ci, rows, k, dil, tf32, p)) throw std::runtime_error("shape outside the kernel's plan");
+    // engine layout of the weights: [ci][k][rows_p], row fastest
+    const int rows_p = rows;
+    std::vector<float> wsrc(size_t(ci) * k * rows_p);
+    for (int co = 0; co < rows; ++co)
+      for (int c = 0; c < ci; ++c)
+        for (int j = 0; j < k; ++j) wsrc[(size_t(c) * k + j) * rows_p + co] = w[(size_t(co) * ci + c) * k + j];
+    std::vector<uint8_t> packed_raw(p.w_bytes + 128);
+    uint8_t* packed = packed_raw.data() + ((128 - reinterpret_cast<uintptr_t>(packed_raw.data()) % 128) % 128);
+    conv2::pack(wsrc.data(), ci, k, rows_p, p, packed);
+
+    MmaConvArgs a;
+    a.x = View{const_cast<float*>(x), (long long)ci * desc[16], desc[16]};
+    a.y = View{y, (long long)desc[20] * desc[17], desc[17]};
+    a.y2 = View{y2, (long long)desc[21] * desc[18], desc[18]};
+    a.r = View{const_cast<float*>(r), (long long)desc[22] * desc[19], desc[19]};
+    a.w = packed; a.bias = bias; a.bias_item = bias_item; a.bias_item_stride = bias_item_stride;
+    a.len = len; a.len_scale = desc[15];
+    a.ci = ci; a.rows = rows; a.k = k; a.dil = dil; a.pad = desc[4]; a.q_extra = desc[5];
+    a.pre = desc[6]; a.slope = slope; a.epi = desc[7]; a.split = desc[8]; a.first = desc[9];
+    a.up = desc[10]; a.up_pad = desc[11]; a.mrf = desc[12]; a.mrf_n = desc[13];
+    int grid = conv2::fill_args(a, p, B, max_len);
+    if (desc[23] > 0) grid = std::min(grid, desc[23]);
+    if (info) {
+      info[0] = p.n_tile; info[1] = p.n_tiles; info[2] = p.mt; info[3] = p.kc; info[4] = p.t_slots; info[5] = a.chains;
+      info[6] = a.total_tiles; info[7] = (int)p.smem;
+    }
+    for (int block = 0; block < grid; ++block) {
+      std::unique_ptr<SimCta> cta(new SimCta);
+      SmemBuf smem(p.smem);
+      cta->smem = smem.p; cta->smem_bytes = (int)p.smem; cta->control_warps = conv2::C2_CONV_WARP0;
+      for (auto& row : cta->tmem) for (float& v : row) v = std::numeric_limits<float>::quiet_NaN();
+      std::unique_ptr<conv2::Barriers<SimMbar>> bar(new conv2::Barriers<SimMbar>);
+      const std::string e = run_cta(*cta, conv2::C2_THREADS, block, grid, [&](SimPrim::Ctx& cx) {
+        if (tf32) conv2::conv2_body<SimPrim, true, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        else if (p.mt == 256) conv2::conv2_body<SimPrim, false, 256>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        else conv2::conv2_body<SimPrim, false, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
+      });
+      if (!e.empty()) throw std::runtime_error("CTA " + std::to_string(block) + ": " + e);
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    if (err && errcap > 0) std::snprintf(err, size_t(errcap), "%s", e.what());
+    return 1;
+  }
+}

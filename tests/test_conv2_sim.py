@@ -1,0 +1,174 @@
+"""The experimental second-generation tensor-core convolution (piper_b200/csrc/conv2_body.inl: uniform-issue TMA warps,
+stacked [W_hi ; W_lo] weights) run on the CPU model of the primitives (tests/sim) against torch, for every fused epilogue,
+both split precisions, ragged batches, dilation, ConvTranspose lowering.  No GPU: checks logic, layouts and the barrier
+protocol, not the hardware's asynchrony."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "sim", "libconv2_sim.so")
+EPI = dict(BIAS=0, RELU=1, RES=2, GATE=3, WN=4, SUBFROM=5, UPSAMPLE=6, MRF=7)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    if not os.path.exists(SIM):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "piper_b200", "csrc"), "../../tests/sim/libconv2_sim.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return C.CDLL(SIM)
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _run(sim, x, w, bias, lens, *, dil=1, pad=None, pre=0, slope=0.1, epi="BIAS", tf32=False, r=None, y2_init=None, split=0,
+         first=0, up=1, up_pad=0, mrf=0, mrf_n=3, q_extra=0, bias_item=None, grid=0, y_channels=None):
+    B, ci, cs_x = x.shape
+    rows, _, k = w.shape
+    if pad is None:
+        pad = (k - 1) // 2 * dil
+    lens = np.asarray(lens, np.int32)
+    C_y = y_channels if y_channels is not None else rows
+    cs_y = cs_x * up
+    y = np.full((B, C_y, cs_y), 7e7, np.float32)
+    y2 = y2_init.copy() if y2_init is not None else np.full((B, max(rows - split, 1), cs_x), 7e7, np.float32)
+    desc = (C.c_int32 * 24)(ci, rows, k, dil, pad, q_extra, pre, EPI[epi], split, first, up, up_pad, mrf, mrf_n, int(tf32), 1,
+                           cs_x, cs_y, y2.shape[2], 0 if r is None else r.shape[2], C_y, y2.shape[1],
+                           0 if r is None else r.shape[1], grid)
+    info = (C.c_int32 * 8)()
+    err = C.create_string_buffer(512)
+    rc = sim.conv2_sim_run(_fp(x), _fp(np.ascontiguousarray(w)), _fp(bias), _fp(bias_item), 0 if bias_item is None else bias_item.shape[1],
+                           _fp(y), _fp(y2), _fp(r), lens.ctypes.data_as(C.POINTER(C.c_int32)), B, desc, C.c_float(slope),
+                           int(lens.max()) + q_extra, info, err, len(err))
+    assert rc == 0, err.value.decode()
+    return y, y2, list(info)
+
+
+def _ragged(B, ci, lens, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    cs = (max(lens) + 3) & ~3
+    x = rng.standard_normal((B, ci, cs)).astype(np.float32) * 40.0      # stale data past each item's length
+    clean = []
+    for b, L in enumerate(lens):
+        v = rng.standard_normal((ci, L)).astype(np.float32) * scale
+        x[b, :, :L] = v
+        clean.append(torch.from_numpy(v))
+    return x, clean
+
+
+def _ref_conv(xb, w, bias, dil, pad, pre, slope):
+    xt = F.leaky_relu(xb, slope) if pre else xb
+    return F.conv1d(xt[None].double(), torch.from_numpy(w).double(), None if bias is None else torch.from_numpy(bias).double(),
+                    dilation=dil, padding=pad)[0].float()
+
+
+def _tol(tf32):
+    return 2e-5 if tf32 else 3e-4      # relative to the output scale: tf32x3 keeps ~21 mantissa bits, bf16x3 ~16
+
+
+@pytest.mark.parametrize("tf32", [False, True])
+@pytest.mark.parametrize("ci,rows,k,dil,lens", [(32, 32, 7, 3, (300, 37, 129)),      # generator stage-3 shape, MT = 256
+                                                 (64, 128, 3, 1, (140, 260)),         # n_tile = 128
+                                                 (48, 96, 5, 2, (131,)),              # rows not a power of two
+                                                 (192, 64, 1, 1, (259, 5))])          # 1x1, several channel chunks
+def test_plain_relu_and_residual_epilogues(sim, tf32, ci, rows, k, dil, lens):
+    if tf32 and ci % 8:
+        pytest.skip("tf32 needs ci % 8 == 0")
+    B = len(lens)
+    x, clean = _ragged(B, ci, lens, seed=ci + k)
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+    bias = rng.standard_normal(rows).astype(np.float32)
+    r = rng.standard_normal((B, rows, x.shape[2])).astype(np.float32)
+    for epi, pre in (("BIAS", 0), ("RELU", 1), ("RES", 1), ("SUBFROM", 0)):
+        y, _, info = _run(sim, x, w, bias, lens, dil=dil, pre=pre, epi=epi, tf32=tf32, r=r if epi in ("RES", "SUBFROM") else None,
+                          grid=3)
+        for b, L in enumerate(lens):
+            ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, pre, 0.1)
+            if epi == "RELU":
+                ref = torch.relu(ref)
+            if epi == "RES":
+                ref = ref + torch.from_numpy(r[b, :, :L])
+            if epi == "SUBFROM":
+                ref = torch.from_numpy(r[b, :, :L]) - ref
+            e = float((torch.from_numpy(y[b, :, :L]) - ref).abs().max())
+            assert e <= _tol(tf32) * max(1.0, float(ref.abs().max())), (epi, b, e, info)
+            assert np.all(y[b, :, L:] == 7e7), "stored outside the utterance"
+
+
+def test_wavenet_gate_and_res_skip(sim):
+    """in_layer -> tanh*sigmoid gate (rows interleaved), then res_skip with in-place residual and skip accumulation."""
+    H, lens = 64, (150, 61)
+    B = len(lens)
+    x, clean = _ragged(B, H, lens, seed=3)
+    rng = np.random.default_rng(2)
+    w = (rng.standard_normal((2 * H, H, 5)) / np.sqrt(H * 5)).astype(np.float32)
+    bias = rng.standard_normal(2 * H).astype(np.float32) * 0.1
+    cond = rng.standard_normal((B, 2 * H)).astype(np.float32) * 0.1            # per-item (speaker) bias
+    y, _, info = _run(sim, x, w, bias, lens, epi="GATE", tf32=True, bias_item=cond, y_channels=H)
+    for b, L in enumerate(lens):
+        pre = _ref_conv(clean[b], w, bias, 1, 2, 0, 0.1) + torch.from_numpy(cond[b])[:, None]
+        ref = torch.tanh(pre[0::2]) * torch.sigmoid(pre[1::2])
+        assert float((torch.from_numpy(y[b, :, :L]) - ref).abs().max()) <= 2e-5, info
+    # res_skip: rows < split update the residual stream (y = r + v), rows >= split accumulate into y2
+    w2 = (rng.standard_normal((2 * H, H, 1)) / np.sqrt(H)).astype(np.float32)
+    b2 = rng.standard_normal(2 * H).astype(np.float32) * 0.1
+    r = rng.standard_normal((B, H, x.shape[2])).astype(np.float32)
+    skip0 = rng.standard_normal((B, H, x.shape[2])).astype(np.float32)
+    for first in (1, 0):
+        y, y2, _ = _run(sim, x, w2, b2, lens, epi="WN", tf32=True, r=r, y2_init=skip0, split=H, first=first, y_channels=H)
+        for b, L in enumerate(lens):
+            v = _ref_conv(clean[b], w2, b2, 1, 0, 0, 0.1)
+            assert float((torch.from_numpy(y[b, :, :L]) - (torch.from_numpy(r[b, :, :L]) + v[:H])).abs().max()) <= 2e-5
+            want = v[H:] if first else torch.from_numpy(skip0[b, :, :L]) + v[H:]
+            assert float((torch.from_numpy(y2[b, :, :L]) - want).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("up,ku", [(8, 16), (4, 8), (2, 4)])
+def test_conv_transpose_lowering(sim, up, ku):
+    """ConvTranspose1d(k = 2 * stride, padding = stride / 2) as stride-phase rows + pixel-shuffle store (voice.cc lowering)."""
+    ci, co, lens = 64, 32, (37, 140)
+    B = len(lens)
+    x, clean = _ragged(B, ci, lens, seed=up)
+    rng = np.random.default_rng(4)
+    Wt = (rng.standard_normal((ci, co, ku)) / np.sqrt(ci * 2)).astype(np.float32)
+    bias_c = rng.standard_normal(co).astype(np.float32)
+    m = ku // up
+    w = np.zeros((co * up, ci, m), np.float32)                      # rows = co * up + phase, taps reversed
+    for j in range(m):
+        for phi in range(up):
+            w[phi::up, :, j] = Wt[:, :, phi + (m - 1 - j) * up].T
+    bias = np.repeat(bias_c, up)
+    y, _, info = _run(sim, x, w, bias, lens, pad=m - 1, pre=1, epi="UPSAMPLE", up=up, up_pad=up // 2, q_extra=m - 1,
+                      y_channels=co)
+    for b, L in enumerate(lens):
+        ref = F.conv_transpose1d(F.leaky_relu(clean[b], 0.1)[None].double(), torch.from_numpy(Wt).double(),
+                                 torch.from_numpy(bias_c).double(), stride=up, padding=up // 2)[0].float()
+        assert ref.shape[1] == L * up
+        e = float((torch.from_numpy(y[b, :, :L * up]) - ref).abs().max())
+        assert e <= 3e-4 * max(1.0, float(ref.abs().max())), (b, e, info)
+        assert np.all(y[b, :, L * up:] == 7e7)
+
+
+def test_mrf_accumulation_modes(sim):
+    C_, lens = 32, (300, 90)
+    B = len(lens)
+    x, clean = _ragged(B, C_, lens, seed=9)
+    rng = np.random.default_rng(5)
+    w = (rng.standard_normal((C_, C_, 3)) / np.sqrt(C_ * 3)).astype(np.float32)
+    bias = rng.standard_normal(C_).astype(np.float32)
+    acc0 = rng.standard_normal((B, C_, x.shape[2])).astype(np.float32)
+    for mode in (0, 1, 2):
+        _, y2, _ = _run(sim, x, w, bias, lens, pre=1, epi="MRF", r=x, y2_init=acc0, mrf=mode, mrf_n=3)
+        for b, L in enumerate(lens):
+            v = _ref_conv(clean[b], w, bias, 1, 1, 1, 0.1) + clean[b]
+            a0 = torch.from_numpy(acc0[b, :, :L])
+            want = v if mode == 0 else (a0 + v if mode == 1 else (a0 + v) / 3)
+            assert float((torch.from_numpy(y2[b, :, :L]) - want).abs().max()) <= 3e-4 * max(1.0, float(want.abs().max()))
