@@ -143,10 +143,11 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
                        float* y);
 
 /* Host-only (no GPU): tiling and packed weights of the EXPERIMENTAL fused MRF stage (csrc/mrf_fused.cu, engine mask bit
- * 16, off by default) for upsample stage `stage` of a voice.  plan = {ok, n_chains, n_steps, pair, hv, to, k[3],
- * dil[3][6]}; w = bf16 tap tiles in consumption order, bias = [step][chain][32].  w / bias may be NULL to query sizes. */
-int pb200_debug_mrf_pack(const char* onnx_path, int32_t stage, int32_t plan[32], uint8_t* w, int64_t* w_bytes,
-                         float* bias, int64_t* n_bias);
+ * 16, off by default) for upsample stage `stage` of a voice; fuse_post != 0 plans it with conv_post + tanh fused behind it.
+ * plan = {ok, n_chains, n_steps, pair, hv, to, k[3], dil[3][6], post_k}; w = bf16 tap tiles in consumption order,
+ * bias = [step][chain][32].  w / bias may be NULL to query sizes. */
+int pb200_debug_mrf_pack(const char* onnx_path, int32_t stage, int32_t fuse_post, int32_t plan[32], uint8_t* w,
+                         int64_t* w_bytes, float* bias, int64_t* n_bias);
 
 /* Host-only: the tensor-core tiling chosen for a layer shape.  out = {supported, rows per tile (MT), channel chunk,
  * staged rows, output rows per tile, number of row tiles, TMEM columns per accumulator, TMEM columns allocated,

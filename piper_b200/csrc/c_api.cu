@@ -109,8 +109,8 @@ int pb200_voice_pack(const char* onnx_path, float* blob, int64_t* n_floats) {
   });
 }
 
-int pb200_debug_mrf_pack(const char* onnx_path, int32_t stage, int32_t plan[32], uint8_t* w, int64_t* w_bytes,
-                         float* bias, int64_t* n_bias) {
+int pb200_debug_mrf_pack(const char* onnx_path, int32_t stage, int32_t fuse_post, int32_t plan[32], uint8_t* w,
+                         int64_t* w_bytes, float* bias, int64_t* n_bias) {
   return guarded([&] {
     if (!onnx_path || !plan || !w_bytes || !n_bias) throw std::runtime_error("pb200_debug_mrf_pack: null argument");
     pb200::PackedVoice pv;
@@ -118,13 +118,14 @@ int pb200_debug_mrf_pack(const char* onnx_path, int32_t stage, int32_t plan[32],
     if (stage < 0 || stage >= int32_t(pv.ups.size())) throw std::runtime_error("pb200_debug_mrf_pack: stage out of range");
     pb200::MrfFusedPlan p;
     const int ch = pv.ups[stage].rows / pv.ups[stage].up;
-    pb200::plan_mrf_fused(pv.resblocks[stage], pv.spec.resblock, ch, p);
+    pb200::plan_mrf_fused(pv.resblocks[stage], pv.spec.resblock, ch, fuse_post ? pv.post_k : 0, p);
     std::memset(plan, 0, 32 * sizeof(int32_t));
     plan[0] = p.ok; plan[1] = p.n_chains; plan[2] = p.n_steps; plan[3] = p.pair; plan[4] = p.hv; plan[5] = p.to;
     for (int c = 0; c < pb200::MRF_MAX_CHAINS; ++c) {
       plan[6 + c] = p.k[c];
       for (int st = 0; st < pb200::MRF_MAX_STEPS; ++st) plan[9 + c * pb200::MRF_MAX_STEPS + st] = p.dil[c][st];
     }
+    plan[27] = p.post_k;
     if (p.ok && w && bias) {
       if (*w_bytes < int64_t(p.w_bytes) || *n_bias < p.n_bias) throw std::runtime_error("pb200_debug_mrf_pack: buffer too small");
       pb200::pack_mrf_fused(pv.blob.data(), pv.resblocks[stage], p, w, bias);

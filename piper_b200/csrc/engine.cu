@@ -552,6 +552,13 @@ void Engine::run_generator() {
       f.x = A; f.y = S; f.len = ylen; f.len_scale = rate; f.slope = 0.1f;
       f.w = mrf_w_.as<uint8_t>() + mrf_w_off_[st];
       f.bias = reinterpret_cast<const float*>(mrf_w_.as<uint8_t>() + mrf_b_off_[st]);
+      if (st + 1 == voice_.ups.size() && mrf_plan_post_.ok && !debug_) {
+        // last stage: conv_post + tanh fused behind it, the stage output never goes to HBM (taps need it: debug off only)
+        f.post_w = W(voice_.post_w); f.post_slope = 0.01f;
+        f.audio = audio_d_.as<float>(); f.out_off = off_d_.as<long long>();
+        launch_mrf_fused(f, mrf_plan_post_, B, L, stream_);
+        return;
+      }
       launch_mrf_fused(f, mrf_plans_[st], B, L, stream_);
       if (debug_) save_tap("stage" + std::to_string(st), S, ch, ylen_h_.data(), rate);
       continue;
@@ -600,7 +607,9 @@ void Engine::prepare_mrf_fused() {
   for (size_t st = 0; st < n; ++st) {
     ch = voice_.ups[st].rows / voice_.ups[st].up;
     MrfFusedPlan& p = mrf_plans_[st];
-    if (!plan_mrf_fused(voice_.resblocks[st], voice_.spec.resblock, ch, p)) continue;
+    if (!plan_mrf_fused(voice_.resblocks[st], voice_.spec.resblock, ch, 0, p)) continue;
+    if (st + 1 == n && ch == voice_.post_c)
+      plan_mrf_fused(voice_.resblocks[st], voice_.spec.resblock, ch, voice_.post_k, mrf_plan_post_);
     const size_t w_off = (host.size() + 127) & ~size_t(127);
     const size_t b_off = w_off + p.w_bytes;
     host.resize(b_off + size_t(p.n_bias) * 4);

@@ -134,6 +134,7 @@ class Engine {
   void prepare_mrf_fused();
   bool mrf_ready_ = false;
   std::vector<MrfFusedPlan> mrf_plans_;
+  MrfFusedPlan mrf_plan_post_;        // last stage with conv_post + tanh fused behind it (used when taps are off)
   std::vector<size_t> mrf_w_off_, mrf_b_off_;
   DeviceBuf mrf_w_;
   int mma_mask_ = 15;  // generator bf16x3; flow, encoder, duration predictor tf32x3 with chained accumulators

@@ -100,6 +100,7 @@ struct MrfFusedPlan {
   int k[MRF_MAX_CHAINS] = {0, 0, 0};
   int dil[MRF_MAX_CHAINS][MRF_MAX_STEPS] = {};
   int hv = 0, to = 0;                           // rows dropped on each side of a 256-row tile / positions stored per tile
+  int post_k = 0;                               // > 0: conv_post (k taps, no bias) + tanh fused behind the stage; its half-width is in hv
   size_t w_bytes = 0;                           // packed tap tiles
   int n_bias = 0;                               // floats
 };
@@ -114,10 +115,16 @@ struct MrfFusedArgs {
   int k[MRF_MAX_CHAINS] = {0, 0, 0};
   int dil[MRF_MAX_CHAINS][MRF_MAX_STEPS] = {};
   int tiles_per_item = 0, total_tiles = 0;
+  // optional fused generator tail: audio[out_off[b] + t] = tanh(conv_post(lrelu_post_slope(y)))  (models.py:364-366)
+  const float* post_w = nullptr;                // [32][post_k]
+  int post_k = 0;
+  float post_slope = 0.01f;
+  float* audio = nullptr;
+  const long long* out_off = nullptr;
 };
 // plan -> launch arguments (shared by the CUDA launcher and the CPU model of the kernel in tests/sim)
 inline void mrf_fill_args(MrfFusedArgs& a, const MrfFusedPlan& p, int B, int max_len) {
-  a.n_chains = p.n_chains; a.n_steps = p.n_steps; a.pair = p.pair; a.hv = p.hv; a.to = p.to;
+  a.n_chains = p.n_chains; a.n_steps = p.n_steps; a.pair = p.pair; a.hv = p.hv; a.to = p.to; a.post_k = p.post_k;
   for (int c = 0; c < MRF_MAX_CHAINS; ++c) {
     a.k[c] = p.k[c];
     for (int s = 0; s < MRF_MAX_STEPS; ++s) a.dil[c][s] = p.dil[c][s];
@@ -125,7 +132,8 @@ inline void mrf_fill_args(MrfFusedArgs& a, const MrfFusedPlan& p, int B, int max
   a.tiles_per_item = (max_len + p.to - 1) / p.to;
   a.total_tiles = a.tiles_per_item * B;
 }
-bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int channels, MrfFusedPlan& p);
+// post_k > 0 plans the stage with conv_post + tanh fused behind it (last stage of the generator only)
+bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int channels, int post_k, MrfFusedPlan& p);
 void pack_mrf_fused(const float* blob, const std::vector<ResBlockW>& stage, const MrfFusedPlan& p, uint8_t* w, float* bias);
 void launch_mrf_fused(MrfFusedArgs a, const MrfFusedPlan& p, int B, int max_len, cudaStream_t st);
 

@@ -77,7 +77,7 @@ const ConvW& step_conv(const ResBlockW& rb, int pair, int s) { return pair == 1 
 
 }  // namespace
 
-bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int channels, MrfFusedPlan& p) {
+bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int channels, int post_k, MrfFusedPlan& p) {
   p = MrfFusedPlan{};
   if (channels != F_C || stage.empty() || int(stage.size()) > MRF_MAX_CHAINS) return false;
   p.n_chains = int(stage.size());
@@ -100,6 +100,11 @@ bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int 
       if (s > 0) later += hw;
     }
     p.hv = std::max(p.hv, later);
+  }
+  if (post_k > 0) {                                                    // fused conv_post: one more halo of (k - 1) / 2
+    if ((post_k & 1) == 0 || post_k > F_POST_MAXK) return false;
+    p.post_k = post_k;
+    p.hv += (post_k - 1) / 2;
   }
   p.to = F_M - 2 * p.hv;
   if (p.to < 64) return false;

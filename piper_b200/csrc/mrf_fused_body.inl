@@ -25,7 +25,9 @@ constexpr int F_OFF_A0 = F_C * F_XS * 4;
 constexpr int F_OFF_AC = F_OFF_A0 + 2 * F_A0_PART;
 constexpr int F_OFF_W = F_OFF_AC + MRF_MAX_CHAINS * 2 * F_AC_PART;
 constexpr int F_OFF_BIAS = F_OFF_W + F_W_SLOTS * F_TAP_BYTES;
-constexpr int F_SMEM = F_OFF_BIAS + MRF_MAX_CHAINS * MRF_MAX_STEPS * F_C * 4;
+constexpr int F_OFF_POST = F_OFF_BIAS + MRF_MAX_CHAINS * MRF_MAX_STEPS * F_C * 4;   // conv_post weights [32][8]
+constexpr int F_POST_MAXK = 7;
+constexpr int F_SMEM = F_OFF_POST + F_C * 8 * 4;
 static_assert(F_SMEM <= 227 * 1024, "fused MRF stage does not fit shared memory");
 constexpr int F_CONV_WARP0 = 3, F_EPI_WARP0 = 5, F_CONV_THREADS = 64, F_EPI_THREADS = 256;
 constexpr int F_THREADS = 13 * 32;        // 416 threads
@@ -70,6 +72,7 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
   uint8_t* AC = smem + F_OFF_AC;
   uint8_t* Wr = smem + F_OFF_W;
   float* bias_s = reinterpret_cast<float*>(smem + F_OFF_BIAS);
+  float* post_s = reinterpret_cast<float*>(smem + F_OFF_POST);
   const int n_chains = a.n_chains, n_steps = a.n_steps, pair = a.pair;
   const int tpi = a.tiles_per_item, total = a.total_tiles;
   const int block = cx.block(), grid = cx.grid();
@@ -78,6 +81,8 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
   for (int i = tid; i < MRF_MAX_CHAINS * 2 * F_AC_PART / 16; i += F_THREADS)
     reinterpret_cast<uint4*>(AC)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < n_chains * n_steps * F_C; i += F_THREADS) bias_s[i] = a.bias[i];
+  if (a.post_w)
+    for (int i = tid; i < F_C * a.post_k; i += F_THREADS) post_s[(i / a.post_k) * 8 + (i % a.post_k)] = a.post_w[i];
   if (warp == 2) P::tmem_alloc(cx, tmem_base_s, 512u);
   if (tid == 0) {
     P::mbar_init(cx, &bar.raw_full, 1); P::mbar_init(cx, &bar.raw_free, F_EPI_THREADS);
@@ -300,10 +305,47 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
           if (last) {
 #pragma unroll
             for (int i = 0; i < F_C; ++i) sum[i] += v[i];
-            if (c == n_chains - 1 && r >= a.hv && r < a.hv + a.to && pos < L) {
-              float* yb = a.y.p + (long long)b * a.y.bs + pos;
+            if (c == n_chains - 1) {
+              const bool stored = r >= a.hv && r < a.hv + a.to && pos < L;
+              if (a.post_w == nullptr) {
+                if (stored) {
+                  float* yb = a.y.p + (long long)b * a.y.bs + pos;
 #pragma unroll
-              for (int i = 0; i < F_C; ++i) yb[(long long)i * a.y.cs] = sum[i] / n_f;
+                  for (int i = 0; i < F_C; ++i) yb[(long long)i * a.y.cs] = sum[i] / n_f;
+                }
+              } else {
+                // Fused generator tail (models.py:364-366): the stage output never goes to HBM.  y -> leaky-relu, zero outside
+                // the utterance (conv_post pads its own input) -> the payload rows of chain 0's operand buffer, free until the
+                // next tile's first epilogue and never its zero guard rows: 8 blocks [256 rows][4 channels] of 16-byte rows.
+#pragma unroll
+                for (int bi = 0; bi < F_C / 4; ++bi) {
+                  float w4[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float yv = sum[bi * 4 + e] / n_f;
+                    w4[e] = inside ? (yv > 0.f ? yv : yv * a.post_slope) : 0.f;
+                  }
+                  uint8_t* blk = AC + (bi < 4 ? bi * F_RA * 16 : F_AC_PART + (bi - 4) * F_RA * 16) + F_GA * 16;
+                  *reinterpret_cast<float4*>(blk + r * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                P::bar_sync(cx, 1, F_EPI_THREADS);
+                if (stored) {
+                  const int half_k = (a.post_k - 1) / 2;
+                  float acc = 0.f;
+                  for (int j = 0; j < a.post_k; ++j) {
+                    const int rr = r + j - half_k;                     // within [hv - half_k, 256 - hv + half_k): exact y rows
+#pragma unroll
+                    for (int bi = 0; bi < F_C / 4; ++bi) {
+                      const uint8_t* blk = AC + (bi < 4 ? bi * F_RA * 16 : F_AC_PART + (bi - 4) * F_RA * 16) + F_GA * 16;
+                      const float4 y4 = *reinterpret_cast<const float4*>(blk + rr * 16);
+                      const float* pw = post_s + bi * 4 * 8 + j;
+                      acc += y4.x * pw[0] + y4.y * pw[8] + y4.z * pw[16] + y4.w * pw[24];
+                    }
+                  }
+                  a.audio[a.out_off[b] + pos] = tanhf(acc);
+                }
+                P::bar_sync(cx, 1, F_EPI_THREADS);                      // the buffer is rewritten by the next tile's first epilogue
+              }
             }
           } else {
             if (closes) {

@@ -21,6 +21,8 @@ struct DevPrim {
   static __device__ __forceinline__ int bcast0(Ctx&, int v) { return __shfl_sync(0xffffffffu, v, 0); }
   static __device__ __forceinline__ void syncwarp() { __syncwarp(); }
   static __device__ __forceinline__ void syncthreads(Ctx&) { __syncthreads(); }
+  // named barrier among `count` threads (a multiple of 32) of the CTA
+  static __device__ __forceinline__ void bar_sync(Ctx&, int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
   static __device__ __forceinline__ bool elect_one(Ctx&) {
     uint32_t pred = 0;
     asm volatile(

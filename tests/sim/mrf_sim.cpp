@@ -13,6 +13,8 @@
 // memory-model fences, PTX encodings.  Test infrastructure only (tests/test_fused_mrf_sim.py).
 #include "../../piper_b200/csrc/kernels.cuh"
 
+#include <cmath>
+
 #include "sim_prim.h"
 
 #define MRF_FN inline
@@ -22,9 +24,11 @@ using namespace pb200;
 using namespace pb200::mrf;
 using namespace simtc;
 
-// plan = the 27 ints pb200_debug_mrf_pack returns.  x / y: [B][32][cs] fp32 (bs = batch stride in floats).
+// plan = the 28 ints pb200_debug_mrf_pack returns.  x / y: [B][32][cs] fp32 (bs = batch stride in floats).
+// post_w != NULL (with a plan made for it): conv_post + tanh fused, audio[out_off[b] + t] written instead of y.
 extern "C" int mrf_sim_run(const float* x, float* y, const int* len, int B, long long bs, int cs, int len_scale,
-                           const uint8_t* w, const float* bias, const int* plan, int max_len, int grid, char* err, int errcap) {
+                           const uint8_t* w, const float* bias, const int* plan, int max_len, int grid, const float* post_w,
+                           float* audio, const long long* out_off, char* err, int errcap) {
   try {
     MrfFusedPlan p;
     p.ok = plan[0] != 0; p.n_chains = plan[1]; p.n_steps = plan[2]; p.pair = plan[3]; p.hv = plan[4]; p.to = plan[5];
@@ -32,11 +36,14 @@ extern "C" int mrf_sim_run(const float* x, float* y, const int* len, int B, long
       p.k[c] = plan[6 + c];
       for (int s = 0; s < MRF_MAX_STEPS; ++s) p.dil[c][s] = plan[9 + c * MRF_MAX_STEPS + s];
     }
+    p.post_k = plan[27];
     if (!p.ok) throw std::runtime_error("plan not ok");
+    if ((p.post_k > 0) != (post_w != nullptr)) throw std::runtime_error("plan and post weights disagree");
     MrfFusedArgs a;
     a.x = View{const_cast<float*>(x), bs, cs};
     a.y = View{y, bs, cs};
     a.len = len; a.len_scale = len_scale; a.w = w; a.bias = bias; a.slope = 0.1f;
+    a.post_w = post_w; a.post_slope = 0.01f; a.audio = audio; a.out_off = out_off;
     mrf_fill_args(a, p, B, max_len);
     if (grid <= 0 || grid > a.total_tiles) grid = a.total_tiles;
     std::string first_err;

@@ -50,6 +50,7 @@ struct SimCta {
   uint32_t tmem_base = 0xdeadbeef;
   uint32_t tmem_cols = 0;
   CtaBarrier sync;
+  CtaBarrier named[16];               // bar.sync id, count (count set on first use)
   std::atomic<bool> abort{false};
   std::mutex err_m;
   std::string err;
@@ -88,6 +89,13 @@ struct SimPrim {
   static int bcast0(Ctx&, int v) { return v; }           // values broadcast in the kernel are warp-uniform by construction
   static void syncwarp() {}
   static void syncthreads(Ctx& c) { c.cta->sync.arrive_and_wait(c.cta->abort); }
+  static void bar_sync(Ctx& c, int id, int count) {
+    check(c, id > 0 && id < 16 && count % 32 == 0, "named barrier id / count");
+    CtaBarrier& b = c.cta->named[id];
+    { std::lock_guard<std::mutex> l(b.m); if (b.n == 0) b.n = count; }
+    check(c, b.n == count, "named barrier used with two different thread counts");
+    b.arrive_and_wait(c.cta->abort);
+  }
   static bool elect_one(Ctx& c) { return (c.tid_ & 31) == 0; }
   static void fence_mbar_init() {}
   static void fence_async_proxy() {}

@@ -125,7 +125,7 @@ def test_fused_kernel_plan_and_packed_taps(lib_built, arch, stage):
     path = voicegen.cached_voice(arch)
     plan = (C.c_int32 * 32)()
     wb, nb = C.c_int64(0), C.c_int64(0)
-    _lib.check(lib.pb200_debug_mrf_pack(path.encode(), stage, plan, None, C.byref(wb), None, C.byref(nb)))
+    _lib.check(lib.pb200_debug_mrf_pack(path.encode(), stage, 0, plan, None, C.byref(wb), None, C.byref(nb)))
     plan_l = list(plan)
     assert plan_l[0] == 1, "a 32-channel stage of a piper preset must be plannable"
     spec, w, attrs = load_voice(path)
@@ -143,7 +143,7 @@ def test_fused_kernel_plan_and_packed_taps(lib_built, arch, stage):
     assert wb.value == 4096 * sum(k) * plan_l[2] and nb.value == plan_l[2] * len(k) * 32
     wbuf = np.zeros(wb.value, np.uint8)
     bbuf = np.zeros(nb.value, np.float32)
-    _lib.check(lib.pb200_debug_mrf_pack(path.encode(), stage, plan, wbuf.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(wb),
+    _lib.check(lib.pb200_debug_mrf_pack(path.encode(), stage, 0, plan, wbuf.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(wb),
                                         bbuf.ctypes.data_as(C.POINTER(C.c_float)), C.byref(nb)))
     o = Oracle(spec, w, attrs)
     dump = {}
@@ -161,5 +161,5 @@ def test_fused_kernel_declines_other_widths(lib_built):
     lib = _lib.load()
     plan = (C.c_int32 * 32)()
     wb, nb = C.c_int64(0), C.c_int64(0)
-    _lib.check(lib.pb200_debug_mrf_pack(voicegen.cached_voice("tiny").encode(), 1, plan, None, C.byref(wb), None, C.byref(nb)))
+    _lib.check(lib.pb200_debug_mrf_pack(voicegen.cached_voice("tiny").encode(), 1, 0, plan, None, C.byref(wb), None, C.byref(nb)))
     assert plan[0] == 0 and wb.value == 0                                # 16 channels: stays on the layer-wise path

@@ -51,6 +51,10 @@ def test_fused_mrf_stage_matches_layerwise_and_oracle(arch, n_ph):
             e_fused = np.abs(out[31][1][i] - r).max()
             assert e_fused <= max(2e-4 * max(1.0, np.abs(r).max()), 2 * e_layer), (i, e_layer, e_fused)
         assert np.abs(out[31][0] - ref).max() <= 1e-3
+        # taps off: the last stage runs with conv_post + tanh fused behind it (no stage output in HBM)
+        v.set_mma(31)
+        audio_tail, _ = v.synthesize(ids, SCALES, eps_dp, eps_z)
+        assert audio_tail.shape == ref.shape and np.abs(audio_tail - ref).max() <= 1e-3
     finally:
         v.close()
 
