@@ -57,7 +57,12 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   if (B <= 0 || max_len <= 0) return true;
   const conv2::Plan p = to_plan(l);
   const int grid = conv2::fill_args(a, p, B, max_len);
-  if (a.total_tiles < 148) return false;                 // small launches stay on the one-tile-per-CTA kernel
+  static int g_small_too = -1;                          // PIPER_B200_V2=2: also take launches with fewer tiles than SMs
+  if (g_small_too < 0) {
+    const char* e = std::getenv("PIPER_B200_V2");
+    g_small_too = (e && std::atoi(e) >= 2) ? 1 : 0;
+  }
+  if (a.total_tiles < 148 && !g_small_too) return false;   // small launches stay on the one-tile-per-CTA kernel
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);

@@ -31,6 +31,7 @@ run uni_small PIPER_B200_UNI=1 PIPER_B200_SMALL=1
 run uni_fused PIPER_B200_UNI=1 PIPER_B200_MMA=31
 run v2 PIPER_B200_V2=1
 run v2_fused PIPER_B200_V2=1 PIPER_B200_MMA=31
+run v2_all_fused PIPER_B200_V2=2 PIPER_B200_MMA=31   # v2 also for launches with < 148 tiles (batch-1 latency)
 PIPER_B200_UNI=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_uni.txt 2>&1
 tail -9 gpurun_out/ab_layer_report_uni.txt
 PIPER_B200_V2=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_v2.txt 2>&1
