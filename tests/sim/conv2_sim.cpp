@@ -14,6 +14,15 @@
 using namespace pb200;
 using namespace simtc;
 
+// info = {ok, n_tile, n_tiles, mt, kc, stage_rows, raw_stride, t_slots, tmem_cols, chains, mh_stride, smem, w_bytes}
+extern "C" void conv2_sim_plan(int ci, int rows, int k, int dil, int tf32, long long* info) {
+  conv2::Plan p;
+  conv2::plan(ci, rows, k, dil, tf32 != 0, p);
+  const long long v[13] = {p.ok, p.n_tile, p.n_tiles, p.mt, p.kc, p.stage_rows, p.raw_stride, p.t_slots, p.tmem_cols, p.chains,
+                           p.mh_stride, (long long)p.smem, (long long)p.w_bytes};
+  for (int i = 0; i < 13; ++i) info[i] = v[i];
+}
+
 // One convolution layer on a ragged batch.  x [B][ci][cs_x], w [rows][ci][k] fp32 (rows = output rows: C_out, or
 // C_out * up for a lowered ConvTranspose), y / y2 / r as the epilogue needs.  desc = {ci, rows, k, dil, pad, q_extra, pre,
 // epi, split, first, up, up_pad, mrf, mrf_n, tf32, len_scale, cs_x, cs_y, cs_y2, cs_r, C_y, C_y2, C_r, grid}.

@@ -172,3 +172,64 @@ def test_mrf_accumulation_modes(sim):
             a0 = torch.from_numpy(acc0[b, :, :L])
             want = v if mode == 0 else (a0 + v if mode == 1 else (a0 + v) / 3)
             assert float((torch.from_numpy(y2[b, :, :L]) - want).abs().max()) <= 3e-4 * max(1.0, float(want.abs().max()))
+
+
+def _piper_layer_shapes():
+    """(ci, rows, k, dil, tf32) of every dense conv the engine sends to the tensor cores, for the three piper presets."""
+    out = set()
+    for H, F_ in ((96, 384), (192, 768)):                      # x-low | medium, high
+        for ci, rows, k in ((H, 3 * H, 1), (H, H, 1), (H, F_, 3), (F_, H, 3), (H, 2 * H, 1)):
+            out.add((ci, rows, k, 1, True))                    # text encoder
+        out.add((H, H, 1, 1, True))                            # duration predictor 1x1
+        for ci, rows, k in ((H // 2, H, 1), (H, 2 * H, 5), (H, 2 * H, 1), (H, H, 1), (H, H // 2, 1)):
+            out.add((ci, rows, k, 1, True))                    # flow
+        out.add((H, 256, 7, 1, False)); out.add((H, 512, 7, 1, False))     # conv_pre
+    for C_, r, ku in ((256, 8, 16), (128, 8, 16), (64, 4, 8), (512, 8, 16), (128, 2, 4), (64, 2, 4)):
+        out.add((C_, C_ // 2 * r, ku // r, 1, False))          # ConvTranspose lowered to stride-phase rows
+    for C_ in (256, 128, 64, 32):
+        for k, ds in ((3, (1, 2)), (5, (2, 6)), (7, (3, 12)), (3, (1, 3, 5)), (7, (1, 3, 5)), (11, (1, 3, 5))):
+            for d in ds:
+                out.add((C_, C_, k, d, False))
+    return sorted(out)
+
+
+def test_plan_respects_hardware_limits_for_every_piper_layer(sim):
+    sim.conv2_sim_plan.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_longlong)]
+    info = (C.c_longlong * 13)()
+    for ci, rows, k, dil, tf32 in _piper_layer_shapes():
+        sim.conv2_sim_plan(ci, rows, k, dil, int(tf32), info)
+        ok, n_tile, n_tiles, mt, kc, stage_rows, raw_stride, t_slots, tmem_cols, chains, mh_stride, smem, w_bytes = list(info)
+        assert ok, (ci, rows, k, dil, tf32)
+        es, kstep = (4, 8) if tf32 else (2, 16)
+        assert n_tile * n_tiles == rows and n_tile % 16 == 0 and 2 * n_tile <= 256       # stacked instruction: N' = 2N <= 256
+        assert chains == (2 if tf32 else 1) and mh_stride == chains * 2 * n_tile
+        assert t_slots * (mt // 128) * mh_stride <= tmem_cols <= 512
+        assert ci % kc == 0 and kc % kstep == 0
+        assert stage_rows >= mt + (k - 1) * dil and stage_rows % 8 == 0 and raw_stride >= stage_rows + 4
+        assert smem == 2 * kc * raw_stride * 4 + 2 * 2 * kc * stage_rows * es + 4 * kc * 2 * n_tile * es <= 196 * 1024
+        assert (kc * raw_stride * 4) % 128 == 0 and (kc * stage_rows * es) % 128 == 0     # ring slots stay 128-byte aligned
+        assert w_bytes == rows * k * ci * 2 * es
+
+
+@pytest.mark.parametrize("ci,rows,k,dil,tf32,epi", [(192, 384, 5, 1, True, "GATE"),     # flow in_layer: 128-wide tiles, one TMEM set
+                                                     (768, 192, 3, 1, True, "BIAS"),     # FFN second conv: 24 channel chunks
+                                                     (192, 256, 7, 1, False, "BIAS"),    # generator conv_pre
+                                                     (128, 128, 7, 12, False, "RES")])   # widest halo of the medium generator
+def test_real_layer_shapes(sim, ci, rows, k, dil, tf32, epi):
+    lens = (150, 40)
+    B = len(lens)
+    x, clean = _ragged(B, ci, lens, seed=rows)
+    rng = np.random.default_rng(7)
+    w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+    bias = rng.standard_normal(rows).astype(np.float32) * 0.1
+    r = rng.standard_normal((B, rows, x.shape[2])).astype(np.float32)
+    y, _, info = _run(sim, x, w, bias, lens, dil=dil, pre=1, epi=epi, tf32=tf32, r=r if epi == "RES" else None,
+                      y_channels=rows // 2 if epi == "GATE" else None, grid=2)
+    for b, L in enumerate(lens):
+        ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, 1, 0.1)
+        if epi == "GATE":
+            ref = torch.tanh(ref[0::2]) * torch.sigmoid(ref[1::2])
+        if epi == "RES":
+            ref = ref + torch.from_numpy(r[b, :, :L])
+        e = float((torch.from_numpy(y[b, :, :L]) - ref).abs().max())
+        assert e <= _tol(tf32) * max(1.0, float(ref.abs().max())), (b, e, info)
