@@ -8,6 +8,8 @@
 // and modules.LayerNorm (modules.py:23-26): LayerNorm over the CHANNEL axis, eps 1e-5.
 #include "kernels.cuh"
 
+#include <cstdlib>
+
 #include <stdexcept>
 
 namespace pb200 {
@@ -237,6 +239,107 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   }
 }
 
+// EXPERIMENTAL (PIPER_B200_LN2=1, off by default, not yet run on a GPU): same arithmetic as layernorm_kernel in the same
+// order, but every warp issues its global loads eight channel rows at a time before using any of them.  The shipped kernel
+// walks its 24 rows (C = 192) one dependent load -> store at a time in both passes, which is what its ~28 us per launch
+// (36 launches per step) looks like: ~2 x 24 exposed L2 / DRAM latencies with only 16 warps per SM to hide them.
+constexpr int LN_U = 8;
+__global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
+  extern __shared__ float sm[];  // [C][33]
+  __shared__ float red[8][32];
+  const int b = blockIdx.z;
+  const int T = a.len[b];
+  const int t0 = blockIdx.x * 32;
+  if (t0 >= T) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = t0 + lane;
+  const bool live = t < T;
+  const int C = a.C;
+  const float* ab = a.a.p + (long long)b * a.a.bs;
+  for (int c0 = warp; c0 < C; c0 += 8 * LN_U) {
+    float v[LN_U];
+    if (a.mode == LN_DW_GELU) {
+      const int half = (a.dw_k - 1) / 2;
+#pragma unroll
+      for (int u = 0; u < LN_U; ++u) {
+        const int c = c0 + 8 * u;
+        v[u] = 0.f;
+        if (live && c < C) {
+          const float* ar = ab + (long long)c * a.a.cs;
+          float acc = __ldg(a.dw_b + c);
+          for (int j = 0; j < a.dw_k; ++j) {
+            const int tt = t + (j - half) * a.dw_dil;
+            if (tt >= 0 && tt < T) acc = fmaf(__ldg(a.dw_w + c * a.dw_k + j), ar[tt], acc);
+          }
+          v[u] = acc;
+        }
+      }
+    } else {
+      float w2[LN_U];
+#pragma unroll
+      for (int u = 0; u < LN_U; ++u) {
+        const int c = c0 + 8 * u;
+        v[u] = 0.f;
+        w2[u] = 0.f;
+        if (live && c < C) {
+          v[u] = ab[(long long)c * a.a.cs + t];
+          if (a.mode == LN_ADD) w2[u] = a.b.p[(long long)b * a.b.bs + (long long)c * a.b.cs + t];
+        }
+      }
+      if (a.mode == LN_ADD) {
+#pragma unroll
+        for (int u = 0; u < LN_U; ++u) v[u] += w2[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LN_U; ++u) {
+      const int c = c0 + 8 * u;
+      if (c < C) sm[c * 33 + lane] = v[u];
+    }
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int c = warp; c < C; c += 8) s += sm[c * 33 + lane];
+  red[warp][lane] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mean += red[w][lane];
+  mean /= (float)C;
+  __syncthreads();
+  float q = 0.f;
+  for (int c = warp; c < C; c += 8) {
+    const float d = sm[c * 33 + lane] - mean;
+    q = fmaf(d, d, q);
+  }
+  red[warp][lane] = q;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) var += red[w][lane];
+  var /= (float)C;
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  if (!live) return;
+  float* yb = a.y.p + (long long)b * a.y.bs;
+  for (int c0 = warp; c0 < C; c0 += 8 * LN_U) {
+    float rv[LN_U];
+#pragma unroll
+    for (int u = 0; u < LN_U; ++u) {                      // the residual loads of the whole batch first
+      const int c = c0 + 8 * u;
+      rv[u] = (a.mode == LN_GELU_RES && c < C) ? a.r.p[(long long)b * a.r.bs + (long long)c * a.r.cs + t] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < LN_U; ++u) {
+      const int c = c0 + 8 * u;
+      if (c >= C) continue;
+      float v = (sm[c * 33 + lane] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
+      if (a.mode == LN_GELU_RES || a.mode == LN_DW_GELU) v = gelu_erf(v);
+      if (a.mode == LN_GELU_RES) v += rv[u];
+      yb[(long long)c * a.y.cs + t] = v;
+    }
+  }
+}
+
 }  // namespace
 
 void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float scale, View x, const int* len, int B,
@@ -278,7 +381,14 @@ void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st) {
     attr_set[dev & 63] = true;
   }
   dim3 grid((Tmax + 31) / 32, 1, B);
-  layernorm_kernel<<<grid, 256, smem, st>>>(a);
+  static int g_ln2 = -1;                                  // experimental batched-load variant (see layernorm_kernel2)
+  if (g_ln2 < 0) {
+    const char* e = std::getenv("PIPER_B200_LN2");
+    g_ln2 = e ? std::atoi(e) : 0;
+    if (g_ln2) cudaFuncSetAttribute(layernorm_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  }
+  if (g_ln2) layernorm_kernel2<<<grid, 256, smem, st>>>(a);
+  else layernorm_kernel<<<grid, 256, smem, st>>>(a);
   count_launch();
 }
 
