@@ -3,6 +3,7 @@
 //   int16 epilogue: per-utterance peak, scale 32767 / max(0.01, peak), clamp, truncate  (piper.cpp:411-431)
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <stdexcept>
 
 namespace pb200 {
@@ -33,6 +34,47 @@ __global__ void __launch_bounds__(256) conv_post_kernel(View x, const float* __r
       const int tt = t0 - half + u;
       float v = (tt >= 0 && tt < L) ? __ldg(xr + tt) : 0.f;
       xs[c * span + u] = v > 0.f ? v : v * slope;
+    }
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float* xr = xs + c * span + threadIdx.x;
+    const float* wr = ws + c * k;
+    for (int j = 0; j < k; ++j) acc = fmaf(wr[j], xr[j], acc);
+  }
+  out[out_off[b] + t] = tanhf(acc);
+}
+
+// EXPERIMENTAL (PIPER_B200_POST2=1, off by default, not yet run on a GPU): the same computation in the same order, with the
+// staging loads of eight channels in flight at once.  The shipped kernel stages its C = 32 rows one exposed load latency
+// after the other (~0.58 ms per step for 0.5 GB, 7x the HBM time).
+__global__ void __launch_bounds__(256) conv_post_kernel2(View x, const float* __restrict__ w, int C, int k, float slope,
+                                                         float* __restrict__ out, const long long* __restrict__ out_off,
+                                                         const int* __restrict__ len, int len_scale) {
+  extern __shared__ float sm[];   // weights [C][k] | activated input tile [C][POST_TT + k - 1]
+  const int b = blockIdx.z;
+  const int L = len[b] * len_scale;
+  const int t0 = blockIdx.x * POST_TT;
+  if (t0 >= L) return;
+  const int half = (k - 1) / 2;
+  const int span = POST_TT + k - 1;
+  float* ws = sm;
+  float* xs = sm + C * k;
+  for (int i = threadIdx.x; i < C * k; i += 256) ws[i] = w[i];
+  const float* xb = x.p + (long long)b * x.bs;
+  for (int u = threadIdx.x; u < span; u += 256) {
+    const int tt = t0 - half + u;
+    const bool in = tt >= 0 && tt < L;
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (in && c0 + e < C) ? __ldg(xb + (long long)(c0 + e) * x.cs + tt) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < C) xs[(c0 + e) * span + u] = v[e] > 0.f ? v[e] : v[e] * slope;
     }
   }
   __syncthreads();
@@ -92,7 +134,14 @@ void launch_conv_post(View x, const float* w, int C, int k, float slope, float* 
     cudaFuncSetAttribute(conv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set[dev & 63] = true;
   }
-  conv_post_kernel<<<grid, 256, smem, st>>>(x, w, C, k, slope, out, out_off, len, len_scale);
+  static int g_post2 = -1;                                // experimental batched-load variant (see conv_post_kernel2)
+  if (g_post2 < 0) {
+    const char* e = std::getenv("PIPER_B200_POST2");
+    g_post2 = e ? std::atoi(e) : 0;
+    if (g_post2) cudaFuncSetAttribute(conv_post_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  }
+  if (g_post2) conv_post_kernel2<<<grid, 256, smem, st>>>(x, w, C, k, slope, out, out_off, len, len_scale);
+  else conv_post_kernel<<<grid, 256, smem, st>>>(x, w, C, k, slope, out, out_off, len, len_scale);
   count_launch();
 }
 
