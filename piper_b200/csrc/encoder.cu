@@ -172,6 +172,152 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, 
   }
 }
 
+// EXPERIMENTAL (PIPER_B200_ATT2=1, off by default, not yet run on a GPU): the same kernel with the staged queries kept
+// per warp as [d][4 queries], so the score loop issues one K load and ONE 16-byte broadcast load per 4 FMAs instead of one
+// K load and four scalar broadcast loads - the loop is bound by the shared-memory pipe.  Same
+// arithmetic in the same order as rel_attention_kernel.
+static_assert(ATT_QPW == 4, "rel_attention_kernel2 packs the four queries of a warp into one float4");
+__global__ void __launch_bounds__(256) rel_attention_kernel2(View qkv, View out, const float* __restrict__ rel_k,
+                                                            const float* __restrict__ rel_v, int H, int dk, int window,
+                                                            const int* __restrict__ len) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int T = len[b];
+  const int i0 = blockIdx.x * ATT_Q;
+  if (i0 >= T) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrel = 2 * window + 1;
+  float* Ks = sm;                       // [dk][33]
+  float* Vs = Ks + dk * 33;             // [dk][33]
+  float* Qs = Vs + dk * 33;             // [ATT_Q][dk]
+  float* Rl = Qs + ATT_Q * dk;          // [ATT_Q][nrel]   relative-key logits per query
+  float* Ev = Rl + ATT_Q * nrel;        // [nrel][dk]      emb_rel_v
+
+  const float* base = qkv.p + (long long)b * qkv.bs;
+  const float* qg = base + (long long)(h * dk) * qkv.cs;
+  const float* kg = base + (long long)(H + h * dk) * qkv.cs;
+  const float* vg = base + (long long)(2 * H + h * dk) * qkv.cs;
+
+  for (int idx = threadIdx.x; idx < ATT_Q * dk; idx += 256) {
+    const int d = idx / ATT_Q, qi = idx - d * ATT_Q;          // consecutive threads -> consecutive query positions
+    const int i = i0 + qi;
+    // per-warp transposed layout [warp][d][ATT_QPW]: one 16-byte broadcast load brings q[d] of the warp's four queries
+    Qs[((qi / ATT_QPW) * dk + d) * ATT_QPW + (qi % ATT_QPW)] = i < T ? qg[(long long)d * qkv.cs + i] / sqrtf((float)dk) : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < nrel * dk; idx += 256) Ev[idx] = rel_v[idx];
+  __syncthreads();
+  // relative-key logits: Rl[qi][r] = q_i . emb_rel_k[r]
+#pragma unroll
+  for (int qq = 0; qq < ATT_QPW; ++qq) {
+    const int qi = warp * ATT_QPW + qq;
+    for (int r = 0; r < nrel; ++r) {
+      float p = 0.f;
+      for (int d = lane; d < dk; d += 32) p += Qs[(warp * dk + d) * ATT_QPW + qq] * __ldg(rel_k + r * dk + d);
+      for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if (lane == 0) Rl[qi * nrel + r] = p;
+    }
+  }
+  __syncwarp();
+
+  float m_run[ATT_QPW], l_run[ATT_QPW], acc[ATT_QPW][ATT_MAXR];
+#pragma unroll
+  for (int qq = 0; qq < ATT_QPW; ++qq) {
+    m_run[qq] = -INFINITY;
+    l_run[qq] = 0.f;
+#pragma unroll
+    for (int r = 0; r < ATT_MAXR; ++r) acc[qq][r] = 0.f;
+  }
+  const int iq0 = i0 + warp * ATT_QPW;            // first query row of this warp
+
+  for (int j0 = 0; j0 < T; j0 += 32) {
+    __syncthreads();  // previous chunk fully consumed
+    for (int idx = threadIdx.x; idx < dk * 32; idx += 256) {
+      const int d = idx >> 5, jj = idx & 31;
+      const int j = j0 + jj;
+      float kv = 0.f, vv = 0.f;
+      if (j < T) {
+        kv = kg[(long long)d * qkv.cs + j];
+        vv = vg[(long long)d * qkv.cs + j];
+      }
+      Ks[d * 33 + jj] = kv;
+      Vs[d * 33 + jj] = vv;
+    }
+    __syncthreads();
+    if (iq0 >= T) continue;                        // warp-uniform; the barriers above are still reached
+    const int j = j0 + lane;
+    const int jn = min(32, T - j0);
+    float s[ATT_QPW];
+#pragma unroll
+    for (int qq = 0; qq < ATT_QPW; ++qq) s[qq] = 0.f;
+    const float4* qw = reinterpret_cast<const float4*>(Qs) + warp * dk;
+    for (int d = 0; d < dk; ++d) {
+      const float kd = Ks[d * 33 + lane];
+      const float4 q4 = qw[d];                          // 2 shared-memory instructions per 4 FMAs instead of 5
+      s[0] = fmaf(q4.x, kd, s[0]);
+      s[1] = fmaf(q4.y, kd, s[1]);
+      s[2] = fmaf(q4.z, kd, s[2]);
+      s[3] = fmaf(q4.w, kd, s[3]);
+    }
+    float p[ATT_QPW];
+#pragma unroll
+    for (int qq = 0; qq < ATT_QPW; ++qq) {
+      const int i = iq0 + qq;
+      float sc = s[qq];
+      const int rel = j - i + window;
+      if (rel >= 0 && rel < nrel) sc += Rl[(warp * ATT_QPW + qq) * nrel + rel];
+      if (j >= T || i >= T) sc = -INFINITY;   // keys past the utterance: masked_fill(-1e4) -> exp underflows to exactly 0
+      float cmax = sc;
+      for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      const float m_new = fmaxf(m_run[qq], cmax);
+      const float corr = (m_new == -INFINITY) ? 1.f : expf(m_run[qq] - m_new);
+      p[qq] = (m_new == -INFINITY) ? 0.f : expf(sc - m_new);
+      float psum = p[qq];
+      for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+      l_run[qq] = l_run[qq] * corr + psum;
+#pragma unroll
+      for (int r = 0; r < ATT_MAXR; ++r) acc[qq][r] *= corr;
+      m_run[qq] = m_new;
+      // banded relative values: keys j with |j - i| <= window inside this chunk
+      const int jlo = max(j0, i - window), jhi = min(j0 + jn - 1, i + window);
+      for (int jb = jlo; jb <= jhi; ++jb) {
+        const float pj = __shfl_sync(0xffffffffu, p[qq], jb - j0);
+        const int relj = jb - i + window;
+#pragma unroll
+        for (int r = 0; r < ATT_MAXR; ++r) {
+          const int d = lane + 32 * r;
+          if (d < dk) acc[qq][r] = fmaf(pj, Ev[relj * dk + d], acc[qq][r]);
+        }
+      }
+    }
+    // P.V: one V read per (key, channel) shared by the warp's queries
+    for (int jj = 0; jj < jn; ++jj) {
+      float pj[ATT_QPW];
+#pragma unroll
+      for (int qq = 0; qq < ATT_QPW; ++qq) pj[qq] = __shfl_sync(0xffffffffu, p[qq], jj);
+#pragma unroll
+      for (int r = 0; r < ATT_MAXR; ++r) {
+        const int d = lane + 32 * r;
+        if (d < dk) {
+          const float v = Vs[d * 33 + jj];
+#pragma unroll
+          for (int qq = 0; qq < ATT_QPW; ++qq) acc[qq][r] = fmaf(pj[qq], v, acc[qq][r]);
+        }
+      }
+    }
+  }
+  float* ob = out.p + (long long)b * out.bs + (long long)(h * dk) * out.cs;
+#pragma unroll
+  for (int qq = 0; qq < ATT_QPW; ++qq) {
+    const int i = iq0 + qq;
+    if (i >= T) continue;
+#pragma unroll
+    for (int r = 0; r < ATT_MAXR; ++r) {
+      const int d = lane + 32 * r;
+      if (d < dk) ob[(long long)d * out.cs + i] = acc[qq][r] / l_run[qq];
+    }
+  }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // LayerNorm over channels for a tile of 32 time steps; 8 warps split the channel axis.
@@ -365,7 +511,14 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
     attr_set[dev & 63] = true;
   }
   dim3 grid((Tmax + ATT_Q - 1) / ATT_Q, n_heads, B);
-  rel_attention_kernel<<<grid, 256, smem, st>>>(qkv, out, rel_k, rel_v, H, dk, window, len);
+  static int g_att2 = -1;
+  if (g_att2 < 0) {
+    const char* e = std::getenv("PIPER_B200_ATT2");
+    g_att2 = e ? std::atoi(e) : 0;
+    if (g_att2) cudaFuncSetAttribute(rel_attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  }
+  if (g_att2) rel_attention_kernel2<<<grid, 256, smem, st>>>(qkv, out, rel_k, rel_v, H, dk, window, len);
+  else rel_attention_kernel<<<grid, 256, smem, st>>>(qkv, out, rel_k, rel_v, H, dk, window, len);
   count_launch();
 }
 
