@@ -31,9 +31,17 @@ struct Barriers {
 MRF_FN uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
 }
-MRF_FN constexpr uint32_t make_idesc(bool tf32, int M, int N) {
-  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+// Operand precision of a layer.  All three are error-compensated three-product schemes (x = hi + lo, w = hi + lo):
+//   PREC_BF16  kind::f16, BF16 operands: 16 mantissa bits kept                 (the shipped generator path)
+//   PREC_TF32  kind::tf32: 21 bits kept, but only K = 8 per instruction        (the shipped encoder / flow path)
+//   PREC_F16   kind::f16, FP16 operands: 22 bits kept at K = 16 per instruction - tf32x3-class accuracy at bf16x3 cost,
+//              half the operand bytes in shared memory and L2 (tools/precision_study.py part 3; operands must stay below
+//              65504 in magnitude, which every activation and weight of the graph does by orders of magnitude)
+enum : int { PREC_BF16 = 0, PREC_TF32 = 1, PREC_F16 = 2 };
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A / B format at bits 7-9 / 10-12 (0 = F16, 1 = BF16, 2 = TF32)
+MRF_FN constexpr uint32_t make_idesc(int prec, int M, int N) {
+  const uint32_t fmt = prec == PREC_TF32 ? 2u : prec == PREC_BF16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 MRF_FN int imax(int a, int b) { return a > b ? a : b; }
 MRF_FN int imin(int a, int b) { return a < b ? a : b; }
@@ -67,9 +75,10 @@ MRF_FN void store_upsampled(const float (&v)[16], float* yb, int cs, int row0, i
   }
 }
 
-template <class P, bool TF32, int MT>
+template <class P, int PREC, int MT>
 MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem, Barriers<typename P::Mbar>& bar,
                        uint32_t* tmem_base_s) {
+  constexpr bool TF32 = PREC == PREC_TF32;
   constexpr int ES = TF32 ? 4 : 2;
   constexpr int E = 16 / ES;
   constexpr int KSTEP = 2 * E;
@@ -175,7 +184,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     // tcgen05 instructions predicated on one elected lane so that every operand stays warp-uniform
     const uint32_t tmem_du = (uint32_t)P::bcast0(cx, (int)tmem_d);
     const uint32_t a_lbo = (uint32_t)R * 16, w_lbo = 2u * (uint32_t)NT * 16;
-    const uint32_t idesc2 = make_idesc(TF32, 128, 2 * NT), idesc1 = make_idesc(TF32, 128, NT);
+    const uint32_t idesc2 = make_idesc(PREC, 128, 2 * NT), idesc1 = make_idesc(PREC, 128, NT);
     const uint32_t a_step = 2u * (uint32_t)R, w_step = 4u * (uint32_t)NT;          // 16-byte units per k-step
     uint32_t a_it = 0, w_it = 0, t_it = 0;
     for (int tile = block; tile < total; tile += grid) {
@@ -284,9 +293,15 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 8; e += 2) {
-                const float ph = P::bf16_round(v[e % E]), qh = P::bf16_round(v[(e + 1) % E]);
-                hi[e >> 1] = P::pack_bf16(ph, qh);
-                lo[e >> 1] = P::pack_bf16(v[e % E] - ph, v[(e + 1) % E] - qh);
+                if (PREC == PREC_F16) {
+                  const float ph = P::f16_round(v[e % E]), qh = P::f16_round(v[(e + 1) % E]);
+                  hi[e >> 1] = P::pack_f16(ph, qh);
+                  lo[e >> 1] = P::pack_f16(v[e % E] - ph, v[(e + 1) % E] - qh);
+                } else {
+                  const float ph = P::bf16_round(v[e % E]), qh = P::bf16_round(v[(e + 1) % E]);
+                  hi[e >> 1] = P::pack_bf16(ph, qh);
+                  lo[e >> 1] = P::pack_bf16(v[e % E] - ph, v[(e + 1) % E] - qh);
+                }
               }
               *reinterpret_cast<uint4*>(A_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(A_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

@@ -13,6 +13,7 @@ namespace conv2 {
 
 struct Plan {
   bool ok = false, tf32 = false;
+  int prec = 0;                       // conv2::PREC_BF16 / PREC_TF32 / PREC_F16
   int n_tile = 0, n_tiles = 0, mt = 128, kc = 0, stage_rows = 0, raw_stride = 0, t_slots = 1, tmem_cols = 0, chains = 1;
   int mh_stride = 0;
   size_t smem = 0, w_bytes = 0;
@@ -22,21 +23,24 @@ inline int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 12
 
 // Output-row tile N (<= 128 so that the stacked instruction has N' = 2N <= 256), K-chains (2 for tf32x3, DESIGN.md
 // section 3), tile height, TMEM double-buffering and the largest channel chunk that fits 196 KB of shared memory.
-inline bool plan(int ci, int rows, int k, int dil, bool tf32, Plan& p) {
+// prec: 0 bf16x3, 1 tf32x3, 2 fp16x3.  chains: K-chains per accumulator pair (2 where fp32-grade accuracy is needed).
+inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p) {
+  const bool tf32 = prec == 1;
   p = Plan{};
   p.tf32 = tf32;
+  p.prec = prec;
   const int es = tf32 ? 4 : 2, kstep = tf32 ? 8 : 16;
   if (ci % kstep != 0 || rows % 16 != 0 || rows < 16) return false;
-  p.chains = tf32 ? 2 : 1;
+  p.chains = chains;
   // candidates: (n_tile, mt) with the accumulator sets of one tile within 512 columns; prefer two TMEM sets
   // (epilogue overlaps the next tile), then the wider row tile (fewer activation re-reads), then the taller tile
   int best_score = -1;
   for (int nt = 1; nt <= 64; ++nt) {
     if (rows % nt || (rows / nt) % 16 || rows / nt > 128) continue;
     const int n_tile = rows / nt;
-    if (tf32 && n_tile > 64 && !(ci * k >= 900 && rows >= 256)) continue;   // as conv_mma.cu: wide tiles only for long reductions
+    if (chains > 1 && n_tile > 64 && !(ci * k >= 900 && rows >= 256)) continue;   // as conv_mma.cu: wide tiles only for long reductions
     for (int mt : {256, 128}) {
-      if (tf32 && mt != 128) continue;
+      if (chains > 1 && mt != 128) continue;
       const int set_cols = mt / 128 * p.chains * 2 * n_tile;
       if (set_cols > 512) continue;
       const int slots = 2 * set_cols <= 512 ? 2 : 1;
@@ -89,6 +93,44 @@ inline float f32_to_tf32_rna(float f) {
   return f;
 }
 
+// IEEE binary16 round-to-nearest-even (overflow -> inf, subnormals kept): what cvt.rn.f16.f32 does
+inline uint16_t f32_to_f16_rn(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x >= 0x7f800000u) return uint16_t(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0u));   // inf / nan
+  if (x >= 0x477ff000u) return uint16_t(sign | 0x7c00u);                                         // rounds to >= 65520: inf
+  if (x < 0x33000001u) return uint16_t(sign);                                                    // below half the smallest subnormal
+  int e = int(x >> 23) - 127;
+  uint32_t m = (x & 0x7fffffu) | 0x800000u;
+  int shift;
+  uint32_t base;
+  if (e < -14) { shift = 13 + (-14 - e); base = 0; }                                             // subnormal result
+  else { shift = 13; base = uint32_t(e + 15) << 10; m &= 0x7fffffu; }
+  const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+  uint32_t r = base + q;
+  if (rem > halfway || (rem == halfway && (q & 1u))) ++r;                                        // carries into the exponent correctly
+  return uint16_t(sign | r);
+}
+inline float f16_to_f32(uint16_t h) {
+  const uint32_t sign = uint32_t(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  uint32_t x;
+  if (e == 0) {
+    if (m == 0) x = sign;
+    else {
+      int sh = 0;
+      uint32_t mm = m;
+      while (!(mm & 0x400u)) { mm <<= 1; ++sh; }
+      x = sign | (uint32_t(113 - sh) << 23) | ((mm & 0x3ffu) << 13);
+    }
+  } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
+  else x = sign | ((e + 112) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &x, 4);
+  return f;
+}
+
 // wsrc: the engine's fp32 layout [ci][k][rows_p] (row fastest).  out: [n tile][tap][ci / E][W_hi rows | W_lo rows][E].
 inline void pack(const float* wsrc, int ci, int k, int rows_p, const Plan& p, uint8_t* out) {
   const int es = p.tf32 ? 4 : 2, E = 16 / es, NT = p.n_tile;
@@ -104,6 +146,10 @@ inline void pack(const float* wsrc, int ci, int k, int rows_p, const Plan& p, ui
             const float hi = f32_to_tf32_rna(v), lo = v - hi;
             memcpy(g + hi_pos * 4, &hi, 4);
             memcpy(g + lo_pos * 4, &lo, 4);
+          } else if (p.prec == 2) {
+            const uint16_t hi = f32_to_f16_rn(v), lo = f32_to_f16_rn(v - f16_to_f32(hi));
+            memcpy(g + hi_pos * 2, &hi, 2);
+            memcpy(g + lo_pos * 2, &lo, 2);
           } else {
             const uint16_t hi = f32_to_bf16_rn(v), lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
             memcpy(g + hi_pos * 2, &hi, 2);

@@ -20,21 +20,21 @@ void count_launch();
 
 namespace {
 
-template <bool TF32, int MT>
+template <int PREC, int MT>
 __global__ void __launch_bounds__(conv2::C2_THREADS, 1) conv2_kernel(const __grid_constant__ MmaConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) conv2::Barriers<uint64_t> bar;
   __shared__ uint32_t tmem_base_s;
   DevPrim::Ctx cx;
-  conv2::conv2_body<DevPrim, TF32, MT>(a, cx, smem, bar, &tmem_base_s);
+  conv2::conv2_body<DevPrim, PREC, MT>(a, cx, smem, bar, &tmem_base_s);
 }
 
 }  // namespace
 
-bool conv2_plan(int ci, int rows, int k, int dil, bool tf32, Conv2Layer& l) {
+bool conv2_plan(int ci, int rows, int k, int dil, int prec, int chains, Conv2Layer& l) {
   conv2::Plan p;
-  if (!conv2::plan(ci, rows, k, dil, tf32, p)) return false;
-  l.tf32 = p.tf32; l.n_tile = p.n_tile; l.n_tiles = p.n_tiles; l.mt = p.mt; l.kc = p.kc; l.stage_rows = p.stage_rows;
+  if (!conv2::plan(ci, rows, k, dil, prec, chains, p)) return false;
+  l.tf32 = p.tf32; l.prec = p.prec; l.n_tile = p.n_tile; l.n_tiles = p.n_tiles; l.mt = p.mt; l.kc = p.kc; l.stage_rows = p.stage_rows;
   l.raw_stride = p.raw_stride; l.t_slots = p.t_slots; l.tmem_cols = p.tmem_cols; l.chains = p.chains; l.mh_stride = p.mh_stride;
   l.smem = p.smem; l.w_bytes = p.w_bytes;
   return true;
@@ -42,7 +42,7 @@ bool conv2_plan(int ci, int rows, int k, int dil, bool tf32, Conv2Layer& l) {
 
 static conv2::Plan to_plan(const Conv2Layer& l) {
   conv2::Plan p;
-  p.ok = true; p.tf32 = l.tf32; p.n_tile = l.n_tile; p.n_tiles = l.n_tiles; p.mt = l.mt; p.kc = l.kc; p.stage_rows = l.stage_rows;
+  p.ok = true; p.tf32 = l.tf32; p.prec = l.prec; p.n_tile = l.n_tile; p.n_tiles = l.n_tiles; p.mt = l.mt; p.kc = l.kc; p.stage_rows = l.stage_rows;
   p.raw_stride = l.raw_stride; p.t_slots = l.t_slots; p.tmem_cols = l.tmem_cols; p.chains = l.chains; p.mh_stride = l.mh_stride;
   p.smem = l.smem; p.w_bytes = l.w_bytes;
   return p;
@@ -67,14 +67,18 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(conv2_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set[dev & 63] = true;
   }
-  if (p.tf32) conv2_kernel<true, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
-  else if (p.mt == 256) conv2_kernel<false, 256><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
-  else conv2_kernel<false, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
+  if (p.prec == 1) conv2_kernel<1, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
+  else if (p.prec == 2 && p.mt == 256) conv2_kernel<2, 256><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
+  else if (p.prec == 2) conv2_kernel<2, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
+  else if (p.mt == 256) conv2_kernel<0, 256><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
+  else conv2_kernel<0, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
   count_launch();
   return true;
 }

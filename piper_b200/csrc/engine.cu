@@ -159,7 +159,15 @@ const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a) {
   auto it = v2_layers_.find(&w);
   if (it == v2_layers_.end()) {
     Conv2Layer l;
-    if (conv2_plan(a.ci, a.rows, a.k, a.dil, w.plan.tf32, l)) {
+    // precision: as the shipped path (bf16x3 generator, tf32x3 elsewhere) or, with PIPER_B200_V2_PREC=f16, fp16x3 for
+    // every family (tf32x3-class accuracy at bf16x3 instruction cost, conv2_body.inl); 2 K-chains where tf32x3 has them
+    static int g_f16 = -1;
+    if (g_f16 < 0) {
+      const char* e = std::getenv("PIPER_B200_V2_PREC");
+      g_f16 = (e && std::string(e) == "f16") ? 1 : 0;
+    }
+    const int prec = g_f16 ? 2 : (w.plan.tf32 ? 1 : 0);
+    if (conv2_plan(a.ci, a.rows, a.k, a.dil, prec, w.plan.tf32 ? 2 : 1, l)) {
       std::vector<uint8_t> host(l.w_bytes);
       conv2_pack(voice_.blob.data() + w.w, a.ci, a.k, a.rows_p, l, host.data());
       CUDA_CHECK(cudaMalloc(&l.w_dev, l.w_bytes));

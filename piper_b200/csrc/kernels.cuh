@@ -83,11 +83,12 @@ void run_mma_bench(int N, int tf32, int n_acc, int iters, int shift, unsigned lo
 // ---- EXPERIMENTAL, off by default (PIPER_B200_V2=1): second-generation persistent tensor-core conv (conv_mma2.cu) ----
 struct Conv2Layer {          // tiling of one layer + where its stacked weights live (filled lazily by the engine)
   bool tf32 = false;
+  int prec = 0;              // 0 bf16x3, 1 tf32x3, 2 fp16x3 (conv2_body.inl)
   int n_tile = 0, n_tiles = 0, mt = 128, kc = 0, stage_rows = 0, raw_stride = 0, t_slots = 1, tmem_cols = 0, chains = 1, mh_stride = 0;
   size_t smem = 0, w_bytes = 0;
   void* w_dev = nullptr;
 };
-bool conv2_plan(int ci, int rows, int k, int dil, bool tf32, Conv2Layer& l);
+bool conv2_plan(int ci, int rows, int k, int dil, int prec, int chains, Conv2Layer& l);
 void conv2_pack(const float* wsrc, int ci, int k, int rows_p, const Conv2Layer& l, uint8_t* out);
 // false: the launch is too small for the persistent kernel (caller falls back to launch_conv_mma)
 bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaStream_t st);

@@ -3,6 +3,7 @@
 // The CPU counterpart (a functional model used by tests) is tests/sim/sim_prim.h.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace pb200 {
@@ -124,6 +125,11 @@ struct DevPrim {
         : "memory");
   }
   static __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+  static __device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
+  static __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);                 // .x = a (low half), .y = b
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
   static __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
   static __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);   // .x = a (low half), .y = b

@@ -15,9 +15,9 @@ using namespace pb200;
 using namespace simtc;
 
 // info = {ok, n_tile, n_tiles, mt, kc, stage_rows, raw_stride, t_slots, tmem_cols, chains, mh_stride, smem, w_bytes}
-extern "C" void conv2_sim_plan(int ci, int rows, int k, int dil, int tf32, long long* info) {
+extern "C" void conv2_sim_plan(int ci, int rows, int k, int dil, int prec, int chains, long long* info) {
   conv2::Plan p;
-  conv2::plan(ci, rows, k, dil, tf32 != 0, p);
+  conv2::plan(ci, rows, k, dil, prec, chains, p);
   const long long v[13] = {p.ok, p.n_tile, p.n_tiles, p.mt, p.kc, p.stage_rows, p.raw_stride, p.t_slots, p.tmem_cols, p.chains,
                            p.mh_stride, (long long)p.smem, (long long)p.w_bytes};
   for (int i = 0; i < 13; ++i) info[i] = v[i];
@@ -25,16 +25,17 @@ extern "C" void conv2_sim_plan(int ci, int rows, int k, int dil, int tf32, long 
 
 // One convolution layer on a ragged batch.  x [B][ci][cs_x], w [rows][ci][k] fp32 (rows = output rows: C_out, or
 // C_out * up for a lowered ConvTranspose), y / y2 / r as the epilogue needs.  desc = {ci, rows, k, dil, pad, q_extra, pre,
-// epi, split, first, up, up_pad, mrf, mrf_n, tf32, len_scale, cs_x, cs_y, cs_y2, cs_r, C_y, C_y2, C_r, grid}.
+// epi, split, first, up, up_pad, mrf, mrf_n, prec (0 bf16x3 / 1 tf32x3 / 2 fp16x3), len_scale, cs_x, cs_y, cs_y2, cs_r, C_y, C_y2, C_r, grid, chains (0 = default)}.
 // info (out) = {n_tile, n_tiles, mt, kc, t_slots, chains, total_tiles, smem bytes}.
 extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, const float* bias_item, int bias_item_stride,
                              float* y, float* y2, const float* r, const int* len, int B, const int* desc, float slope, int max_len,
                              int* info, char* err, int errcap) {
   try {
     const int ci = desc[0], rows = desc[1], k = desc[2], dil = desc[3];
-    const bool tf32 = desc[14] != 0;
+    const int prec = desc[14], chains = desc[24] > 0 ? desc[24] : (prec == 1 ? 2 : 1);
+    const bool tf32 = prec == 1;
     conv2::Plan p;
-    if (!conv2::plan(ci, rows, k, dil, tf32, p)) throw std::runtime_error("shape outside the kernel's plan");
+    if (!conv2::plan(ci, rows, k, dil, prec, chains, p)) throw std::runtime_error("shape outside the kernel's plan");
     // engine layout of the weights: [ci][k][rows_p], row fastest
     const int rows_p = rows;
     std::vector<float> wsrc(size_t(ci) * k * rows_p);
@@ -68,9 +69,11 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
       for (auto& row : cta->tmem) for (float& v : row) v = std::numeric_limits<float>::quiet_NaN();
       std::unique_ptr<conv2::Barriers<SimMbar>> bar(new conv2::Barriers<SimMbar>);
       const std::string e = run_cta(*cta, conv2::C2_THREADS, block, grid, [&](SimPrim::Ctx& cx) {
-        if (tf32) conv2::conv2_body<SimPrim, true, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
-        else if (p.mt == 256) conv2::conv2_body<SimPrim, false, 256>(a, cx, cta->smem, *bar, &cta->tmem_base);
-        else conv2::conv2_body<SimPrim, false, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        if (tf32) conv2::conv2_body<SimPrim, 1, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        else if (prec == 2 && p.mt == 256) conv2::conv2_body<SimPrim, 2, 256>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        else if (prec == 2) conv2::conv2_body<SimPrim, 2, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        else if (p.mt == 256) conv2::conv2_body<SimPrim, 0, 256>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        else conv2::conv2_body<SimPrim, 0, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
       });
       if (!e.empty()) throw std::runtime_error("CTA " + std::to_string(block) + ": " + e);
     }

@@ -67,6 +67,31 @@ inline uint16_t f2bf(float f) {
   return uint16_t((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
 }
 inline float bf2f(uint16_t h) { uint32_t u = uint32_t(h) << 16; float f; memcpy(&f, &u, 4); return f; }
+inline float h2f(uint16_t h) {                                // IEEE binary16 -> float
+  const uint32_t sign = uint32_t(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  uint32_t x;
+  if (e == 0) {
+    if (m == 0) x = sign;
+    else { int sh = 0; uint32_t mm = m; while (!(mm & 0x400u)) { mm <<= 1; ++sh; } x = sign | (uint32_t(113 - sh) << 23) | ((mm & 0x3ffu) << 13); }
+  } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
+  else x = sign | ((e + 112) << 23) | (m << 13);
+  float f; memcpy(&f, &x, 4); return f;
+}
+inline uint16_t f2h(float f) {                                // round to nearest even, overflow -> inf
+  uint32_t x; memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x >= 0x7f800000u) return uint16_t(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0u));
+  if (x >= 0x477ff000u) return uint16_t(sign | 0x7c00u);
+  if (x < 0x33000001u) return uint16_t(sign);
+  const int e = int(x >> 23) - 127;
+  uint32_t m = (x & 0x7fffffu) | 0x800000u, base; int shift;
+  if (e < -14) { shift = 13 + (-14 - e); base = 0; } else { shift = 13; base = uint32_t(e + 15) << 10; m &= 0x7fffffu; }
+  const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+  uint32_t r = base + q;
+  if (rem > halfway || (rem == halfway && (q & 1u))) ++r;
+  return uint16_t(sign | r);
+}
 
 struct SimPrim {
   static constexpr bool kSim = true;
@@ -164,8 +189,8 @@ struct SimPrim {
     const uint32_t b0 = (b_lo & 0x3FFFu) << 4, blbo = ((b_lo >> 16) & 0x3FFFu) << 4;
     const int N = int((idesc >> 17) & 0x3Fu) << 3, M = int((idesc >> 24) & 0x1Fu) << 4;
     check(c, M == 128 && N >= 16 && N <= 256 && N % 16 == 0, "instruction descriptor shape");
-    const uint32_t fmt = TF32 ? 2u : 1u;
-    check(c, ((idesc >> 4) & 3u) == 1 && ((idesc >> 7) & 7u) == fmt && ((idesc >> 10) & 7u) == fmt, "instruction descriptor formats");
+    const uint32_t fmt = (idesc >> 7) & 7u;               // kind::f16: 0 = F16, 1 = BF16; kind::tf32: 2
+    check(c, ((idesc >> 4) & 3u) == 1 && ((idesc >> 10) & 7u) == fmt && (TF32 ? fmt == 2 : fmt <= 1), "instruction descriptor formats");
     const uint32_t col0 = tmem_d & 0xFFFFu;
     check(c, (tmem_d >> 16) == 0 && col0 + N <= c.cta->tmem_cols, "accumulator address outside the TMEM allocation");
     auto elem = [&](uint32_t start, uint32_t lbo, int row, int k) -> float {
@@ -178,7 +203,7 @@ struct SimPrim {
         return f;
       }
       uint16_t h; memcpy(&h, c.cta->smem + addr, 2);
-      return bf2f(h);
+      return fmt == 0 ? h2f(h) : bf2f(h);
     };
     std::vector<float> B(size_t(N) * K);
     for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) B[size_t(n) * K + k] = elem(b0, blbo, n, k);
@@ -217,6 +242,8 @@ struct SimPrim {
     for (int i = 0; i < 16; ++i) c.cta->tmem[lane0 + (c.tid_ & 31)][col + i] = v[i];
   }
   static void tmem_wait_st() {}
+  static float f16_round(float v) { return h2f(f2h(v)); }
+  static uint32_t pack_f16(float a, float b) { return uint32_t(f2h(a)) | (uint32_t(f2h(b)) << 16); }
   static float bf16_round(float v) { return bf2f(f2bf(v)); }
   static uint32_t pack_bf16(float a, float b) { return uint32_t(f2bf(a)) | (uint32_t(f2bf(b)) << 16); }
 };

@@ -28,7 +28,7 @@ def _fp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-def _run(sim, x, w, bias, lens, *, dil=1, pad=None, pre=0, slope=0.1, epi="BIAS", tf32=False, r=None, y2_init=None, split=0,
+def _run(sim, x, w, bias, lens, *, dil=1, pad=None, pre=0, slope=0.1, epi="BIAS", tf32=False, prec=None, chains=0, r=None, y2_init=None, split=0,
          first=0, up=1, up_pad=0, mrf=0, mrf_n=3, q_extra=0, bias_item=None, grid=0, y_channels=None):
     B, ci, cs_x = x.shape
     rows, _, k = w.shape
@@ -39,9 +39,11 @@ def _run(sim, x, w, bias, lens, *, dil=1, pad=None, pre=0, slope=0.1, epi="BIAS"
     cs_y = cs_x * up
     y = np.full((B, C_y, cs_y), 7e7, np.float32)
     y2 = y2_init.copy() if y2_init is not None else np.full((B, max(rows - split, 1), cs_x), 7e7, np.float32)
-    desc = (C.c_int32 * 24)(ci, rows, k, dil, pad, q_extra, pre, EPI[epi], split, first, up, up_pad, mrf, mrf_n, int(tf32), 1,
+    if prec is None:
+        prec = 1 if tf32 else 0
+    desc = (C.c_int32 * 25)(ci, rows, k, dil, pad, q_extra, pre, EPI[epi], split, first, up, up_pad, mrf, mrf_n, prec, 1,
                            cs_x, cs_y, y2.shape[2], 0 if r is None else r.shape[2], C_y, y2.shape[1],
-                           0 if r is None else r.shape[1], grid)
+                           0 if r is None else r.shape[1], grid, chains)
     info = (C.c_int32 * 8)()
     err = C.create_string_buffer(512)
     rc = sim.conv2_sim_run(_fp(x), _fp(np.ascontiguousarray(w)), _fp(bias), _fp(bias_item), 0 if bias_item is None else bias_item.shape[1],
@@ -194,10 +196,10 @@ def _piper_layer_shapes():
 
 
 def test_plan_respects_hardware_limits_for_every_piper_layer(sim):
-    sim.conv2_sim_plan.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_longlong)]
+    sim.conv2_sim_plan.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_longlong)]
     info = (C.c_longlong * 13)()
     for ci, rows, k, dil, tf32 in _piper_layer_shapes():
-        sim.conv2_sim_plan(ci, rows, k, dil, int(tf32), info)
+        sim.conv2_sim_plan(ci, rows, k, dil, int(tf32), 2 if tf32 else 1, info)
         ok, n_tile, n_tiles, mt, kc, stage_rows, raw_stride, t_slots, tmem_cols, chains, mh_stride, smem, w_bytes = list(info)
         assert ok, (ci, rows, k, dil, tf32)
         es, kstep = (4, 8) if tf32 else (2, 16)
@@ -233,3 +235,22 @@ def test_real_layer_shapes(sim, ci, rows, k, dil, tf32, epi):
             ref = ref + torch.from_numpy(r[b, :, :L])
         e = float((torch.from_numpy(y[b, :, :L]) - ref).abs().max())
         assert e <= _tol(tf32) * max(1.0, float(ref.abs().max())), (b, e, info)
+
+
+@pytest.mark.parametrize("ci,rows,k,dil,chains,lens", [(192, 384, 5, 1, 2, (150, 40)),      # flow in_layer with fp16 operands
+                                                        (192, 192, 1, 1, 2, (259, 5)),      # encoder 1x1
+                                                        (32, 32, 7, 12, 1, (300, 90)),      # generator stage 3
+                                                        (768, 192, 3, 1, 2, (131,))])       # FFN second conv
+def test_fp16x3_mode_has_tf32x3_class_accuracy(sim, ci, rows, k, dil, chains, lens):
+    """PREC_F16: FP16 hi/lo operands (22 bits kept, K = 16 per instruction).  Same harness, tf32x3's tolerance."""
+    B = len(lens)
+    x, clean = _ragged(B, ci, lens, seed=k)
+    rng = np.random.default_rng(11)
+    w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+    bias = rng.standard_normal(rows).astype(np.float32) * 0.1
+    y, _, info = _run(sim, x, w, bias, lens, dil=dil, pre=1, prec=2, chains=chains, grid=2)
+    assert info[5] == chains
+    for b, L in enumerate(lens):
+        ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, 1, 0.1)
+        e = float((torch.from_numpy(y[b, :, :L]) - ref).abs().max())
+        assert e <= 2e-5 * max(1.0, float(ref.abs().max())), (b, e, info)

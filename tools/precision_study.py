@@ -5,7 +5,10 @@ from operands rounded like the tensor core sees them: single-pass TF32, bf16x3 (
 Part 2 — the tensor core adds into its fp32 accumulator with truncation (round toward zero): emulate that per k-step
 and evaluate the two mitigations shipped in conv_mma.cu (separate correction accumulator, K split into chains).
 
-usage: python tools/precision_study.py [part1|part2|all]  > profiles/r01_precision_study.txt
+Part 3 - FP16 operands: hi = fp16(x), lo = fp16(x - hi) keeps 22 mantissa bits at kind::f16's K = 16 per instruction,
+i.e. tf32x3-class accuracy at bf16x3 cost (conv2_body.inl PREC_F16); with the accumulator truncation emulated as well.
+
+usage: python tools/precision_study.py [part1|part2|part3|all]  > profiles/r01_precision_study.txt
 """
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -83,6 +86,53 @@ class RZOracle(Oracle):
         return y if b is None else y + b[:, None]
 
 
+def f16(x): return x.to(torch.float16).to(torch.float32)
+
+
+class F16Oracle(Oracle):
+    """hi*hi + hi*lo + lo*hi with FP16 operands, exact accumulation."""
+    scope = ("flow.",)
+
+    def conv(self, x, name, dilation=1, pad=0, groups=1):
+        if groups != 1 or not name.startswith(self.scope):
+            return super().conv(x, name, dilation, pad, groups)
+        w, b = self.w[name + ".weight"], self.w.get(name + ".bias")
+        cv = lambda a, ww: F.conv1d(a[None].double(), ww.double(), None, dilation=dilation, padding=pad)[0]
+        xh, wh = f16(x), f16(w)
+        xl, wl = f16(x - xh), f16(w - wh)
+        y = (cv(xh, wh) + (cv(xh, wl) + cv(xl, wh))).float()
+        return y if b is None else y + b[:, None]
+
+
+class F16RZOracle(Oracle):
+    """FP16 operands, 16 channels per k-step, truncating fp32 accumulation, one (main | correction) pair per K-chain."""
+    scope, chains = ("flow.",), 2
+
+    def conv(self, x, name, dilation=1, pad=0, groups=1):
+        if groups != 1 or not name.startswith(self.scope):
+            return super().conv(x, name, dilation, pad, groups)
+        w, b = self.w[name + ".weight"], self.w.get(name + ".bias")
+        co, ci, k = w.shape
+        xp = F.pad(x, (pad, pad))
+        T = x.shape[1]
+        xh, wh = f16(xp), f16(w)
+        xl, wl = f16(xp - xh), f16(w - wh)
+        steps = [(j, kb) for j in range(k) for kb in range(0, ci, 16)]
+        per_chain = -(-len(steps) // self.chains)
+        total, acc, corr = torch.zeros(T, co), torch.zeros(T, co), torch.zeros(T, co)
+        for s, (j, kb) in enumerate(steps):
+            sl = slice(kb, kb + 16)
+            a_h = xh[sl, j * dilation:j * dilation + T].t().double()
+            a_l = xl[sl, j * dilation:j * dilation + T].t().double()
+            w_h, w_l = wh[:, sl, j].double(), wl[:, sl, j].double()
+            acc = rz32(acc.double() + a_h @ w_h.t())
+            corr = rz32(rz32(corr.double() + a_h @ w_l.t()).double() + a_l @ w_h.t())
+            if (s + 1) % per_chain == 0 or s == len(steps) - 1:
+                total, acc, corr = total + acc + corr, torch.zeros(T, co), torch.zeros(T, co)
+        y = total.t().contiguous()
+        return y if b is None else y + b[:, None]
+
+
 def real_voice():
     for p in ("/root/reference/etc/test_voice.onnx", os.path.join(ROOT, "oracle", "_ref", "voice", "test_voice.onnx")):
         if os.path.exists(p):
@@ -132,9 +182,44 @@ def part2():
               f"max|audio err|={np.abs(out - ref).max():.3e} max|z err|={float((d['z'] - d0['z']).abs().max()):.3e}", flush=True)
 
 
+def part3():
+    path, lines = real_voice()
+    cases = [("real x-low voice", path, lines[2]["phoneme_ids"]),
+             ("synthetic medium", voicegen.cached_voice("medium"), voicegen.benchmark_ids(64))]
+    for tag, p, ids in cases:
+        s, w, a = load_voice(p)
+        rng = np.random.default_rng(4)
+        eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
+        eps_z = rng.standard_normal((s.inter, 6 * len(ids))).astype(np.float32)
+        d0 = {}
+        ref = Oracle(s, w, a).infer(ids, (0.667, 1, 0.8), eps_dp, eps_z, dump=d0)
+        for scope in (("dec.",), ("flow.",), ("enc_p.",), ("dp.",)):
+            o = F16Oracle(s, w, a)
+            o.scope = scope
+            d = {}
+            out = o.infer(ids, (0.667, 1, 0.8), eps_dp, eps_z, dump=d)
+            same = np.array_equal(d["w_ceil"].numpy(), d0["w_ceil"].numpy())
+            err = float(np.abs(out - ref).max()) if out.shape == ref.shape else float("nan")
+            print(f"{tag:18s} {scope[0]:7s} fp16x3  durations_equal={same} max|audio err|={err:.3e}", flush=True)
+    ids = lines[4]["phoneme_ids"]
+    s, w, a = load_voice(path)
+    rng = np.random.default_rng(1235)
+    eps_dp = rng.standard_normal((2, len(ids))).astype(np.float32)
+    eps_z = rng.standard_normal((s.inter, 3 * len(ids))).astype(np.float32)
+    ref = Oracle(s, w, a).infer(ids, (0.667, 1, 0.8), eps_dp, eps_z)
+    for chains in (1, 2):
+        o = F16RZOracle(s, w, a)
+        o.chains = chains
+        out = o.infer(ids, (0.667, 1, 0.8), eps_dp, eps_z)
+        print(f"real x-low voice, flow fp16x3 (K = 16 per step) with RZ accumulation: chains={chains} "
+              f"max|audio err|={np.abs(out - ref).max():.3e}", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("part1", "all"):
         part1()
     if what in ("part2", "all"):
         part2()
+    if what in ("part3", "all"):
+        part3()
