@@ -224,8 +224,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
                 P::mma_tf32(cx, d_pair, ah, wb, idesc2, acc);                            // main | hi*lo
                 P::mma_tf32(cx, d_pair + (uint32_t)NT, al, wb, idesc1, 1u);              //        lo*hi
               } else {
-                P::mma_bf16(cx, d_pair, ah, wb, idesc2, acc);
-                P::mma_bf16(cx, d_pair + (uint32_t)NT, al, wb, idesc1, 1u);
+                P::mma_f16(cx, d_pair, ah, wb, idesc2, acc);
+                P::mma_f16(cx, d_pair + (uint32_t)NT, al, wb, idesc1, 1u);
               }
             }
             if (MH == 2 && mh_live == 2) {
@@ -234,8 +234,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
                   P::mma_tf32(cx, d_pair + (uint32_t)a.mh_stride, ah + 128u, wb, idesc2, acc);
                   P::mma_tf32(cx, d_pair + (uint32_t)(a.mh_stride + NT), al + 128u, wb, idesc1, 1u);
                 } else {
-                  P::mma_bf16(cx, d_pair + (uint32_t)a.mh_stride, ah + 128u, wb, idesc2, acc);
-                  P::mma_bf16(cx, d_pair + (uint32_t)(a.mh_stride + NT), al + 128u, wb, idesc1, 1u);
+                  P::mma_f16(cx, d_pair + (uint32_t)a.mh_stride, ah + 128u, wb, idesc2, acc);
+                  P::mma_f16(cx, d_pair + (uint32_t)(a.mh_stride + NT), al + 128u, wb, idesc1, 1u);
                 }
               }
             }

@@ -19,7 +19,7 @@
 // The reference zero-pads the input of EVERY conv at the utterance edges: operands are written as 0 for positions
 // outside [0, L) whatever the recompute produced there.
 //
-// Split precision as in conv_mma.cu (bf16x3), but with the two weight halves stacked along N so a k-step is two
+// Split precision: FP16 hi/lo operands (fp16x3, 22 mantissa bits at K = 16 per instruction - DESIGN.md section 3), with the two weight halves stacked along N so a k-step is two
 // instructions instead of three (the SS-form instruction is paced by reading A from shared memory):
 //     D[128][ 0..31] += A_hi * W_hi^T,  D[128][32..63] += A_hi * W_lo^T      one tcgen05.mma, N = 64, B = [W_hi ; W_lo]
 //     D[128][32..63] += A_lo * W_hi^T                                         one tcgen05.mma, N = 32
@@ -43,6 +43,7 @@
 #define MRF_FN __device__ __forceinline__
 #include "tc_policy_dev.cuh"
 #include "mrf_fused_body.inl"
+#include "conv2_host.h"   // f32_to_f16_rn / f16_to_f32
 
 namespace pb200 {
 void count_launch();
@@ -56,20 +57,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) mrf_fused_kernel(const __grid_co
   __shared__ uint32_t tmem_base_s;
   DevPrim::Ctx cx;
   mrf_fused_body<DevPrim>(a, cx, smem, bar, &tmem_base_s);
-}
-
-inline uint16_t f32_to_bf16_rn(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return uint16_t((u >> 16) | 0x40);
-  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
-  return uint16_t((u + r) >> 16);
-}
-inline float bf16_to_f32(uint16_t h) {
-  uint32_t u = uint32_t(h) << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
 }
 
 // conv of chain c, step s (ResBlock1 alternates convs1 / convs2; ResBlock2 walks convs)
@@ -117,7 +104,7 @@ bool plan_mrf_fused(const std::vector<ResBlockW>& stage, int resblock_kind, int 
 }
 
 // Tap tiles in consumption order (step-major over the chains), each [ci / 8][64 rows = W_hi co 0..31 | W_lo co 0..31][8 ci]
-// bf16; biases [step][chain][32].  `blob` is the engine's fp32 weight blob: a conv is [ci][k][rows_p], row fastest.
+// fp16; biases [step][chain][32].  `blob` is the engine's fp32 weight blob: a conv is [ci][k][rows_p], row fastest.
 void pack_mrf_fused(const float* blob, const std::vector<ResBlockW>& stage, const MrfFusedPlan& p, uint8_t* w, float* bias) {
   uint16_t* out = reinterpret_cast<uint16_t*>(w);
   for (int s = 0; s < p.n_steps; ++s)
@@ -128,7 +115,7 @@ void pack_mrf_fused(const float* blob, const std::vector<ResBlockW>& stage, cons
         for (int ci = 0; ci < F_C; ++ci)
           for (int co = 0; co < F_C; ++co) {
             const float v = blob[cw.w + (int64_t(ci) * cw.k + j) * cw.rows_p + co];
-            const uint16_t hi = f32_to_bf16_rn(v), lo = f32_to_bf16_rn(v - bf16_to_f32(hi));
+            const uint16_t hi = conv2::f32_to_f16_rn(v), lo = conv2::f32_to_f16_rn(v - conv2::f16_to_f32(hi));
             const int g = ci / 8, e = ci % 8;
             out[(g * 64 + co) * 8 + e] = hi;
             out[(g * 64 + 32 + co) * 8 + e] = lo;

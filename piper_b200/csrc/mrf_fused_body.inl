@@ -19,7 +19,7 @@ constexpr int F_R0 = F_M + 2 * F_G0;      // 280 rows
 constexpr int F_RA = F_M + 2 * F_GA;      // 328 rows
 constexpr int F_XS = F_R0 + 8;            // row stride (floats) of the staged fp32 input
 constexpr int F_W_SLOTS = 6;
-constexpr int F_TAP_BYTES = 4 * 64 * 16;  // one tap: [ci / 8][W_hi rows 0..31 | W_lo rows 0..31][8 x bf16]
+constexpr int F_TAP_BYTES = 4 * 64 * 16;  // one tap: [ci / 8][W_hi rows 0..31 | W_lo rows 0..31][8 x fp16]
 constexpr int F_A0_PART = 4 * F_R0 * 16, F_AC_PART = 4 * F_RA * 16;
 constexpr int F_OFF_A0 = F_C * F_XS * 4;
 constexpr int F_OFF_AC = F_OFF_A0 + 2 * F_A0_PART;
@@ -42,9 +42,11 @@ struct FBarriers {
 MRF_FN uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
   return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-MRF_FN constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Operands are FP16 hi/lo pairs (fp16x3: 22 mantissa bits at kind::f16's K = 16).
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = F16 (format 0 at bits 7-9 / 10-12),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+MRF_FN constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 MRF_FN int imax(int a, int b) { return a > b ? a : b; }
 MRF_FN int imin(int a, int b) { return a < b ? a : b; }
@@ -55,9 +57,9 @@ MRF_FN void store_split8(uint8_t* hi_row, uint8_t* lo_row, const float* v) {
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int e = 0; e < 8; e += 2) {
-    const float ph = P::bf16_round(v[e]), qh = P::bf16_round(v[e + 1]);
-    hi[e >> 1] = P::pack_bf16(ph, qh);
-    lo[e >> 1] = P::pack_bf16(v[e] - ph, v[e + 1] - qh);
+    const float ph = P::f16_round(v[e]), qh = P::f16_round(v[e + 1]);
+    hi[e >> 1] = P::pack_f16(ph, qh);
+    lo[e >> 1] = P::pack_f16(v[e] - ph, v[e + 1] - qh);
   }
   *reinterpret_cast<uint4*>(hi_row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(lo_row) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -159,7 +161,7 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
     // -------------------------------------------------------------------- MMA issue (whole warp converged; only the
     // tcgen05 instructions are predicated on the elected lane so that every operand stays warp-uniform)
     const uint32_t tmem_du = (uint32_t)P::bcast0(cx, (int)tmem_d);
-    constexpr uint32_t idesc64 = make_idesc_bf16(128, 64), idesc32 = make_idesc_bf16(128, 32);
+    constexpr uint32_t idesc64 = make_idesc_f16(128, 64), idesc32 = make_idesc_f16(128, 32);
     uint32_t g_it = 0, w_it = 0, ti = 0, a_par = 0;
     for (int tile = block; tile < total; tile += grid) {
       int b, t0, L;
@@ -195,10 +197,10 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
             for (int kk = 0; kk < F_C / 16; ++kk) {
               const uint32_t accf = (j > 0 || kk > 0) ? 1u : 0u;
               if (P::elect_one(cx)) {
-                P::mma_bf16(cx, d0, ah, wb, idesc64, accf);              // rows   0..127: main | correction (hi*lo)
-                P::mma_bf16(cx, d0 + 32u, al, wb, idesc32, 1u);          //                correction += lo*hi
-                P::mma_bf16(cx, d0 + 64u, ah + 128u, wb, idesc64, accf); // rows 128..255
-                P::mma_bf16(cx, d0 + 96u, al + 128u, wb, idesc32, 1u);
+                P::mma_f16(cx, d0, ah, wb, idesc64, accf);              // rows   0..127: main | correction (hi*lo)
+                P::mma_f16(cx, d0 + 32u, al, wb, idesc32, 1u);          //                correction += lo*hi
+                P::mma_f16(cx, d0 + 64u, ah + 128u, wb, idesc64, accf); // rows 128..255
+                P::mma_f16(cx, d0 + 96u, al + 128u, wb, idesc32, 1u);
               }
               P::syncwarp();
               ah += a_step; al += a_step; wb += 2u * 64u;

@@ -77,7 +77,8 @@ struct DevPrim {
   static __device__ __forceinline__ void tmem_dealloc(Ctx&, uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
   }
-  static __device__ __forceinline__ void mma_bf16(Ctx&, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  // kind::f16: FP16 or BF16 operands, chosen by the instruction descriptor's format fields
+  static __device__ __forceinline__ void mma_f16(Ctx&, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
     constexpr uint32_t HI = (128u >> 4) | (1u << 14);     // SBO = 128 bytes, descriptor version 1
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"

@@ -218,7 +218,7 @@ struct SimPrim {
       }
     }
   }
-  static void mma_bf16(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) { mma_any<false>(c, d, a, b, idesc, acc); }
+  static void mma_f16(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) { mma_any<false>(c, d, a, b, idesc, acc); }
   static void mma_tf32(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) { mma_any<true>(c, d, a, b, idesc, acc); }
   static float to_tf32(float v) {                          // cvt.rna.tf32.f32: nearest, ties away from zero
     uint32_t u; memcpy(&u, &v, 4);

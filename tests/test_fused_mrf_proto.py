@@ -56,19 +56,19 @@ def test_halos_of_the_piper_presets():
 
 
 # ---- the packed operands of the experimental CUDA kernel (csrc/mrf_fused.cu), emulated on the CPU --------------------
-def _bf16(t):
-    return t.to(torch.bfloat16).to(torch.float32)
+def _bf16(t):                 # operand rounding of the kernel: FP16 (fp16x3 split)
+    return t.to(torch.float16).to(torch.float32)
 
 
 def _emulate_kernel_stage(x, plan, w_bytes, bias):
     """Functional model of mrf_fused_kernel: 256-row tiles with one row <-> position mapping for every conv, guard rows,
-    zero-masked operands, stacked [W_hi ; W_lo] tap tiles consumed step-major, bf16x3 products (exact accumulation)."""
+    zero-masked operands, stacked [W_hi ; W_lo] tap tiles consumed step-major, fp16x3 products (exact accumulation)."""
     ok, n_chains, n_steps, pair, hv, TO = plan[:6]
     k = plan[6:9]
     dil = np.asarray(plan[9:27]).reshape(3, 6)
     G0, GA, M, C = 12, 36, 256, 32
     taps = np.frombuffer(w_bytes, np.uint16).reshape(-1, 4, 64, 8)              # [tap][ci / 8][hi co | lo co][ci % 8]
-    taps = torch.from_numpy((taps.astype(np.uint32) << 16).view(np.float32).copy())
+    taps = torch.from_numpy(taps.view(np.float16).astype(np.float32))
     taps = taps.permute(0, 2, 1, 3).reshape(-1, 64, 32)                            # [tap][row][ci]
     bias = torch.from_numpy(bias.reshape(n_steps, n_chains, C).copy())
     L = x.shape[1]
