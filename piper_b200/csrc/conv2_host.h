@@ -44,7 +44,9 @@ inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p
       const int set_cols = mt / 128 * p.chains * 2 * n_tile;
       if (set_cols > 512) continue;
       const int slots = 2 * set_cols <= 512 ? 2 : 1;
-      const int score = slots * 100000 + n_tile * 100 + mt / 128;
+      // accumulator halves start at multiples of n_tile columns: keep them 32-column aligned when the layer allows it
+      // (every accumulator the shipped kernel has exercised on hardware is)
+      const int score = (n_tile % 32 == 0 ? 1000000 : 0) + slots * 100000 + n_tile * 100 + mt / 128;
       if (score > best_score) {
         best_score = score;
         p.n_tile = n_tile; p.n_tiles = nt; p.mt = mt; p.t_slots = slots;
