@@ -291,7 +291,8 @@ def run_engine(args):
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):           # dram__bytes_read+write per launch from the committed `ncu --set full` capture
         traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
-    kname = "conv_mma_persist_kernel (tcgen05)" if dom.endswith(".mma") else "conv1d_kernel (fp32 FFMA)"
+    kname = ("mrf_fused_kernel (tcgen05, one launch per MRF stage; bytes = the layer-wise work it replaces)" if dom.startswith("dec.mrf")
+             else "conv_mma_persist_kernel (tcgen05)" if dom.endswith(".mma") else "conv1d_kernel (fp32 FFMA)")
     roofline = {"kernel": f"{kname}: {dom}", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": traffic,
                 "peak_source": peaks["source"], "avg_launch_us": d["ms"] / d["launches"] * 1e3,

@@ -560,14 +560,44 @@ void Engine::run_generator() {
       f.x = A; f.y = S; f.len = ylen; f.len_scale = rate; f.slope = 0.1f;
       f.w = mrf_w_.as<uint8_t>() + mrf_w_off_[st];
       f.bias = reinterpret_cast<const float*>(mrf_w_.as<uint8_t>() + mrf_b_off_[st]);
-      if (st + 1 == voice_.ups.size() && mrf_plan_post_.ok && !debug_) {
+      // profile record: the layer-wise algorithmic work of everything this one launch replaces, so the
+      // roofline fraction stays comparable with the layer-wise path (and may exceed 1: the fused kernel moves less)
+      const bool tail = st + 1 == voice_.ups.size() && mrf_plan_post_.ok && !debug_;
+      ProfRec pr{};
+      if (profile_) {
+        if (ev_used_ + 2 > ev_pool_.size()) {
+          const size_t old_n = ev_pool_.size();
+          ev_pool_.resize(old_n + 256);
+          for (size_t i = old_n; i < ev_pool_.size(); ++i) CUDA_CHECK(cudaEventCreate(&ev_pool_[i]));
+        }
+        const MrfFusedPlan& pl = tail ? mrf_plan_post_ : mrf_plans_[st];
+        const double Ls = sum_F_ * rate;
+        double taps = 0;
+        for (int c = 0; c < pl.n_chains; ++c) taps += double(pl.k[c]) * pl.n_steps;
+        const double n_convs = double(pl.n_chains) * pl.n_steps;
+        pr.tag = "dec.mrf"; pr.mma = true;
+        pr.bytes = 4.0 * (n_convs * 2.0 * Ls * ch + taps * ch * ch + n_convs * ch);
+        pr.flops = 2.0 * Ls * ch * ch * taps;
+        if (tail) { pr.bytes += 4.0 * (Ls * ch + Ls + double(ch) * voice_.post_k); pr.flops += 2.0 * Ls * ch * voice_.post_k; }
+        pr.ci = ch; pr.rows = ch; pr.k = int(taps); pr.dil = 0; pr.up = 1; pr.max_len = L; pr.len_sum = Ls;
+        pr.e0 = ev_pool_[ev_used_++]; pr.e1 = ev_pool_[ev_used_++];
+        CUDA_CHECK(cudaEventRecord(pr.e0, stream_));
+      }
+      auto done = [&] {
+        if (!profile_) return;
+        CUDA_CHECK(cudaEventRecord(pr.e1, stream_));
+        recs_.push_back(pr);
+      };
+      if (tail) {
         // last stage: conv_post + tanh fused behind it, the stage output never goes to HBM (taps need it: debug off only)
         f.post_w = W(voice_.post_w); f.post_slope = 0.01f;
         f.audio = audio_d_.as<float>(); f.out_off = off_d_.as<long long>();
         launch_mrf_fused(f, mrf_plan_post_, B, L, stream_);
+        done();
         return;
       }
       launch_mrf_fused(f, mrf_plans_[st], B, L, stream_);
+      done();
       if (debug_) save_tap("stage" + std::to_string(st), S, ch, ylen_h_.data(), rate);
       continue;
     }

@@ -35,7 +35,7 @@ rows = []
 for i in range(n_l):
     r = dict(runs[0][i])
     r["us"] = statistics.median(x[i]["us"] for x in runs)
-    if r["mma"]:
+    if r["mma"] and r["tag"] != "dec.mrf":
         tf32 = not r["tag"].startswith("dec")
         L = r["len_sum"] / a.batch
         m = pm.layer(r["tag"], r["tag"], r["ci"], r["rows"], r["k"], r["dil"], L, tf32)
@@ -51,13 +51,14 @@ print(f"{a.arch}, {a.batch} utterances: {n} samples in {ms:.3f} ms (profiled ste
 print(f"{'#':>3s} {'tag':8s} {'ci':>4s} {'rows':>5s} {'k':>2s} {'d':>2s} {'N':>4s} {'mt':>3s} {'tiles':>6s} | {'us':>7s} | {'t_hbm':>6s} {'t_mma':>6s} {'t_w':>6s} | {'us/bound':>8s}")
 fam = {}
 for i, r in enumerate(rows):
-    if r["mma"]:
+    if r["mma"] and "bound" in r:
         print(f"{i:3d} {r['tag']:8s} {r['ci']:4d} {r['rows']:5d} {r['k']:2d} {r['dil']:2d} {r['n_tile']:4d} {r['mt']:3d} {r['tiles']:6d} | {r['us']:7.1f} | "
               f"{r['t_hbm']:6.1f} {r['t_mma']:6.1f} {r['t_w']:6.1f} | {r['us'] / r['bound']:8.2f}")
         f = fam.setdefault(r["tag"], [0.0, 0.0, 0])
         f[0] += r["us"]; f[1] += r["bound"]; f[2] += 1
     else:
-        print(f"{i:3d} {r['tag']:8s} {r['ci']:4d} {r['rows']:5d} {r['k']:2d} {r['dil']:2d}   (CUDA-core kernel)       | {r['us']:7.1f} |")
+        what = "(fused MRF stage, k = taps)" if r["tag"] == "dec.mrf" else "(CUDA-core kernel)       "
+        print(f"{i:3d} {r['tag']:8s} {r['ci']:4d} {r['rows']:5d} {r['k']:2d} {r['dil']:2d}   {what} | {r['us']:7.1f} |")
 print("\nfamily    launches   measured ms   bound ms   ratio")
 for k, (us, b, c) in fam.items():
     print(f"{k:9s} {c:8d} {us / 1e3:13.3f} {b / 1e3:10.3f} {us / b:7.2f}")
