@@ -433,6 +433,10 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
             break;
         }
       }
+      if (work == 0) {                                   // a 16-row tile leaves the odd half of the warps without a chunk:
+        P::fence_tc_before();                            // they still owe the accumulator set their arrival
+        P::mbar_arrive(cx, &bar.t_empty[ts]);
+      }
       ++t_it;
     }
   }

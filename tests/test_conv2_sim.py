@@ -79,7 +79,8 @@ def _tol(tf32):
 @pytest.mark.parametrize("ci,rows,k,dil,lens", [(32, 32, 7, 3, (300, 37, 129)),      # generator stage-3 shape, MT = 256
                                                  (64, 128, 3, 1, (140, 260)),         # n_tile = 128
                                                  (48, 96, 5, 2, (131,)),              # rows not a power of two
-                                                 (192, 64, 1, 1, (259, 5))])          # 1x1, several channel chunks
+                                                 (192, 64, 1, 1, (259, 5)),           # 1x1, several channel chunks
+                                                 (32, 16, 3, 1, (400, 130))])         # one 16-row chunk: half the epilogue warps idle
 def test_plain_relu_and_residual_epilogues(sim, tf32, ci, rows, k, dil, lens):
     if tf32 and ci % 8:
         pytest.skip("tf32 needs ci % 8 == 0")
