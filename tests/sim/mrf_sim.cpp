@@ -4,13 +4,14 @@
 //   * shared memory  = a byte array; "shared addresses" are offsets into it, exactly what the descriptors encode
 //   * TMEM           = float[128 lanes][512 columns]; tcgen05.ld / st check the warp's lane-quadrant rule
 //   * tcgen05.mma    = decoded from the shared-memory descriptor lo words (start, LBO; SBO = 128, no swizzle, K-major)
-//                      and the instruction descriptor (N), executed synchronously; tcgen05.commit = immediate arrive
-//   * cp.async.bulk  = memcpy + complete_tx, with the TMA alignment rules asserted (16-byte addresses and sizes)
+//                      and the instruction descriptor (N); queued and executed LATER, in order, by a "tensor core" thread
+//                      with random pauses; tcgen05.commit arrives when everything queued before it has run
+//   * cp.async.bulk  = queued to a "TMA" thread: memcpy + complete_tx some time later (alignment rules asserted)
 //   * mbarrier       = blocking phase barrier with arrival and transaction counts; a wait that lasts 20 s aborts the run
 //
-// What it can show: index arithmetic, operand layouts, TMEM column maps and the barrier protocol (phases, counts,
-// deadlocks) are consistent and reproduce the oracle.  What it cannot: asynchrony of the real MMA / TMA pipelines,
-// memory-model fences, PTX encodings.  Test infrastructure only (tests/test_fused_mrf_sim.py).
+// What it can show: index arithmetic, operand layouts, TMEM column maps and the barrier protocol - liveness (phases,
+// counts, deadlocks) and sufficiency (a result read before its barrier is stale, an operand overwritten before the engine
+// consumed it is seen overwritten) - reproduce the oracle.  What it cannot: memory-model fences, PTX encodings, speed.  Test infrastructure only (tests/test_fused_mrf_sim.py).
 #include "../../piper_b200/csrc/kernels.cuh"
 
 #include <cmath>

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -42,6 +43,46 @@ struct CtaBarrier {   // __syncthreads for n threads, reusable
   }
 };
 
+// An in-order asynchronous engine (the tensor core, the TMA unit): operations are queued by the issuing thread and executed
+// LATER by a worker, with random pauses, so that (a) results the kernel reads before waiting on the right mbarrier are
+// stale and (b) operands the kernel overwrites before the engine has consumed them are seen overwritten - the two ways a
+// pipelined kernel's barrier protocol can be insufficient even though it never deadlocks.
+struct AsyncEngine {
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<std::function<void()>> q;
+  size_t head = 0;
+  bool stop = false;
+  uint32_t rng = 12345u;
+  std::thread worker;
+  void start(uint32_t seed) {
+    rng = seed * 2654435761u + 1u;
+    worker = std::thread([this] {
+      for (;;) {
+        std::function<void()> op;
+        {
+          std::unique_lock<std::mutex> l(m);
+          cv.wait(l, [this] { return stop || head < q.size(); });
+          if (head >= q.size()) return;                 // stop requested and the queue is drained
+          op = std::move(q[head++]);
+        }
+        rng = rng * 1664525u + 1013904223u;
+        if ((rng >> 28) == 0) std::this_thread::sleep_for(std::chrono::microseconds(50 + ((rng >> 16) & 255)));
+        op();
+      }
+    });
+  }
+  void push(std::function<void()> op) {
+    { std::lock_guard<std::mutex> l(m); q.push_back(std::move(op)); }
+    cv.notify_one();
+  }
+  void finish() {
+    { std::lock_guard<std::mutex> l(m); stop = true; }
+    cv.notify_one();
+    if (worker.joinable()) worker.join();
+  }
+};
+
 struct SimCta {
   uint8_t* smem = nullptr;            // 128-byte aligned, smem_bytes long
   int smem_bytes = 0;
@@ -50,6 +91,7 @@ struct SimCta {
   uint32_t tmem_base = 0xdeadbeef;
   uint32_t tmem_cols = 0;
   CtaBarrier sync;
+  AsyncEngine tensor_core, tma;       // in-order, asynchronous (see AsyncEngine)
   CtaBarrier named[16];               // bar.sync id, count (count set on first use)
   std::atomic<bool> abort{false};
   std::mutex err_m;
@@ -171,8 +213,11 @@ struct SimPrim {
     check(c, (dst & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (bytes & 15) == 0 && bytes > 0,
           "cp.async.bulk needs 16-byte aligned addresses and size");
     check(c, dst + bytes <= (uint32_t)c.cta->smem_bytes, "cp.async.bulk writes past shared memory");
-    memcpy(c.cta->smem + dst, src, bytes);
-    complete_tx(m, bytes);
+    SimCta* cta = c.cta;
+    cta->tma.push([cta, dst, src, bytes, m] {            // lands some time later; the mbarrier is how the kernel finds out
+      memcpy(cta->smem + dst, src, bytes);
+      complete_tx(m, bytes);
+    });
   }
   static void tmem_alloc(Ctx& c, uint32_t* slot, uint32_t cols) {
     check(c, cols >= 32 && cols <= 512 && (cols & (cols - 1)) == 0, "tmem columns must be a power of two in [32, 512]");
@@ -218,8 +263,15 @@ struct SimPrim {
       }
     }
   }
-  static void mma_f16(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) { mma_any<false>(c, d, a, b, idesc, acc); }
-  static void mma_tf32(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) { mma_any<true>(c, d, a, b, idesc, acc); }
+  // issue = enqueue: the operands are read and the accumulator written when the tensor core gets to it
+  static void mma_f16(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) {
+    Ctx cc = c;
+    c.cta->tensor_core.push([cc, d, a, b, idesc, acc]() mutable { try { mma_any<false>(cc, d, a, b, idesc, acc); } catch (const SimAbort&) {} });
+  }
+  static void mma_tf32(Ctx& c, uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t acc) {
+    Ctx cc = c;
+    c.cta->tensor_core.push([cc, d, a, b, idesc, acc]() mutable { try { mma_any<true>(cc, d, a, b, idesc, acc); } catch (const SimAbort&) {} });
+  }
   static float to_tf32(float v) {                          // cvt.rna.tf32.f32: nearest, ties away from zero
     uint32_t u; memcpy(&u, &v, 4);
     if ((u & 0x7f800000u) == 0x7f800000u) return v;
@@ -228,7 +280,11 @@ struct SimPrim {
     return f;
   }
   static float ldg(const float* p) { return *p; }
-  static void mma_commit(Ctx& c, Mbar* m) { mbar_arrive(c, m); }   // the model executes MMAs synchronously
+  // tcgen05.commit: the arrival happens when every MMA issued before it has completed (the engine is in order)
+  static void mma_commit(Ctx& c, Mbar* m) {
+    Ctx cc = c;
+    c.cta->tensor_core.push([cc, m]() mutable { try { mbar_arrive(cc, m); } catch (const SimAbort&) {} });
+  }
   static void tmem_ld16(Ctx& c, uint32_t taddr, float (&v)[16]) {
     const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFFu;
     check(c, lane0 == 32u * ((c.tid_ >> 5) & 3), "tcgen05.ld outside the warp's TMEM lane quadrant (warp id % 4)");
@@ -253,6 +309,8 @@ struct SimPrim {
 template <class Body>
 inline std::string run_cta(SimCta& cta, int threads, int block, int grid, Body body) {
   cta.sync.n = threads;
+  cta.tensor_core.start(2u * (uint32_t)block + 1u);
+  cta.tma.start(2u * (uint32_t)block + 2u);
   std::vector<std::thread> th;
   for (int t = 0; t < threads; ++t)
     th.emplace_back([&, t] {
@@ -265,6 +323,8 @@ inline std::string run_cta(SimCta& cta, int threads, int block, int grid, Body b
       }
     });
   for (auto& t : th) t.join();
+  cta.tensor_core.finish();
+  cta.tma.finish();
   return cta.err;
 }
 
