@@ -40,7 +40,7 @@ inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p
     const int n_tile = rows / nt;
     if (chains > 1 && n_tile > 64 && !(ci * k >= 900 && rows >= 256)) continue;   // as conv_mma.cu: wide tiles only for long reductions
     for (int mt : {256, 128}) {
-      if (chains > 1 && mt != 128) continue;
+      if ((chains > 1 || tf32) && mt != 128) continue;     // 256-row tiles: single-chain bf16 / fp16 layers only (kernel instantiations)
       const int set_cols = mt / 128 * p.chains * 2 * n_tile;
       if (set_cols > 512) continue;
       const int slots = 2 * set_cols <= 512 ? 2 : 1;

@@ -255,3 +255,32 @@ def test_fp16x3_mode_has_tf32x3_class_accuracy(sim, ci, rows, k, dil, chains, le
         ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, 1, 0.1)
         e = float((torch.from_numpy(y[b, :, :L]) - ref).abs().max())
         assert e <= 2e-5 * max(1.0, float(ref.abs().max())), (b, e, info)
+
+
+def test_seeded_random_shapes(sim):
+    """A small seeded sample of tools/conv2_fuzz.py (random shapes, precisions, epilogues, ragged batches, grid sizes)."""
+    rng = np.random.default_rng(2024)
+    done = 0
+    while done < 10:
+        prec = int(rng.integers(0, 3))
+        ci = int(rng.choice([16, 32, 48, 64, 96, 128, 192]))
+        rows = int(rng.choice([16, 32, 48, 64, 96, 128, 192, 384]))
+        k = int(rng.choice([1, 3, 5, 7]))
+        dil = int(rng.choice([1, 2, 3, 6])) if k > 1 else 1
+        B = int(rng.integers(1, 4))
+        lens = tuple(int(v) for v in rng.integers(1, 400, size=B))
+        epi = str(rng.choice(["BIAS", "RES", "RELU"]))
+        pre, chains, grid = int(rng.integers(0, 2)), int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        x, clean = _ragged(B, ci, lens, seed=done)
+        w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+        bias = rng.standard_normal(rows).astype(np.float32)
+        r = rng.standard_normal((B, rows, x.shape[2])).astype(np.float32)
+        y, _, info = _run(sim, x, w, bias, lens, dil=dil, pre=pre, epi=epi, prec=prec, chains=chains, r=r if epi == "RES" else None,
+                          grid=grid)
+        for b, L in enumerate(lens):
+            ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, pre, 0.1)
+            ref = torch.relu(ref) if epi == "RELU" else ref + torch.from_numpy(r[b, :, :L]) if epi == "RES" else ref
+            e = float((torch.from_numpy(y[b, :, :L]) - ref).abs().max()) / max(1.0, float(ref.abs().max()))
+            assert e <= (3e-4 if prec == 0 else 2e-5), (prec, ci, rows, k, dil, lens, epi, chains, grid, e, info)
+            assert np.all(y[b, :, L:] == 7e7)
+        done += 1
