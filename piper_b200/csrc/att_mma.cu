@@ -1,0 +1,49 @@
+// EXPERIMENTAL - OFF BY DEFAULT (PIPER_B200_ATT3=1).  CUDA instantiation of the tensor-core relative-position attention;
+// the body is att_body.inl (design notes there), the primitives tc_policy_dev.cuh.  The same body runs on the CPU model of
+// the primitives in tests/test_att_sim.py; it has NOT yet run on a GPU.
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <stdexcept>
+
+#define MRF_FN __device__ __forceinline__
+#include "tc_policy_dev.cuh"
+#include "att_body.inl"
+
+namespace pb200 {
+void count_launch();
+
+namespace {
+__global__ void __launch_bounds__(att::A_THREADS, 1) att_kernel(const __grid_constant__ att::Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) att::Barriers<uint64_t> bar;
+  __shared__ uint32_t tmem_base_s;
+  DevPrim::Ctx cx;
+  att::att_body<DevPrim>(a, cx, smem, bar, &tmem_base_s);
+}
+}  // namespace
+
+// false: shape outside what the kernel handles (caller keeps the CUDA-core kernel)
+bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
+                             const int* len, int B, int Tmax, cudaStream_t st) {
+  if (B <= 0 || Tmax <= 0) return true;
+  const int dk = H / n_heads;
+  if (window != 4 || dk % 16 != 0 || dk > att::A_MAXDK || dk * n_heads != H) return false;
+  att::Args a;
+  a.qkv = qkv; a.out = out; a.rel_k = rel_k; a.rel_v = rel_v; a.len = len;
+  a.H = H; a.dk = dk; a.n_heads = n_heads; a.q_tiles = (Tmax + att::A_QT - 1) / att::A_QT;
+  const int smem = att::smem_bytes(dk);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaFuncSetAttribute(att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set[dev & 63] = true;
+  }
+  att_kernel<<<a.q_tiles * n_heads * B, att::A_THREADS, smem, st>>>(a);
+  count_launch();
+  return true;
+}
+
+}  // namespace pb200

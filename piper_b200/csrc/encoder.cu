@@ -511,6 +511,12 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
     attr_set[dev & 63] = true;
   }
   dim3 grid((Tmax + ATT_Q - 1) / ATT_Q, n_heads, B);
+  static int g_att3 = -1;                                 // experimental tensor-core attention (att_mma.cu)
+  if (g_att3 < 0) {
+    const char* e = std::getenv("PIPER_B200_ATT3");
+    g_att3 = e ? std::atoi(e) : 0;
+  }
+  if (g_att3 && launch_rel_attention_tc(qkv, out, rel_k, rel_v, H, n_heads, window, len, B, Tmax, st)) return;
   static int g_att2 = -1;
   if (g_att2 < 0) {
     const char* e = std::getenv("PIPER_B200_ATT2");

@@ -145,6 +145,10 @@ void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float 
 void launch_rel_attention(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
                           const int* len, int B, int Tmax, cudaStream_t st);
 
+// EXPERIMENTAL, off by default (PIPER_B200_ATT3=1): the same attention on the tensor cores (att_mma.cu); false = shape not handled
+bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
+                             const int* len, int B, int Tmax, cudaStream_t st);
+
 enum LnMode {
   LN_ADD = 0,          // y = LN(a + b)
   LN_GELU_RES = 1,     // y = r + gelu(LN(a))

@@ -8,6 +8,7 @@
 #   PIPER_B200_LN2=1     LayerNorm with batched global loads (encoder.cu layernorm_kernel2)
 #   PIPER_B200_POST2=1   conv_post with batched staging loads (vocoder_tail.cu conv_post_kernel2)
 #   PIPER_B200_ATT2=1    attention with one 16-byte query broadcast per 4 FMAs (encoder.cu rel_attention_kernel2)
+#   PIPER_B200_ATT3=1    attention on the tensor cores (att_mma.cu: fp16x3, two passes over 64-key blocks)
 #   PIPER_B200_V2=1      second-generation conv kernel: uniform TMA issue + stacked [W_hi;W_lo] weights (conv_mma2.cu)
 #   PIPER_B200_V2_PREC=f16  ... with FP16 hi/lo operands for every family (22 bits at K = 16: half the MMAs of tf32x3)
 set -u
@@ -34,10 +35,11 @@ run uni PIPER_B200_UNI=1
 run uni_small PIPER_B200_UNI=1 PIPER_B200_SMALL=1
 run uni_fused PIPER_B200_UNI=1 PIPER_B200_MMA=31
 run ln2_post2_att2 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT2=1
+run att3 PIPER_B200_ATT3=1
 run v2 PIPER_B200_V2=1
 run v2_f16 PIPER_B200_V2=1 PIPER_B200_V2_PREC=f16
 run v2_fused PIPER_B200_V2=1 PIPER_B200_MMA=31
-run everything PIPER_B200_V2=2 PIPER_B200_V2_PREC=f16 PIPER_B200_MMA=31 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT2=1   # v2 also for launches with < 148 tiles (batch-1 latency)
+run everything PIPER_B200_V2=2 PIPER_B200_V2_PREC=f16 PIPER_B200_MMA=31 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT3=1   # v2 also for launches with < 148 tiles (batch-1 latency)
 PIPER_B200_UNI=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_uni.txt 2>&1
 tail -9 gpurun_out/ab_layer_report_uni.txt
 PIPER_B200_V2=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_v2.txt 2>&1
