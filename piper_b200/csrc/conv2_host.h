@@ -24,7 +24,8 @@ inline int pow2_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 12
 // Output-row tile N (<= 128 so that the stacked instruction has N' = 2N <= 256), K-chains (2 for tf32x3, DESIGN.md
 // section 3), tile height, TMEM double-buffering and the largest channel chunk that fits 196 KB of shared memory.
 // prec: 0 bf16x3, 1 tf32x3, 2 fp16x3.  chains: K-chains per accumulator pair (2 where fp32-grade accuracy is needed).
-inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p) {
+// opts bit 0: allow 256-row tiles for multi-chain fp16 / bf16 layers (one TMEM set, but every weight unit serves twice the rows)
+inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p, int opts = 0) {
   const bool tf32 = prec == 1;
   p = Plan{};
   p.tf32 = tf32;
@@ -40,13 +41,15 @@ inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p
     const int n_tile = rows / nt;
     if (chains > 1 && n_tile > 64 && !(ci * k >= 900 && rows >= 256)) continue;   // as conv_mma.cu: wide tiles only for long reductions
     for (int mt : {256, 128}) {
-      if ((chains > 1 || tf32) && mt != 128) continue;     // 256-row tiles: single-chain bf16 / fp16 layers only (kernel instantiations)
+      if (tf32 && mt != 128) continue;                     // no 256-row tf32 kernel instantiation
+      if (chains > 1 && mt != 128 && !(opts & 1)) continue;
       const int set_cols = mt / 128 * p.chains * 2 * n_tile;
       if (set_cols > 512) continue;
       const int slots = 2 * set_cols <= 512 ? 2 : 1;
       // accumulator halves start at multiples of n_tile columns: keep them 32-column aligned when the layer allows it
       // (every accumulator the shipped kernel has exercised on hardware is)
-      const int score = (n_tile % 32 == 0 ? 1000000 : 0) + slots * 100000 + n_tile * 100 + mt / 128;
+      int score = (n_tile % 32 == 0 ? 1000000 : 0) + slots * 100000 + n_tile * 5000 + mt / 128;
+      if ((opts & 1) && chains > 1 && mt == 256) score += 500000;    // the option asks for the tall tile where it fits
       if (score > best_score) {
         best_score = score;
         p.n_tile = n_tile; p.n_tiles = nt; p.mt = mt; p.t_slots = slots;

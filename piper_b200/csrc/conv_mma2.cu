@@ -32,8 +32,13 @@ __global__ void __launch_bounds__(conv2::C2_THREADS, 1) conv2_kernel(const __gri
 }  // namespace
 
 bool conv2_plan(int ci, int rows, int k, int dil, int prec, int chains, Conv2Layer& l) {
+  static int g_opts = -1;                               // PIPER_B200_V2_OPTS: plan options (conv2_host.h)
+  if (g_opts < 0) {
+    const char* e = std::getenv("PIPER_B200_V2_OPTS");
+    g_opts = e ? std::atoi(e) : 0;
+  }
   conv2::Plan p;
-  if (!conv2::plan(ci, rows, k, dil, prec, chains, p)) return false;
+  if (!conv2::plan(ci, rows, k, dil, prec, chains, p, g_opts)) return false;
   l.tf32 = p.tf32; l.prec = p.prec; l.n_tile = p.n_tile; l.n_tiles = p.n_tiles; l.mt = p.mt; l.kc = p.kc; l.stage_rows = p.stage_rows;
   l.raw_stride = p.raw_stride; l.t_slots = p.t_slots; l.tmem_cols = p.tmem_cols; l.chains = p.chains; l.mh_stride = p.mh_stride;
   l.smem = p.smem; l.w_bytes = p.w_bytes;

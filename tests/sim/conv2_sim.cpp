@@ -25,7 +25,7 @@ extern "C" void conv2_sim_plan(int ci, int rows, int k, int dil, int prec, int c
 
 // One convolution layer on a ragged batch.  x [B][ci][cs_x], w [rows][ci][k] fp32 (rows = output rows: C_out, or
 // C_out * up for a lowered ConvTranspose), y / y2 / r as the epilogue needs.  desc = {ci, rows, k, dil, pad, q_extra, pre,
-// epi, split, first, up, up_pad, mrf, mrf_n, prec (0 bf16x3 / 1 tf32x3 / 2 fp16x3), len_scale, cs_x, cs_y, cs_y2, cs_r, C_y, C_y2, C_r, grid, chains (0 = default)}.
+// epi, split, first, up, up_pad, mrf, mrf_n, prec (0 bf16x3 / 1 tf32x3 / 2 fp16x3), len_scale, cs_x, cs_y, cs_y2, cs_r, C_y, C_y2, C_r, grid, chains (0 = default), plan opts}.
 // info (out) = {n_tile, n_tiles, mt, kc, t_slots, chains, total_tiles, smem bytes}.
 extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, const float* bias_item, int bias_item_stride,
                              float* y, float* y2, const float* r, const int* len, int B, const int* desc, float slope, int max_len,
@@ -35,7 +35,7 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
     const int prec = desc[14], chains = desc[24] > 0 ? desc[24] : (prec == 1 ? 2 : 1);
     const bool tf32 = prec == 1;
     conv2::Plan p;
-    if (!conv2::plan(ci, rows, k, dil, prec, chains, p)) throw std::runtime_error("shape outside the kernel's plan");
+    if (!conv2::plan(ci, rows, k, dil, prec, chains, p, desc[25])) throw std::runtime_error("shape outside the kernel's plan");
     // engine layout of the weights: [ci][k][rows_p], row fastest
     const int rows_p = rows;
     std::vector<float> wsrc(size_t(ci) * k * rows_p);

@@ -28,7 +28,7 @@ def _fp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
 
 
-def _run(sim, x, w, bias, lens, *, dil=1, pad=None, pre=0, slope=0.1, epi="BIAS", tf32=False, prec=None, chains=0, r=None, y2_init=None, split=0,
+def _run(sim, x, w, bias, lens, *, dil=1, pad=None, pre=0, slope=0.1, epi="BIAS", tf32=False, prec=None, chains=0, opts=0, r=None, y2_init=None, split=0,
          first=0, up=1, up_pad=0, mrf=0, mrf_n=3, q_extra=0, bias_item=None, grid=0, y_channels=None):
     B, ci, cs_x = x.shape
     rows, _, k = w.shape
@@ -41,9 +41,9 @@ def _run(sim, x, w, bias, lens, *, dil=1, pad=None, pre=0, slope=0.1, epi="BIAS"
     y2 = y2_init.copy() if y2_init is not None else np.full((B, max(rows - split, 1), cs_x), 7e7, np.float32)
     if prec is None:
         prec = 1 if tf32 else 0
-    desc = (C.c_int32 * 25)(ci, rows, k, dil, pad, q_extra, pre, EPI[epi], split, first, up, up_pad, mrf, mrf_n, prec, 1,
+    desc = (C.c_int32 * 26)(ci, rows, k, dil, pad, q_extra, pre, EPI[epi], split, first, up, up_pad, mrf, mrf_n, prec, 1,
                            cs_x, cs_y, y2.shape[2], 0 if r is None else r.shape[2], C_y, y2.shape[1],
-                           0 if r is None else r.shape[1], grid, chains)
+                           0 if r is None else r.shape[1], grid, chains, opts)
     info = (C.c_int32 * 8)()
     err = C.create_string_buffer(512)
     rc = sim.conv2_sim_run(_fp(x), _fp(np.ascontiguousarray(w)), _fp(bias), _fp(bias_item), 0 if bias_item is None else bias_item.shape[1],
@@ -284,3 +284,18 @@ def test_seeded_random_shapes(sim):
             assert e <= (3e-4 if prec == 0 else 2e-5), (prec, ci, rows, k, dil, lens, epi, chains, grid, e, info)
             assert np.all(y[b, :, L:] == 7e7)
         done += 1
+
+
+def test_tall_tiles_for_two_chain_layers(sim):
+    """Plan option 1: 256-row tiles for a two-chain fp16 layer (flow in_layer shape): one TMEM set of 512 columns."""
+    ci, rows, k, lens = 192, 384, 5, (300, 70)
+    x, clean = _ragged(len(lens), ci, lens, seed=1)
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+    bias = rng.standard_normal(rows).astype(np.float32) * 0.1
+    y, _, info = _run(sim, x, w, bias, lens, epi="GATE", prec=2, chains=2, opts=1, grid=1, y_channels=rows // 2)
+    assert info[2] == 256 and info[4] == 1 and info[5] == 2, info          # mt, TMEM sets, chains
+    for b, L in enumerate(lens):
+        pre = _ref_conv(clean[b], w, bias, 1, 2, 0, 0.1)
+        ref = torch.tanh(pre[0::2]) * torch.sigmoid(pre[1::2])
+        assert float((torch.from_numpy(y[b, :, :L]) - ref).abs().max()) <= 2e-5, info
