@@ -12,7 +12,14 @@ the CPU, no GPU needed.  For every dense convolution it derives, from the same t
 and prints them next to the measured per-family conv time of the final round-1 bench line.  The gap between
 max(t_hbm, t_mma, t_w) and the measurement is what per-tile latency, the epilogue and the converters cost today.
 
-usage: python tools/perf_model.py [--stack]     (--stack: model the [W_hi;W_lo] N-stacked two-instruction scheme)
+  * t_tma   - issue time of the activation-row bulk copies by the single TMA thread: rows per tile x ~150 cycles in the
+              shipped kernel (address arithmetic in vector registers + R2UR + ELECT loop), ~20 cycles
+              with uniform issue (experimental kernels)
+
+usage: python tools/perf_model.py [--stack] [--v2 [--f16]]
+  --stack  model the [W_hi;W_lo] N-stacked two-instruction scheme on the shipped tiling
+  --v2     project the experimental second-generation kernel (conv_mma2.cu): its own plan (tests/sim/libconv2_sim.so),
+           stacked weights, uniform TMA issue; --f16: fp16x3 operands for every family (K = 16 per instruction)
 """
 import json, math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,6 +28,9 @@ CLK = 1.965e9
 SMS = 148
 L2_B_PER_CLK_SM = 6300.0 / SMS
 STACK = "--stack" in sys.argv
+V2 = "--v2" in sys.argv
+F16 = "--f16" in sys.argv
+TMA_CYC = 20.0 if V2 else 150.0
 
 B, T, TP = 32, 259, 509          # utterances, ids, frames per utterance (bench: 4 071 680 samples / 256 / 32 = 497..520)
 
@@ -49,24 +59,48 @@ def plan(ci, rows, k, dil, tf32):
     return n_tile, nt, 128
 
 
+_sim = None
+
+
+def plan_v2(ci, rows, k, dil, prec, chains):
+    """(n_tile, n_tiles, mt, kc) from the experimental kernel's own planner."""
+    global _sim
+    import ctypes as C
+    if _sim is None:
+        _sim = C.CDLL(os.path.join(ROOT, "tests", "sim", "libconv2_sim.so"))
+        _sim.conv2_sim_plan.argtypes = [C.c_int] * 6 + [C.POINTER(C.c_longlong)]
+    info = (C.c_longlong * 13)()
+    _sim.conv2_sim_plan(ci, rows, k, dil, prec, chains, info)
+    assert info[0], (ci, rows, k, dil, prec, chains)
+    return int(info[1]), int(info[2]), int(info[3]), int(info[4])
+
+
 def layer(name, fam, ci, rows, k, dil, L, tf32, extra_rw=0.0, up=1):
     """L: output positions per utterance *before* the pixel shuffle (ConvT computes L_in positions x rows = co*stride)."""
-    n_tile, n_tiles, mt = plan(ci, rows, k, dil, tf32)
-    kstep = 8 if tf32 else 16
+    if V2:
+        prec = 2 if F16 else (1 if tf32 else 0)
+        n_tile, n_tiles, mt, kc = plan_v2(ci, rows, k, dil, prec, 2 if tf32 else 1)
+        es = 4 if prec == 1 else 2
+    else:
+        n_tile, n_tiles, mt = plan(ci, rows, k, dil, tf32)
+        es = 4 if tf32 else 2
+    kstep = 32 // es // 2 * 2 if False else (8 if es == 4 else 16)
     tiles = math.ceil(L / mt) * B * n_tiles
     per_cta = math.ceil(tiles / SMS)
-    if STACK:   # A_hi x [W_hi;W_lo] (N doubled) + A_lo x W_hi
+    if STACK or V2:   # A_hi x [W_hi;W_lo] (N doubled) + A_lo x W_hi
         per_k = mma_cost(2 * n_tile) + mma_cost(n_tile)
     else:
         per_k = 3 * mma_cost(n_tile)
     mma_tile = (mt // 128) * (ci // kstep) * k * per_k
-    w_tile = 2 * ci * k * n_tile * (4 if tf32 else 2)
+    w_tile = 2 * ci * k * n_tile * es
     t_mma = per_cta * mma_tile / CLK
     t_w = per_cta * w_tile / L2_B_PER_CLK_SM / CLK
+    t_tma = per_cta * ci * TMA_CYC / CLK                 # one bulk copy per input-channel row and tile
     bytes_alg = 4.0 * B * (L * ci + L * rows) * (1 + extra_rw) + 4.0 * ci * k * rows
     flop = 2.0 * B * L * ci * rows * k
     return dict(name=name, fam=fam, n_tile=n_tile, n_tiles=n_tiles, mt=mt, tiles=tiles, per_cta=per_cta,
-                waste=per_cta * SMS / tiles * (math.ceil(L / mt) * mt / L), t_hbm=bytes_alg / HBM, t_mma=t_mma, t_w=t_w, flop=flop, bytes=bytes_alg)
+                waste=per_cta * SMS / tiles * (math.ceil(L / mt) * mt / L), t_hbm=bytes_alg / HBM, t_mma=t_mma, t_w=t_w, t_tma=t_tma,
+                flop=flop, bytes=bytes_alg)
 
 
 def medium():
@@ -100,15 +134,21 @@ if __name__ == "__main__":
     if os.path.exists(p):
         meas = {k: v["ms_per_step"] for k, v in json.load(open(p))["roofline"]["stages"].items()}
     rows = medium()
-    print(f"{'layer':14s} {'N':>4s} {'nt':>2s} {'mt':>3s} {'tiles':>6s} {'/CTA':>4s} {'waste':>5s} | {'t_hbm':>7s} {'t_mma':>7s} {'t_w':>7s} us")
+    print(f"{'layer':14s} {'N':>4s} {'nt':>2s} {'mt':>3s} {'tiles':>6s} {'/CTA':>4s} {'waste':>5s} | {'t_hbm':>7s} {'t_mma':>7s} {'t_w':>7s} {'t_tma':>7s} us")
     fam = {}
     for r in rows:
         print(f"{r['name']:14s} {r['n_tile']:4d} {r['n_tiles']:2d} {r['mt']:3d} {r['tiles']:6d} {r['per_cta']:4d} {r['waste']:5.2f} | "
-              f"{r['t_hbm'] * 1e6:7.1f} {r['t_mma'] * 1e6:7.1f} {r['t_w'] * 1e6:7.1f}")
-        f = fam.setdefault(r["fam"], dict(hbm=0.0, mma=0.0, w=0.0, bound=0.0, n=0))
-        f["hbm"] += r["t_hbm"]; f["mma"] += r["t_mma"]; f["w"] += r["t_w"]; f["n"] += 1
+              f"{r['t_hbm'] * 1e6:7.1f} {r['t_mma'] * 1e6:7.1f} {r['t_w'] * 1e6:7.1f} {r['t_tma'] * 1e6:7.1f}")
+        f = fam.setdefault(r["fam"], dict(hbm=0.0, mma=0.0, w=0.0, bound=0.0, tma=0.0, all=0.0, n=0))
+        f["hbm"] += r["t_hbm"]; f["mma"] += r["t_mma"]; f["w"] += r["t_w"]; f["tma"] += r["t_tma"]; f["n"] += 1
         f["bound"] += max(r["t_hbm"], r["t_mma"], r["t_w"])
-    print(f"\nscheme: {'N-stacked [W_hi;W_lo] + A_lo x W_hi (2 instructions per k-step)' if STACK else 'three instructions per k-step (shipped)'}")
-    print(f"{'family':12s} {'launches':>8s} {'sum t_hbm':>10s} {'sum t_mma':>10s} {'sum t_w':>9s} {'sum max()':>10s} {'measured':>9s}  ms per step")
+        f["all"] += max(r["t_hbm"], r["t_mma"], r["t_w"], r["t_tma"])
+    what = ("second-generation kernel, " + ("fp16x3 everywhere" if F16 else "bf16x3 / tf32x3") + ", stacked weights, uniform TMA issue (PROJECTION)") if V2 \
+        else ("N-stacked [W_hi;W_lo] + A_lo x W_hi (2 instructions per k-step)" if STACK else "three instructions per k-step (shipped)")
+    print(f"\nscheme: {what}")
+    print(f"{'family':12s} {'launches':>8s} {'sum t_hbm':>10s} {'sum t_mma':>10s} {'sum t_w':>9s} {'sum t_tma':>10s} {'max w/o tma':>12s} {'max with tma':>13s} {'measured':>9s}  ms per step")
     for k, f in fam.items():
-        print(f"{k:12s} {f['n']:8d} {f['hbm'] * 1e3:10.3f} {f['mma'] * 1e3:10.3f} {f['w'] * 1e3:9.3f} {f['bound'] * 1e3:10.3f} {meas.get(k, float('nan')):9.3f}")
+        print(f"{k:12s} {f['n']:8d} {f['hbm'] * 1e3:10.3f} {f['mma'] * 1e3:10.3f} {f['w'] * 1e3:9.3f} {f['tma'] * 1e3:10.3f} {f['bound'] * 1e3:12.3f} "
+              f"{f['all'] * 1e3:13.3f} {meas.get(k, float('nan')):9.3f}")
+    if V2:
+        print("(measured = the shipped kernel, for reference; the projection has not been measured)")
