@@ -31,6 +31,11 @@ v.set_profile(False)
 n_l = len(runs[0])
 assert all(len(r) == n_l for r in runs)
 pm.B = a.batch
+# model the kernel that is actually running (opt-in variants are selected by environment variables)
+if os.environ.get("PIPER_B200_V2"):
+    pm.V2, pm.F16, pm.TMA_CYC = True, os.environ.get("PIPER_B200_V2_PREC") == "f16", 20.0
+elif os.environ.get("PIPER_B200_UNI"):
+    pm.TMA_CYC = 20.0
 rows = []
 for i in range(n_l):
     r = dict(runs[0][i])
@@ -40,20 +45,20 @@ for i in range(n_l):
         L = r["len_sum"] / a.batch
         m = pm.layer(r["tag"], r["tag"], r["ci"], r["rows"], r["k"], r["dil"], L, tf32)
         # tiles follow the longest item; bytes follow the recorded algorithmic figure
-        n_tile, n_tiles, mt = pm.plan(r["ci"], r["rows"], r["k"], r["dil"], tf32)
+        n_tile, n_tiles, mt = m["n_tile"], m["n_tiles"], m["mt"]
         tiles = math.ceil(r["max_len"] / mt) * a.batch * n_tiles
         scale = math.ceil(tiles / pm.SMS) / max(1, m["per_cta"])
         r.update(n_tile=n_tile, n_tiles=n_tiles, mt=mt, tiles=tiles, t_hbm=r["bytes"] / pm.HBM * 1e6,
-                 t_mma=m["t_mma"] * scale * 1e6, t_w=m["t_w"] * scale * 1e6)
-        r["bound"] = max(r["t_hbm"], r["t_mma"], r["t_w"])
+                 t_mma=m["t_mma"] * scale * 1e6, t_w=m["t_w"] * scale * 1e6, t_tma=m["t_tma"] * scale * 1e6)
+        r["bound"] = max(r["t_hbm"], r["t_mma"], r["t_w"], r["t_tma"])
     rows.append(r)
 print(f"{a.arch}, {a.batch} utterances: {n} samples in {ms:.3f} ms (profiled step), {n_l} conv launches")
-print(f"{'#':>3s} {'tag':8s} {'ci':>4s} {'rows':>5s} {'k':>2s} {'d':>2s} {'N':>4s} {'mt':>3s} {'tiles':>6s} | {'us':>7s} | {'t_hbm':>6s} {'t_mma':>6s} {'t_w':>6s} | {'us/bound':>8s}")
+print(f"{'#':>3s} {'tag':8s} {'ci':>4s} {'rows':>5s} {'k':>2s} {'d':>2s} {'N':>4s} {'mt':>3s} {'tiles':>6s} | {'us':>7s} | {'t_hbm':>6s} {'t_mma':>6s} {'t_w':>6s} {'t_tma':>6s} | {'us/bound':>8s}")
 fam = {}
 for i, r in enumerate(rows):
     if r["mma"] and "bound" in r:
         print(f"{i:3d} {r['tag']:8s} {r['ci']:4d} {r['rows']:5d} {r['k']:2d} {r['dil']:2d} {r['n_tile']:4d} {r['mt']:3d} {r['tiles']:6d} | {r['us']:7.1f} | "
-              f"{r['t_hbm']:6.1f} {r['t_mma']:6.1f} {r['t_w']:6.1f} | {r['us'] / r['bound']:8.2f}")
+              f"{r['t_hbm']:6.1f} {r['t_mma']:6.1f} {r['t_w']:6.1f} {r['t_tma']:6.1f} | {r['us'] / r['bound']:8.2f}")
         f = fam.setdefault(r["tag"], [0.0, 0.0, 0])
         f[0] += r["us"]; f[1] += r["bound"]; f[2] += 1
     else:
