@@ -43,7 +43,8 @@ def _reference(q, k, v, rel_k, rel_v, window=4):
 
 @pytest.mark.parametrize("H,n_heads,lens", [(192, 2, (259, 17)),       # medium: dk = 96, five key blocks, ragged
                                              (96, 2, (130,)),           # x-low: dk = 48
-                                             (32, 2, (64, 1, 65))])     # dk = 16; exactly one block, one key, one past a block
+                                             (32, 2, (64, 1, 65)),      # dk = 16; exactly one block, one key, one past a block
+                                             (64, 4, (600,))])          # four heads, five query tiles, ten key blocks
 def test_tensor_core_attention_on_cpu_model(sim, H, n_heads, lens):
     B, dk = len(lens), H // n_heads
     Tmax = max(lens)
