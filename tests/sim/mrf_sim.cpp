@@ -7,7 +7,7 @@
 //                      and the instruction descriptor (N); queued and executed LATER, in order, by a "tensor core" thread
 //                      with random pauses; tcgen05.commit arrives when everything queued before it has run
 //   * cp.async.bulk  = queued to a "TMA" thread: memcpy + complete_tx some time later (alignment rules asserted)
-//   * mbarrier       = blocking phase barrier with arrival and transaction counts; a wait that lasts 20 s aborts the run
+//   * mbarrier       = blocking phase barrier with arrival and transaction counts; a wait that lasts 60 s aborts the run
 //
 // What it can show: index arithmetic, operand layouts, TMEM column maps and the barrier protocol - liveness (phases,
 // counts, deadlocks) and sufficiency (a result read before its barrier is stale, an operand overwritten before the engine

@@ -37,7 +37,7 @@ struct CtaBarrier {   // __syncthreads for n threads, reusable
     const unsigned g = gen;
     if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); return; }
     while (gen == g) {
-      if (cv.wait_for(l, std::chrono::seconds(20)) == std::cv_status::timeout || abort.load())
+      if (cv.wait_for(l, std::chrono::seconds(60)) == std::cv_status::timeout || abort.load())
         if (gen == g) { abort = true; throw SimAbort("__syncthreads never completed"); }
     }
   }
@@ -197,14 +197,14 @@ struct SimPrim {
     // flipped twice and wait forever - so in the model only the elected lane of a control warp blocks.
     if ((c.tid_ >> 5) < c.cta->control_warps && (c.tid_ & 31) != 0) return;
     std::unique_lock<std::mutex> l(m->m);
-    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(20);
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(60);
     while (m->phase == parity) {                          // the phase with this parity has not completed yet
       if (c.cta->abort.load()) throw SimAbort("aborted");
       if (m->cv.wait_until(l, std::chrono::steady_clock::now() + std::chrono::milliseconds(200)) == std::cv_status::timeout &&
           std::chrono::steady_clock::now() > deadline) {
         l.unlock();
         c.cta->fail("deadlock: thread " + std::to_string(c.tid_) + " (warp " + std::to_string(c.tid_ >> 5) +
-                    ") waited 20 s on an mbarrier, parity " + std::to_string(parity));
+                    ") waited 60 s on an mbarrier, parity " + std::to_string(parity));
         throw SimAbort("deadlock");
       }
     }
