@@ -139,7 +139,8 @@ int pb200_synthesize(pb200_voice* v, const int64_t* ids, int64_t n_ids, const fl
                      const pb200_noise* noise, const float** audio, int64_t* n_samples, double* infer_seconds) {
   return guarded([&] {
     if (!v || !ids || !scales || !audio || !n_samples) throw std::runtime_error("pb200_synthesize: null argument");
-    if (sid) v->engine.set_speakers(sid, 1);
+    // NULL = speaker 0 (include/piper_b200.h): never inherit the speaker of an earlier call
+    v->engine.set_speakers(sid, sid ? 1 : 0);
     int64_t lens[1] = {n_ids};
     *audio = v->engine.synthesize(ids, lens, 1, scales, to_spec(noise), nullptr, n_samples, infer_seconds);
   });

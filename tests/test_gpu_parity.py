@@ -46,7 +46,7 @@ def _noise(inter, n_ids, seed, cols=None):
 
 
 @pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                                        if not os.path.basename(p).startswith("stream_")))
+                                        if not os.path.basename(p).startswith(("stream_", "int16_"))))
 def test_engine_matches_reference_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     voice, _ = _pair(str(g["voice"]))
@@ -125,15 +125,19 @@ def test_vocoder_only():
             assert np.abs(out[b] - ref).max() <= TOL
 
 
-def test_int16_epilogue_matches_host_semantics():
-    from piper_b200 import host
+def test_int16_epilogue_matches_reference_loops():
+    """pb200_synthesize_int16 against the oracle of piper.cpp:411-431 (oracle/int16_oracle.py, pinned to the reference's
+    compiled loops and golden) and, when it travelled, against those compiled loops themselves."""
+    from oracle import int16_oracle
     voice, _ = _pair("synthetic:tiny:1234")
-    ids_list = [voicegen.benchmark_ids(10, seed=1), voicegen.benchmark_ids(25, seed=2)]
+    ids_list = [voicegen.benchmark_ids(10, seed=1), voicegen.benchmark_ids(25, seed=2), voicegen.benchmark_ids(1, seed=3)]
     f32, _ = voice.synthesize_batch(ids_list, seed=42)
     i16, _ = voice.synthesize_int16(ids_list, seed=42)
     for a, q in zip(f32, i16):
         assert q.dtype == np.int16 and q.shape == a.shape
-        assert np.array_equal(q, host.audio_float_to_int16(a))       # piper.cpp:411-431, bit for bit
+        assert np.array_equal(q, int16_oracle.float_to_int16_cpp(a))
+        if int16_oracle.ref_lib() is not None:
+            assert np.array_equal(q, int16_oracle.float_to_int16_ref(a))
         assert np.abs(q).max() >= 32766                               # peak-normalised (truncating cast)
 
 
@@ -221,6 +225,34 @@ def test_full_size_properties_medium_batch32():
     assert np.abs(out - outs3[0]).max() <= 2e-4
 
 
+def test_high_ragged_batch8_matches_per_item_oracle():
+    """BASELINE.json configs[3]'s per-GPU share: the "high" preset (ResBlock1, 512-channel generator,
+    piper_train/__main__.py:72-82), 8 ragged utterances of up to 128 phonemes in ONE batch launch, every item against its own
+    B = 1 oracle run, stage taps of the longest item included."""
+    voice, orc = _pair("synthetic:high:1234")
+    n_ph = [128, 96, 128, 57, 120, 33, 128, 101]
+    ids_list = [voicegen.benchmark_ids(n, seed=40 + i) for i, n in enumerate(n_ph)]
+    rng = np.random.default_rng(31)
+    eps_dp = [rng.standard_normal((2, len(i))).astype(np.float32) for i in ids_list]
+    eps_z = rng.standard_normal((len(ids_list), orc.s.inter, 6 * 259)).astype(np.float32)
+    scales = (0.667, 1.0, 0.8)
+    voice.set_debug(True)
+    outs, _ = voice.synthesize_batch(ids_list, scales, eps_dp, eps_z)
+    keys = ["z"] + [f"stage{i}" for i in range(len(orc.s.up_rates))]
+    taps = {(k, b): voice.tap(k, b) for k in keys for b in (0, 3)}
+    voice.set_debug(False)
+    for b, ids in enumerate(ids_list):
+        dump = {}
+        ref = orc.infer(ids, scales, eps_dp[b], eps_z[b], dump=dump)
+        assert outs[b].shape == ref.shape, (b, outs[b].shape, ref.shape)
+        assert np.abs(outs[b] - ref).max() <= TOL, (b, float(np.abs(outs[b] - ref).max()))
+        assert float(np.sqrt((ref ** 2).mean())) > 0.05
+        if b in (0, 3):
+            for k in keys:
+                r = dump[k].numpy()
+                assert taps[(k, b)].shape == r.shape and np.abs(taps[(k, b)] - r).max() <= 2e-3, (b, k)
+
+
 def test_streaming_encode_decode_split():
     """pb200_encode / pb200_decode + the host chunker against the reference-minted streaming fixture and the oracle."""
     from piper_b200 import streaming
@@ -293,6 +325,11 @@ def test_multi_speaker_conditioning(tag, n_ph):
         ref = orc.infer(ids, scales, eps_dp3[bi], eps_z3[bi], sid=sid)
         assert batch[bi].shape == ref.shape and np.abs(batch[bi] - ref).max() <= TOL, (bi, sid)
     voice.set_speakers([])
+    # sid = None means speaker 0 (include/piper_b200.h), whatever an earlier call used
+    last = orc.s.n_speakers - 1
+    voice.synthesize(ids, scales, eps_dp, eps_z, sid=last)
+    again, _ = voice.synthesize(ids, scales, eps_dp, eps_z, sid=None)
+    assert again.shape == outs[0].shape and np.array_equal(again, outs[0])
     from piper_b200._lib import PiperB200Error
     with pytest.raises(PiperB200Error, match="speaker id"):
         voice.synthesize(ids, sid=orc.s.n_speakers)

@@ -26,7 +26,7 @@ def _oracle_for(tag):
 
 
 @pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                                        if not os.path.basename(p).startswith("stream_")))
+                                        if not os.path.basename(p).startswith(("stream_", "int16_"))))
 def test_oracle_matches_golden(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     orc, w = _oracle_for(str(g["voice"]))
@@ -146,3 +146,52 @@ def test_streaming_matches_reference_chunk_loop():
     mine = list(streaming.SpeechStreamer(_V(), 45, 10, True).chunk(z_p, decode=orc.decode))
     assert [len(a) for a in mine] == [len(a) for a in ref]
     assert max(np.abs(a - b).max() for a, b in zip(mine, ref)) <= 1e-4
+
+
+# ---- int16 peak normalisation (piper.cpp:411-431 / python_run/piper/util.py:5-12): the oracle pinned three ways
+
+def _int16_golden():
+    g = np.load(os.path.join(GOLDEN, "int16_cpp.npz"))
+    return {k[:-3]: (g[k], g[k[:-3] + ".cpp"], g[k[:-3] + ".py"]) for k in g.files if k.endswith(".in")}
+
+
+def test_int16_oracle_matches_reference_minted_golden():
+    """tests/golden/int16_cpp.npz holds the outputs of the reference's own loops (compiled from piper.cpp:411-431)."""
+    from oracle import int16_oracle
+    from piper_b200 import host
+    cases = _int16_golden()
+    assert len(cases) >= 10
+    for name, (a, cpp, py) in cases.items():
+        assert np.array_equal(int16_oracle.float_to_int16_cpp(a), cpp), name
+        assert np.array_equal(int16_oracle.float_to_int16_python(a), py), name
+        assert np.array_equal(host.audio_float_to_int16(a), cpp), name            # the shim's Python mirror
+        assert np.array_equal(host.audio_float_to_int16(a, "python"), py), name
+
+
+def test_int16_oracle_matches_compiled_reference_loops():
+    """oracle/_ref/libint16_ref.so = the reference's lines themselves (oracle/build_ref.py); travels to the GPU box."""
+    from oracle import int16_oracle
+    if int16_oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref/libint16_ref.so not built (python -m oracle.build_ref needs /root/reference)")
+    rng = np.random.default_rng(11)
+    for n, amp in ((1, 1.0), (7, 0.004), (1000, 0.5), (65536, 1.0), (4099, 3.0)):
+        a = (amp * np.tanh(rng.standard_normal(n))).astype(np.float32) if amp <= 1 else (amp * rng.standard_normal(n)).astype(np.float32)
+        assert np.array_equal(int16_oracle.float_to_int16_cpp(a), int16_oracle.float_to_int16_ref(a)), (n, amp)
+    for name, (a, cpp, _) in _int16_golden().items():
+        assert np.array_equal(int16_oracle.float_to_int16_ref(a), cpp), name
+
+
+@pytest.mark.needs_reference
+def test_int16_oracle_matches_reference_python_util():
+    import importlib.util
+    util_py = "/root/reference/src/python_run/piper/util.py"
+    if not os.path.exists(util_py):
+        pytest.skip("/root/reference not present (GPU box)")
+    from oracle import int16_oracle
+    spec = importlib.util.spec_from_file_location("ref_piper_util", util_py)
+    util = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(util)
+    rng = np.random.default_rng(12)
+    for n, amp in ((3, 1.0), (500, 0.003), (30000, 0.7)):
+        a = (amp * np.tanh(rng.standard_normal(n))).astype(np.float32)
+        assert np.array_equal(int16_oracle.float_to_int16_python(a), util.audio_float_to_int16(a))

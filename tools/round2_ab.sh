@@ -32,18 +32,13 @@ PY
 }
 run base PIPER_B200_NOP=1
 run uni PIPER_B200_UNI=1
-run uni_small PIPER_B200_UNI=1 PIPER_B200_SMALL=1
 run uni_fused PIPER_B200_UNI=1 PIPER_B200_MMA=31
 run ln2_post2_att2 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT2=1
 run att3 PIPER_B200_ATT3=1
 run v2 PIPER_B200_V2=1
 run v2_f16 PIPER_B200_V2=1 PIPER_B200_V2_PREC=f16
-run v2_f16_tall PIPER_B200_V2=1 PIPER_B200_V2_PREC=f16 PIPER_B200_V2_OPTS=1   # 256-row tiles for the two-chain layers
-run v2_fused PIPER_B200_V2=1 PIPER_B200_MMA=31
 run everything PIPER_B200_V2=2 PIPER_B200_V2_PREC=f16 PIPER_B200_MMA=31 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT3=1   # v2 also for launches with < 148 tiles (batch-1 latency)
 PIPER_B200_UNI=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_uni.txt 2>&1
 tail -9 gpurun_out/ab_layer_report_uni.txt
-PIPER_B200_V2=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_v2.txt 2>&1
-tail -9 gpurun_out/ab_layer_report_v2.txt
 PIPER_B200_V2=1 PIPER_B200_V2_PREC=f16 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_v2_f16.txt 2>&1
 tail -9 gpurun_out/ab_layer_report_v2_f16.txt
