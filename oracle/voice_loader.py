@@ -134,6 +134,8 @@ def infer_spec(w: Dict[str, np.ndarray], attrs: Dict[str, ConvAttr]) -> VoiceSpe
     s.inter = int(w["enc_p.proj.weight"].shape[0]) // 2
     s.dds_layers = len(_indices(w, r"dp\.convs\.convs_sep\.(\d+)\.weight"))
     cf = _indices(w, r"dp\.flows\.(\d+)\.pre\.weight")
+    if len(cf) > 1 and min(cf) == 1:      # self.flows[1] is dropped by the reverse pass (models.py:110) even if a file keeps it
+        cf = [i for i in cf if i != 1]
     s.dp_flows = sorted(cf, reverse=True)
     s.spline_bins = (int(w[f"dp.flows.{cf[0]}.proj.weight"].shape[0]) + 1) // 3
     fl = _indices(w, r"flow\.flows\.(\d+)\.pre\.weight")

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) durations_kernel(View z, float ea_m, floa
       if (!(c >= 0.f)) c = 0.f;
       if (c > 1048576.f) c = 1048576.f;
       wc = (int)c;
-      if (w_override) wc = w_override[(long long)b * w_override_pitch + t];
+      if (w_override) wc = min(max(w_override[(long long)b * w_override_pitch + t], 0), 1048576);
     }
     int v = wc;
     for (int o = 1; o < 32; o <<= 1) {
@@ -180,11 +180,14 @@ __global__ void __launch_bounds__(256) durations_kernel(View z, float ea_m, floa
     }
     if (lane == 31) warp_tot[warp] = v;
     __syncthreads();
-    int prefix = carry_s;
+    // a block adds at most 256 * 2^20 = 2^28; the running total saturates at 2^30 so it can never wrap: an absurd
+    // length stays monotonic and far above the engine's frame limit, where plan_back() rejects it
+    long long prefix = carry_s;
     for (int w2 = 0; w2 < warp; ++w2) prefix += warp_tot[w2];
-    if (t < T) cum[(long long)b * cum_pitch + t] = prefix + v;
+    const int tot = (int)min(prefix + v, 1LL << 30);
+    if (t < T) cum[(long long)b * cum_pitch + t] = tot;
     __syncthreads();
-    if (threadIdx.x == 255) carry_s = prefix + v;
+    if (threadIdx.x == 255) carry_s = tot;
     __syncthreads();
   }
   if (threadIdx.x == 0) y_len[b] = max(carry_s, 1);   // clamp_min(sum, 1)  (models.py:704)

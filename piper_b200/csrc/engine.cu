@@ -84,6 +84,8 @@ Engine::~Engine() {
   for (auto* p : pbs) p->release();
   for (auto& ev : ev_)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ev_pool_)
+    if (ev) cudaEventDestroy(ev);
   if (stream_) cudaStreamDestroy(stream_);
 }
 

@@ -19,6 +19,10 @@ namespace pb200 {
 struct DeviceBuf {
   void* p = nullptr;
   size_t cap = 0;
+  DeviceBuf() = default;
+  DeviceBuf(const DeviceBuf&) = delete;
+  DeviceBuf& operator=(const DeviceBuf&) = delete;
+  ~DeviceBuf() { release(); }        // an Engine constructor that throws half-way must not leak HBM
   void ensure(size_t bytes);
   void release();
   template <class T> T* as() const { return static_cast<T*>(p); }
@@ -26,6 +30,10 @@ struct DeviceBuf {
 struct PinnedBuf {
   void* p = nullptr;
   size_t cap = 0;
+  PinnedBuf() = default;
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { release(); }
   void ensure(size_t bytes);
   void release();
   template <class T> T* as() const { return static_cast<T*>(p); }

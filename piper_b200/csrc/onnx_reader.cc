@@ -1,6 +1,7 @@
 #include "onnx_reader.h"
 
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <stdexcept>
 
@@ -84,10 +85,27 @@ void parse_tensor(Span s, OnnxTensor& t) {
       default: break;
     }
   }
-  if (t.dtype == 1 && t.raw == nullptr && t.owned.empty() && t.numel() != 0)
+  // A truncated or hostile file must fail here, not as an out-of-bounds read in the packer (the reference gets this
+  // validation from onnxruntime's model loader).
+  int64_t n = 1;
+  for (int64_t d : t.dims) {
+    if (d < 0 || d > (int64_t(1) << 31)) throw std::runtime_error("onnx: tensor '" + t.name + "' has a bad dimension");
+    n *= d;
+    if (n > (int64_t(1) << 36)) throw std::runtime_error("onnx: tensor '" + t.name + "' is implausibly large");
+  }
+  if (t.dtype == 1 && t.raw == nullptr && t.owned.empty() && n != 0)
     throw std::runtime_error("onnx: float tensor '" + t.name + "' has no data");
-  if (t.dtype == 1 && t.raw != nullptr && int64_t(t.raw_bytes) != t.numel() * 4)
+  if (t.dtype == 1 && t.raw != nullptr && int64_t(t.raw_bytes) != n * 4)
     throw std::runtime_error("onnx: tensor '" + t.name + "' raw_data size does not match dims");
+  if (t.dtype == 1 && t.raw == nullptr && int64_t(t.owned.size()) != n)
+    throw std::runtime_error("onnx: tensor '" + t.name + "' float_data size does not match dims");
+  if (t.dtype == 1 && t.raw != nullptr && (reinterpret_cast<uintptr_t>(t.raw) & 3u) != 0) {
+    // raw_data sits at an arbitrary byte offset of the file: give f32() an aligned copy
+    t.owned.resize(size_t(n));
+    std::memcpy(t.owned.data(), t.raw, size_t(n) * 4);
+    t.raw = nullptr;
+    t.raw_bytes = 0;
+  }
 }
 
 void parse_attr(Span s, OnnxNode& n) {

@@ -279,6 +279,10 @@ void load_voice_file(const std::string& onnx_path, PackedVoice& v) {
   {
     auto cf = indices(c, R"(dp\.flows\.(\d+)\.pre\.weight)");
     if (cf.empty()) fail("no ConvFlow in the duration predictor (deterministic DurationPredictor voices are not supported)");
+    // SynthesizerTrn's reverse pass drops self.flows[1], the first ConvFlow after the ElementwiseAffine ("remove a useless
+    // vflow", models.py:110: flows[:-2] + [flows[-1]] of the reversed list).  The stock exporter prunes its weights from
+    // the file; an exporter that keeps initializers must not make us run it.
+    if (cf.size() > 1 && cf.front() == 1) cf.erase(cf.begin());
     s.dp_flows.assign(cf.rbegin(), cf.rend());
     s.spline_bins = (int(P.get("dp.flows." + std::to_string(cf[0]) + ".proj.weight", 3).dims[0]) + 1) / 3;
     auto fl = indices(c, R"(flow\.flows\.(\d+)\.pre\.weight)");

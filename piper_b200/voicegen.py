@@ -46,6 +46,11 @@ ARCHS: Dict[str, dict] = {
     "tiny": dict(hidden=32, inter=32, filter=64, heads=2, layers=2, resblock=2,
                  up_rates=(8, 8, 4), up_kernels=(16, 16, 8), up_initial=64,
                  rb_kernels=(3, 5, 7), rb_dilations=((1, 2), (2, 6), (3, 12)), sample_rate=22050),
+    # an exporter that keeps the initializers of the ConvFlow the reverse pass drops (dp.flows.1, models.py:110)
+    "tiny-keepflow": dict(hidden=32, inter=32, filter=64, heads=2, layers=2, resblock=2,
+                          up_rates=(8, 8, 4), up_kernels=(16, 16, 8), up_initial=64,
+                          rb_kernels=(3, 5, 7), rb_dilations=((1, 2), (2, 6), (3, 12)), sample_rate=22050,
+                          dp_flow_ids=(1, 3, 5, 7)),
     # multi-speaker variants (emb_g + dp.cond + WN cond_layer + dec.cond; gin 512 in piper: lightning.py:81-83)
     "tiny-ms": dict(hidden=32, inter=32, filter=64, heads=2, layers=2, resblock=2,
                     up_rates=(8, 8, 4), up_kernels=(16, 16, 8), up_initial=64,
@@ -157,7 +162,7 @@ def build(arch: str = "medium", seed: int = 1234, n_vocab: int = 256) -> onnx_wi
             b.layer_norm(f"{prefix}.norms_2.{i}", H)
     b.add("dp.flows.0.m", np.array([[-0.3], [0.1]], np.float32))
     logs0 = np.array([[0.35], [-0.1]], np.float32)
-    for f in (3, 5, 7):
+    for f in cfg.get("dp_flow_ids", (3, 5, 7)):
         b.conv(f"dp.flows.{f}.pre", H, 1, 1, gain=1.0)
         dds(f"dp.flows.{f}.convs")
         b.conv(f"dp.flows.{f}.proj", 29, H, 1, std=0.05)

@@ -125,6 +125,35 @@ def test_cpp_loader_errors(lib_built, tmp_path):
         engine.describe(p)
 
 
+def test_loader_drops_the_useless_vflow_even_if_the_file_keeps_it(lib_built):
+    """models.py:110 drops self.flows[1] in the reverse pass; the stock exporter prunes its weights, another exporter may
+    keep them - both loaders must still run ConvFlows 7, 5, 3 only."""
+    from piper_b200 import engine
+    from oracle.voice_loader import load_voice
+    p = voicegen.cached_voice("tiny-keepflow")
+    assert engine.describe(p)["dp_flows"] == [7, 5, 3]
+    assert load_voice(p)[0].dp_flows == [7, 5, 3]
+
+
+def test_cpp_loader_rejects_truncated_and_inconsistent_tensors(lib_built, tmp_path):
+    """A tensor whose payload does not match its dims must be refused at load (heap over-read in the packer)."""
+    from piper_b200 import engine
+    from piper_b200._lib import PiperB200Error
+    good = open(voicegen.cached_voice("tiny"), "rb").read()
+    p = tmp_path / "trunc.onnx"
+    for cut in (len(good) // 3, len(good) - 7):
+        p.write_bytes(good[:cut])
+        with pytest.raises(PiperB200Error):
+            engine.describe(str(p))
+    m = voicegen.build("tiny")
+    name = "dec.conv_pre.weight"
+    m.initializers[name] = m.initializers[name].reshape(-1)[:-3].copy()        # payload shorter than the conv's shape needs
+    q = str(tmp_path / "short.onnx")
+    onnx_wire.save(q, m)
+    with pytest.raises(PiperB200Error):
+        engine.describe(q)
+
+
 def test_cabi_exports_every_declared_symbol(lib_built):
     header = open(os.path.join(ROOT, "include", "piper_b200.h")).read()
     declared = set(re.findall(r"\b(pb200_[a-z0-9_]+)\s*\(", header))
