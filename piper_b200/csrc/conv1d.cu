@@ -27,6 +27,7 @@ namespace pb200 {
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long launch_count() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }   // a replayed CUDA graph
 
 namespace {
 

@@ -51,7 +51,9 @@ __global__ void __launch_bounds__(256) speaker_cond_kernel(const float* __restri
 }
 
 __global__ void dp_noise_kernel(View z, const float* __restrict__ eps, const long long* __restrict__ eps_off,
-                                unsigned long long seed, float noise_w, const int* __restrict__ len) {
+                                const CallParams* __restrict__ cp, const int* __restrict__ len) {
+  const unsigned long long seed = cp->seed;
+  const float noise_w = cp->noise_w;
   const int b = blockIdx.z, ch = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int T = len[b];
@@ -148,12 +150,13 @@ __global__ void spline_inverse_kernel(View z, int x1_ch, View h, int nb, float i
 }
 
 // One CTA per utterance: durations, inclusive scan, output length.
-__global__ void __launch_bounds__(256) durations_kernel(View z, float ea_m, float ea_scale, float length_scale,
+__global__ void __launch_bounds__(256) durations_kernel(View z, float ea_m, float ea_scale, const CallParams* __restrict__ cp,
                                                         const int* __restrict__ w_override, int w_override_pitch,
                                                         int* __restrict__ cum, int cum_pitch, int* __restrict__ y_len,
                                                         float* __restrict__ logw_out, const int* __restrict__ len) {
   __shared__ int warp_tot[8];
   __shared__ int carry_s;
+  const float length_scale = cp->length_scale;
   const int b = blockIdx.x;
   const int T = len[b];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -196,7 +199,9 @@ __global__ void __launch_bounds__(256) durations_kernel(View z, float ea_m, floa
 __global__ void __launch_bounds__(256) expand_kernel(View stats, int inter, const int* __restrict__ cum, int cum_pitch,
                                                      const int* __restrict__ len, const int* __restrict__ y_len, View zp,
                                                      const float* __restrict__ eps, long long eps_bs, int eps_cs,
-                                                     unsigned long long seed, float noise_scale) {
+                                                     const CallParams* __restrict__ cp) {
+  const unsigned long long seed = cp->seed;
+  const float noise_scale = cp->noise_scale;
   const int b = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int F = y_len[b];
@@ -235,11 +240,11 @@ void launch_speaker_cond(const float* w, const float* bias, const float* emb_g, 
   count_launch();
 }
 
-void launch_dp_noise(View z, const float* eps, const long long* eps_off, unsigned long long seed, float noise_w,
+void launch_dp_noise(View z, const float* eps, const long long* eps_off, const CallParams* cp,
                      const int* len, int B, int Tmax, cudaStream_t st) {
   if (B <= 0 || Tmax <= 0) return;
   dim3 grid((Tmax + 127) / 128, 2, B);
-  dp_noise_kernel<<<grid, 128, 0, st>>>(z, eps, eps_off, seed, noise_w, len);
+  dp_noise_kernel<<<grid, 128, 0, st>>>(z, eps, eps_off, cp, len);
   count_launch();
 }
 
@@ -259,23 +264,22 @@ void launch_spline_inverse(View z, int x1_ch, View h, int bins, float inv_sqrt_c
   count_launch();
 }
 
-void launch_durations(View z, float ea_m, float ea_scale, float length_scale, const int* w_override,
+void launch_durations(View z, float ea_m, float ea_scale, const CallParams* cp, const int* w_override,
                       int w_override_pitch, int* cum, int cum_pitch, int* y_len, float* logw_out, const int* len,
                       int B, int Tmax, cudaStream_t st) {
   if (B <= 0) return;
   (void)Tmax;
-  durations_kernel<<<B, 256, 0, st>>>(z, ea_m, ea_scale, length_scale, w_override, w_override_pitch, cum, cum_pitch,
+  durations_kernel<<<B, 256, 0, st>>>(z, ea_m, ea_scale, cp, w_override, w_override_pitch, cum, cum_pitch,
                                       y_len, logw_out, len);
   count_launch();
 }
 
 void launch_expand(View stats, int inter, const int* cum, int cum_pitch, const int* len, const int* y_len, View zp,
-                   const float* eps, long long eps_bs, int eps_cs, unsigned long long seed, float noise_scale, int B,
+                   const float* eps, long long eps_bs, int eps_cs, const CallParams* cp, int B,
                    int Fmax, cudaStream_t st) {
   if (B <= 0 || Fmax <= 0) return;
   dim3 grid((Fmax + 255) / 256, 8, B);
-  expand_kernel<<<grid, 256, 0, st>>>(stats, inter, cum, cum_pitch, len, y_len, zp, eps, eps_bs, eps_cs, seed,
-                                      noise_scale);
+  expand_kernel<<<grid, 256, 0, st>>>(stats, inter, cum, cum_pitch, len, y_len, zp, eps, eps_bs, eps_cs, cp);
   count_launch();
 }
 

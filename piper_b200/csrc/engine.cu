@@ -1,6 +1,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -17,8 +18,14 @@ namespace pb200 {
       throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr); \
   } while (0)
 
+// Bumped whenever any workspace buffer is re-allocated: captured CUDA graphs hold raw pointers and are re-captured
+// when the generation they were built against is stale.
+static std::atomic<unsigned long long> g_ws_generation{1};
+void count_launches(unsigned long long n);
+
 void DeviceBuf::ensure(size_t bytes) {
   if (bytes <= cap) return;
+  g_ws_generation.fetch_add(1);
   release();
   size_t want = bytes + bytes / 4 + 256;   // headroom: data-dependent lengths vary call to call
   CUDA_CHECK(cudaMalloc(&p, want));
@@ -74,13 +81,14 @@ Engine::Engine(const std::string& onnx_path, int device, bool upload) : device_(
 Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
+  drop_graphs();
   DeviceBuf* dbs[] = {&weights_, &weights_mma_, &ids_d_, &len_d_, &ylen_d_, &cum_d_, &logw_d_, &override_d_, &epsdp_d_, &epsoff_d_,
                       &off_d_, &sid_d_, &cond_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
-                      &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_, &mrf_w_};
+                      &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_, &mrf_w_, &params_d_};
   for (auto* d : dbs) d->release();
   for (auto& kv : v2_layers_)
     if (kv.second.w_dev) cudaFree(kv.second.w_dev);
-  PinnedBuf* pbs[] = {&ids_pin_, &misc_pin_, &audio_pin_, &audio16_pin_, &eps_pin_};
+  PinnedBuf* pbs[] = {&ids_pin_, &misc_pin_, &audio_pin_, &audio16_pin_, &eps_pin_, &params_pin_, &override_pin_};
   for (auto* p : pbs) p->release();
   for (auto& ev : ev_)
     if (ev) cudaEventDestroy(ev);
@@ -268,11 +276,18 @@ void Engine::upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B
     Tmax = std::max<int>(Tmax, int(lens[b]));
     total += lens[b];
   }
+  Tmax = bucket_ids(Tmax);                 // shape bucket (identity unless CUDA graphs are on): every kernel masks by len[b]
   B_ = B; Tmax_ = Tmax; Tp_ = round4(Tmax);
   sum_T_ = double(total);
   for (int i = 0; i < 3; ++i) scales_[i] = scales[i];
   seed_ = noise.seed;
   ensure_front(B, Tmax);
+  // per-call scalars go to device memory (kernels.cuh CallParams): a replayed graph must see this call's values
+  params_d_.ensure(sizeof(CallParams));
+  params_pin_.ensure(sizeof(CallParams));
+  CallParams* cp = params_pin_.as<CallParams>();
+  cp->seed = seed_; cp->noise_scale = scales_[0]; cp->length_scale = scales_[1]; cp->noise_w = scales_[2]; cp->pad_ = 0.f;
+  CUDA_CHECK(cudaMemcpyAsync(params_d_.p, cp, sizeof(CallParams), cudaMemcpyHostToDevice, stream_));
   len_h_.assign(B, 0);
   // ids: int64 host -> int32 [B][Tp] (validated: an out-of-range id would index past the embedding table)
   ids_pin_.ensure(size_t(B) * Tp_ * 4);
@@ -316,8 +331,11 @@ void Engine::upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B
   have_override_ = w_ceil_override != nullptr;
   if (have_override_) {
     override_d_.ensure(size_t(total) * 4 + size_t(B) * Tp_ * 4);
-    // ragged host array -> padded [B][Tp]
-    std::vector<int> tmp(size_t(B) * Tp_, 0);
+    // ragged host array -> padded [B][Tp] (pinned: the copy leaves it before the next call, which starts after this
+    // call's final stream synchronisation)
+    override_pin_.ensure(size_t(B) * Tp_ * 4);
+    int* tmp = override_pin_.as<int>();
+    std::memset(tmp, 0, size_t(B) * Tp_ * 4);
     int64_t p2 = 0;
     for (int b = 0; b < B; ++b) {
       for (int t = 0; t < len_h_[b]; ++t) {
@@ -327,11 +345,10 @@ void Engine::upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B
       }
       p2 += len_h_[b];
     }
-    CUDA_CHECK(cudaMemcpyAsync(override_d_.p, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, stream_));
-    CUDA_CHECK(cudaStreamSynchronize(stream_));   // tmp goes out of scope
+    CUDA_CHECK(cudaMemcpyAsync(override_d_.p, tmp, size_t(B) * Tp_ * 4, cudaMemcpyHostToDevice, stream_));
   }
-  // pinned scratch is reused by the next call: make sure the copies have left it
-  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  // No synchronisation here: the pinned staging buffers are next written by the NEXT call, and every public call ends
+  // with a stream synchronisation; within this call the stream orders the copies before the kernels that read them.
 }
 
 void Engine::set_speakers(const int64_t* sids, int n) {
@@ -351,8 +368,8 @@ void Engine::upload_speakers(int B) {
     if (!sids_.empty()) sid[b] = sids_[std::min<size_t>(b, sids_.size() - 1)];
   sid_d_.ensure(size_t(B) * 4);
   cond_d_.ensure(size_t(B) * voice_.cond_rows * 4);
+  // `sid` is pageable memory: cudaMemcpyAsync returns once it has been copied to the driver's staging buffer
   CUDA_CHECK(cudaMemcpyAsync(sid_d_.p, sid.data(), size_t(B) * 4, cudaMemcpyHostToDevice, stream_));
-  CUDA_CHECK(cudaStreamSynchronize(stream_));      // `sid` is a stack vector
   launch_speaker_cond(W(voice_.cond_w), W(voice_.cond_b), W(voice_.emb_g), sid_d_.as<int>(), cond_d_.as<float>(),
                       voice_.cond_rows, s.gin, B, stream_);
 }
@@ -393,17 +410,114 @@ const HostTap* Engine::tap(const std::string& name) const {
   return it == taps_.end() ? nullptr : &it->second;
 }
 
+// ---- CUDA graphs ------------------------------------------------------------------------------------------------
+bool Engine::graphs_on() {
+  if (graph_mode_ < 0) {
+    const char* e = std::getenv("PIPER_B200_GRAPH");
+    graph_mode_ = e ? std::atoi(e) : 0;
+  }
+  return graph_mode_ > 0;
+}
+// Shape buckets: with graphs on, the grid-sizing lengths are rounded up so that one captured graph serves every call
+// of the bucket (kernels read the true per-item lengths from device memory and skip tiles past them).
+int Engine::bucket_ids(int t) const { return const_cast<Engine*>(this)->graphs_on() ? (t + 31) / 32 * 32 : t; }
+int Engine::bucket_frames(int f) const { return const_cast<Engine*>(this)->graphs_on() ? (f + 63) / 64 * 64 : f; }
+
+void Engine::record(int i) {
+  // inside a capture a plain cudaEventRecord only expresses a dependency; the external flag makes it a record node
+  if (capturing_) CUDA_CHECK(cudaEventRecordWithFlags(ev_[i], stream_, cudaEventRecordExternal));
+  else CUDA_CHECK(cudaEventRecord(ev_[i], stream_));
+}
+
+void Engine::drop_graphs() {
+  for (auto& kv : graphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
+}
+
+void Engine::run_graphed(unsigned long long key, const std::function<void()>& enqueue) {
+  // explicit noise / duration overrides are test inputs with their own strides: only the production path is graphed
+  if (!graphs_on() || debug_ || profile_ || have_eps_dp_ || have_eps_z_ || have_override_) {
+    enqueue();
+    return;
+  }
+  GraphSlot& g = graphs_[key];
+  if (g.exec && g.gen == g_ws_generation.load()) {
+    CUDA_CHECK(cudaGraphLaunch(g.exec, stream_));
+    count_launches(g.launches);
+    return;
+  }
+  if (g.exec) {
+    cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+  }
+  if (g.seen++ == 0) {                 // first call of a key runs directly: lazy weight packing, function attributes
+    enqueue();
+    return;
+  }
+  const unsigned long long n0 = launch_count();
+  CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+  capturing_ = true;
+  cudaGraph_t graph = nullptr;
+  try {
+    enqueue();
+  } catch (...) {
+    capturing_ = false;
+    cudaStreamEndCapture(stream_, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  capturing_ = false;
+  CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+  g.exec = exec;
+  g.gen = g_ws_generation.load();
+  g.launches = launch_count() - n0;    // counted once while capturing; the launch below is that one execution
+  CUDA_CHECK(cudaGraphLaunch(exec, stream_));
+}
+
 void Engine::run_front() {
+  const int B = B_;
+  if (debug_) taps_.clear();
+  if (profile_) profile_begin();
+  upload_speakers(B);
+  CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
+  const unsigned long long key = (1ull << 60) | ((unsigned long long)B << 36) | ((unsigned long long)Tmax_ << 8) |
+                                 (unsigned long long)(mma_mask_ & 0xff);
+  run_graphed(key, [this] { enqueue_front(); });
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
+  // ---- the one data-dependent host round trip: output lengths size everything downstream
+  misc_pin_.ensure(size_t(B) * 32);
+  int* yl = misc_pin_.as<int>();
+  CUDA_CHECK(cudaMemcpyAsync(yl, ylen_d_.p, size_t(B) * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  ylen_h_.assign(yl, yl + B);
+  if (debug_) {
+    const int Tp = Tp_;
+    HostTap t;
+    t.B = B; t.C = 1; t.pitch = Tp; t.len = len_h_;
+    t.data.resize(size_t(B) * Tp);
+    CUDA_CHECK(cudaMemcpy(t.data.data(), logw_d_.p, size_t(B) * Tp * 4, cudaMemcpyDeviceToHost));
+    taps_["logw"] = t;
+    std::vector<int> cum(size_t(B) * Tp);
+    CUDA_CHECK(cudaMemcpy(cum.data(), cum_d_.p, cum.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < cum.size(); ++i) t.data[i] = float(cum[i]);
+    taps_["cum"] = t;
+  }
+}
+
+void Engine::enqueue_front() {
   const VoiceSpec& s = voice_.spec;
   const int H = s.hidden, I = s.inter, Tp = Tp_, B = B_, T = Tmax_;
   const int* len = len_d_.as<int>();
-  if (debug_) taps_.clear();
-  if (profile_) profile_begin();
+  const CallParams* cp = params_d_.as<CallParams>();
   View x = view(x_.as<float>(), H, Tp), t1 = view(t1_.as<float>(), H, Tp), qkv = view(qkv_.as<float>(), 3 * H, Tp),
        att = view(att_.as<float>(), H, Tp), ffn = view(ffn_.as<float>(), s.filter, Tp),
        stats = view(stats_.as<float>(), 2 * I, Tp);
-  upload_speakers(B);
-  CUDA_CHECK(cudaEventRecord(ev_[0], stream_));
   // ---- text encoder (models.py:198-209)
   launch_embed(ids_d_.as<int>(), Tp, W(voice_.emb), H, std::sqrt(float(H)), x, len, B, T, stream_);
   for (const EncLayerW& e : voice_.enc) {
@@ -431,7 +545,7 @@ void Engine::run_front() {
     c.y = stats;
     conv("enc", c, T, sum_T_);
   }
-  CUDA_CHECK(cudaEventRecord(ev_[1], stream_));
+  record(1);
   if (debug_) {
     save_tap("x", x, H, len_h_.data(), 1);
     save_tap("stats", stats, 2 * I, len_h_.data(), 1);
@@ -452,8 +566,7 @@ void Engine::run_front() {
     c.y = g;
     conv("dp", c, T, sum_T_);
   }
-  launch_dp_noise(z2, have_eps_dp_ ? epsdp_d_.as<float>() : nullptr, epsoff_d_.as<long long>(), seed_, scales_[2], len, B,
-                  T, stream_);
+  launch_dp_noise(z2, have_eps_dp_ ? epsdp_d_.as<float>() : nullptr, epsoff_d_.as<long long>(), cp, len, B, T, stream_);
   bool flipped = false;
   for (const ConvFlowW& cf : voice_.dp_flows) {
     flipped = !flipped;                       // Flip precedes every ConvFlow in the reversed list
@@ -467,28 +580,9 @@ void Engine::run_front() {
   }
   flipped = !flipped;                         // the Flip before ElementwiseAffine
   const int lw_ch = flipped ? 1 : 0;
-  launch_durations(z2.offset_channels(lw_ch), voice_.ea_m[0], voice_.ea_scale[0], scales_[1],
+  launch_durations(z2.offset_channels(lw_ch), voice_.ea_m[0], voice_.ea_scale[0], cp,
                    have_override_ ? override_d_.as<int>() : nullptr, Tp, cum_d_.as<int>(), Tp, ylen_d_.as<int>(),
                    logw_d_.as<float>(), len, B, T, stream_);
-  CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaEventRecord(ev_[2], stream_));
-  // ---- the one data-dependent host round trip: output lengths size everything downstream
-  misc_pin_.ensure(size_t(B) * 32);
-  int* yl = misc_pin_.as<int>();
-  CUDA_CHECK(cudaMemcpyAsync(yl, ylen_d_.p, size_t(B) * 4, cudaMemcpyDeviceToHost, stream_));
-  CUDA_CHECK(cudaStreamSynchronize(stream_));
-  ylen_h_.assign(yl, yl + B);
-  if (debug_) {
-    HostTap t;
-    t.B = B; t.C = 1; t.pitch = Tp; t.len = len_h_;
-    t.data.resize(size_t(B) * Tp);
-    CUDA_CHECK(cudaMemcpy(t.data.data(), logw_d_.p, size_t(B) * Tp * 4, cudaMemcpyDeviceToHost));
-    taps_["logw"] = t;
-    std::vector<int> cum(size_t(B) * Tp);
-    CUDA_CHECK(cudaMemcpy(cum.data(), cum_d_.p, cum.size() * 4, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < cum.size(); ++i) t.data[i] = float(cum[i]);
-    taps_["cum"] = t;
-  }
 }
 
 void Engine::plan_back() {
@@ -510,6 +604,7 @@ void Engine::plan_back() {
   }
   total_samples_ = off;
   sum_F_ = double(off) / s.hop;
+  Fmax = bucket_frames(Fmax);              // shape bucket (identity unless CUDA graphs are on)
   Fmax_ = Fmax;
   Fp_ = round4(Fmax);
   ensure_back(B_, Fmax);
@@ -699,21 +794,27 @@ void Engine::run_flow() {
   }
 }
 
-void Engine::run_back() {
+void Engine::enqueue_back() {
   const VoiceSpec& s = voice_.spec;
-  const int B = B_, H = s.hidden, I = s.inter, Fp = Fp_, F = Fmax_;
+  const int B = B_, I = s.inter, Fp = Fp_, F = Fmax_;
   const int* ylen = ylen_d_.as<int>();
   const int* len = len_d_.as<int>();
-  CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
   View stats = view(stats_.as<float>(), 2 * I, Tp_);
   View z = view(z_.as<float>(), I, Fp);
   launch_expand(stats, I, cum_d_.as<int>(), Tp_, len, ylen, z, have_eps_z_ ? epsz_d_.as<float>() : nullptr,
-                (long long)I * z_stride_, int(z_stride_), seed_, scales_[0], B, F, stream_);
+                (long long)I * z_stride_, int(z_stride_), params_d_.as<CallParams>(), B, F, stream_);
   if (debug_) save_tap("z_p", z, I, ylen_h_.data(), 1);
   run_flow();
   if (debug_) save_tap("z", z, I, ylen_h_.data(), 1);
-  CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
+  record(4);
   run_generator();
+}
+
+void Engine::run_back() {
+  CUDA_CHECK(cudaEventRecord(ev_[3], stream_));
+  const unsigned long long key = (2ull << 60) | ((unsigned long long)B_ << 36) | ((unsigned long long)Fmax_ << 8) |
+                                 (unsigned long long)(mma_mask_ & 0xff);
+  run_graphed(key, [this] { enqueue_back(); });
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaEventRecord(ev_[5], stream_));
 }
@@ -810,8 +911,8 @@ const float* Engine::encode(const int64_t* ids, int64_t n_ids, const float scale
   View stats = view(stats_.as<float>(), 2 * s.inter, Tp_);
   View z = view(z_.as<float>(), s.inter, Fp_);
   launch_expand(stats, s.inter, cum_d_.as<int>(), Tp_, len_d_.as<int>(), ylen_d_.as<int>(), z,
-                have_eps_z_ ? epsz_d_.as<float>() : nullptr, (long long)s.inter * z_stride_, int(z_stride_), seed_,
-                scales_[0], 1, Fmax_, stream_);
+                have_eps_z_ ? epsz_d_.as<float>() : nullptr, (long long)s.inter * z_stride_, int(z_stride_),
+                params_d_.as<CallParams>(), 1, Fmax_, stream_);
   const int F = ylen_h_[0];
   audio_pin_.ensure(size_t(s.inter) * F * 4);
   CUDA_CHECK(cudaMemcpy2DAsync(audio_pin_.p, size_t(F) * 4, z.p, size_t(Fp_) * 4, size_t(F) * 4, size_t(s.inter),
@@ -837,16 +938,22 @@ const float* Engine::vocode(const float* z, int B, int64_t frames, bool with_flo
   for (int b = 0; b < B; ++b) yl[b] = int(frames);
   CUDA_CHECK(cudaMemcpyAsync(ylen_d_.p, yl, size_t(B) * 4, cudaMemcpyHostToDevice, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  have_eps_z_ = false;
+  have_eps_z_ = have_eps_dp_ = have_override_ = false;
   plan_back();
   upload_speakers(B);
   if (debug_) taps_.clear();
   // z host [B][inter][frames] -> device [B][inter][Fp]
   CUDA_CHECK(cudaMemcpy2DAsync(z_.p, size_t(Fp_) * 4, z, size_t(frames) * 4, size_t(frames) * 4, size_t(B) * s.inter,
                                cudaMemcpyHostToDevice, stream_));
-  if (with_flow) run_flow();                 // decoder half of the reference's streaming split (flow + generator)
-  CUDA_CHECK(cudaEventRecord(ev_[4], stream_));
-  run_generator();
+  {
+    const unsigned long long key = (3ull << 60) | ((unsigned long long)B << 36) | ((unsigned long long)Fmax_ << 8) |
+                                   (unsigned long long)(mma_mask_ & 0x7f) | (with_flow ? 0x80ull : 0ull);
+    run_graphed(key, [this, with_flow] {
+      if (with_flow) run_flow();             // decoder half of the reference's streaming split (flow + generator)
+      record(4);
+      run_generator();
+    });
+  }
   CUDA_CHECK(cudaEventRecord(ev_[5], stream_));
   audio_pin_.ensure(size_t(total_samples_) * 4);
   CUDA_CHECK(cudaMemcpyAsync(audio_pin_.p, audio_d_.p, size_t(total_samples_) * 4, cudaMemcpyDeviceToHost, stream_));

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -170,6 +171,29 @@ class Engine {
   // sample-rate workspace
   DeviceBuf ga_, gp_, gq_, gs_, audio_d_, audio16_d_, peak_d_;
   PinnedBuf ids_pin_, misc_pin_, audio_pin_, audio16_pin_, eps_pin_;
+
+  // ---- CUDA graphs (PIPER_B200_GRAPH, engine.cu): the launch sequences of the front half (text encoder + duration
+  // predictor) and of the back half (expand + flow + generator) are captured once per shape bucket and replayed; the
+  // data-dependent output lengths are read from device memory by every kernel, so one graph serves a whole bucket.
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long gen = 0;      // workspace generation the graph's pointers belong to
+    int seen = 0;                    // calls with this key so far (the first one runs un-captured: lazy initialisation)
+    unsigned long long launches = 0; // kernel nodes (for launch_count)
+  };
+  std::map<unsigned long long, GraphSlot> graphs_;
+  int graph_mode_ = -1;              // -1: read PIPER_B200_GRAPH on first use
+  bool capturing_ = false;
+  bool graphs_on();
+  void run_graphed(unsigned long long key, const std::function<void()>& enqueue);
+  void record(int ev);               // stage event, usable inside a captured region
+  void drop_graphs();
+  int bucket_ids(int t) const;       // shape buckets (identity when graphs are off)
+  int bucket_frames(int f) const;
+  void enqueue_front();
+  void enqueue_back();
+  DeviceBuf params_d_;               // CallParams of the current call
+  PinnedBuf params_pin_, override_pin_;
 
   struct ProfRec { const char* tag; bool mma; cudaEvent_t e0, e1; double bytes, flops; int ci, rows, k, dil, up, max_len; double len_sum; };
   bool profile_ = false;

@@ -171,9 +171,16 @@ void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st);
 void launch_speaker_cond(const float* w, const float* bias, const float* emb_g, const int* sid, float* cond, int rows,
                          int gin, int B, cudaStream_t st);
 
+// Per-call scalars (the graph's `scales` input, piper.cpp:357-365, and the noise seed).  They live in device memory so
+// that a captured CUDA graph of the pipeline does not bake them in: a replay reads the values of the current call.
+struct CallParams {
+  unsigned long long seed;
+  float noise_scale, length_scale, noise_w, pad_;
+};
+
 // ---- stochastic duration predictor ------------------------------------------------------------
 // z[b][ch][t] = eps * noise_w  (eps explicit [sum_b 2*len_b] item-major, or Philox(seed) when eps == null)
-void launch_dp_noise(View z, const float* eps, const long long* eps_off, unsigned long long seed, float noise_w,
+void launch_dp_noise(View z, const float* eps, const long long* eps_off, const CallParams* cp,
                      const int* len, int B, int Tmax, cudaStream_t st);
 // h[c][t] = w[c] * z[x0_ch][t] + b[c] + g[c][t]
 void launch_cf_pre(View z, int x0_ch, const float* w, const float* b, View g, View h, int C, const int* len, int B,
@@ -182,12 +189,12 @@ void launch_cf_pre(View z, int x0_ch, const float* w, const float* b, View g, Vi
 void launch_spline_inverse(View z, int x1_ch, View h, int bins, float inv_sqrt_c, float bound, const int* len, int B,
                            int Tmax, cudaStream_t st);
 // logw = (z0 - m)*s ; w = exp(logw)*length_scale ; w_ceil = ceil(w) ; cum = inclusive scan ; y_len = max(sum, 1)
-void launch_durations(View z, float ea_m, float ea_scale, float length_scale, const int* w_override,
+void launch_durations(View z, float ea_m, float ea_scale, const CallParams* cp, const int* w_override,
                       int w_override_pitch, int* cum, int cum_pitch, int* y_len, float* logw_out, const int* len,
                       int B, int Tmax, cudaStream_t st);
 // z_p[c][j] = m_p[c][i(j)] + eps * exp(logs_p[c][i(j)]) * noise_scale   for j < y_len  (models.py:705-718)
 void launch_expand(View stats, int inter, const int* cum, int cum_pitch, const int* len, const int* y_len, View zp,
-                   const float* eps, long long eps_bs, int eps_cs, unsigned long long seed, float noise_scale, int B,
+                   const float* eps, long long eps_bs, int eps_cs, const CallParams* cp, int B,
                    int Fmax, cudaStream_t st);
 
 // ---- generator tail / audio epilogue ------------------------------------------------------------

@@ -31,6 +31,7 @@ except Exception as e:
 PY
 }
 run base PIPER_B200_NOP=1
+run graph PIPER_B200_GRAPH=1
 run uni PIPER_B200_UNI=1
 run uni_fused PIPER_B200_UNI=1 PIPER_B200_MMA=31
 run ln2_post2_att2 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT2=1
