@@ -75,9 +75,11 @@ MRF_FN void store_upsampled(const float (&v)[16], float* yb, int cs, int row0, i
   }
 }
 
-template <class P, int PREC, int MT>
+// TM: the activation rows of a channel chunk arrive as one tensor-map TMA copy (cp.async.bulk.tensor.3d, box
+// [KC channels][R / boxes columns], any start column, out-of-bounds zero filled) instead of KC per-row bulk copies.
+template <class P, int PREC, int MT, bool TM = false>
 MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem, Barriers<typename P::Mbar>& bar,
-                       uint32_t* tmem_base_s) {
+                       uint32_t* tmem_base_s, const typename P::TensorMap* tmx = nullptr) {
   constexpr bool TF32 = PREC == PREC_TF32;
   constexpr int ES = TF32 ? 4 : 2;
   constexpr int E = 16 / ES;
@@ -124,7 +126,32 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     return t0 < Lq;
   };
 
-  if (warp == 0) {
+  if (TM && warp == 0) {
+    // ---------------------------------------------------------------------- raw activation window via tensor-map TMA
+    if (P::elect_one(cx)) P::tma_prefetch_desc(tmx);
+    P::syncwarp();
+    const int n_box = a.tm_boxes, Wb = R / n_box;
+    const uint32_t box_bytes = (uint32_t)KC * (uint32_t)Wb * 4u;
+    uint32_t it = 0;
+    for (int tile = block; tile < total; tile += grid) {
+      int nt, b, t0, L, Lq;
+      bool ok = decode(tile, nt, b, t0, L, Lq);
+      ok = P::bcast0(cx, (int)ok) != 0;
+      if (!ok) continue;
+      const int t_lo = t0 - a.pad;                                     // may be negative: the box is zero filled there
+      for (int kc = 0; kc < n_kc; ++kc, ++it) {
+        const int s = it % C2_RAW_SLOTS;
+        if (it >= C2_RAW_SLOTS) P::mbar_wait(cx, &bar.raw_empty[s], ((it / C2_RAW_SLOTS) - 1) & 1);
+        if (P::elect_one(cx)) {
+          P::mbar_expect_tx(cx, &bar.raw_full[s], box_bytes * (uint32_t)n_box);
+          const uint32_t d = P::saddr(cx, RAW_ring + size_t(s) * raw_bytes);
+          P::tma_load_3d(cx, d, tmx, t_lo, kc * KC, b, &bar.raw_full[s]);
+          if (n_box == 2) P::tma_load_3d(cx, d + box_bytes, tmx, t_lo + Wb, kc * KC, b, &bar.raw_full[s]);
+        }
+        P::syncwarp();
+      }
+    }
+  } else if (warp == 0) {
     // ---------------------------------------------------------------------- raw activation rows via TMA, uniform issue
     uint32_t it = 0;
     for (int tile = block; tile < total; tile += grid) {
@@ -261,7 +288,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       int nt, b, t0, L, Lq;
       if (!decode(tile, nt, b, t0, L, Lq)) continue;
       const int t_lo = t0 - a.pad;
-      const int off = t_lo - (t_lo & ~3);                               // smem column of stage row 0
+      const int off = TM ? 0 : t_lo - (t_lo & ~3);                      // smem column of stage row 0
+      const int Wb = TM ? R / a.tm_boxes : RS;                          // TM: dense boxes [box][KC][Wb]
       for (int kc = 0; kc < n_kc; ++kc, ++raw_it, ++a_it) {
         const int rs = raw_it % C2_RAW_SLOTS, as = a_it % C2_A_SLOTS;
         P::mbar_wait(cx, &bar.raw_full[rs], (raw_it / C2_RAW_SLOTS) & 1);
@@ -270,14 +298,15 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
         uint8_t* A_lo = A_hi + a_part;
         for (int g = 0; g < KC / E; ++g) {
-          const float* rg = raw + (size_t)(g * E) * RS;
           for (int r = ctid; r < R; r += C2_CONV_THREADS) {
             const int t = t_lo + r;
             const bool live = t >= 0 && t < L;                          // outside the utterance: zeros, whatever the
             float v[E];                                                 // (unwritten / stale) smem holds
+            const int bx = (TM && r >= Wb) ? 1 : 0;
+            const float* rg = raw + (size_t)bx * KC * Wb + (size_t)(g * E) * Wb + (r - bx * Wb);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-              float x = live ? rg[(size_t)e * RS + r] : 0.f;
+              float x = live ? rg[(size_t)e * Wb] : 0.f;
               if (a.pre == PRE_LRELU) x = x > 0.f ? x : x * a.slope;
               v[e] = x;
             }

@@ -165,13 +165,24 @@ inline void pack(const float* wsrc, int ci, int k, int rows_p, const Plan& p, ui
 }
 
 // plan -> the tiling fields of the launch arguments; returns the grid size (0: nothing to do)
-inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len) {
+// tm: stage the activation rows with one tensor-map TMA copy per channel chunk (two when the staged window is wider than
+// the 256-element box limit) instead of one bulk copy per channel row; `td` then describes the tensor and the box.
+inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm = false, TmapDesc* td = nullptr) {
   a.n_tile = p.n_tile; a.acc_cols = p.n_tile; a.chains = p.chains; a.mh_stride = p.mh_stride; a.sep_corr = 0;
   a.kc = p.kc; a.stage_rows = p.stage_rows; a.raw_stride = p.raw_stride; a.t_slots = p.t_slots; a.tmem_cols = p.tmem_cols;
   a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);          // never more chains than weight units
   a.tiles_per_item = (max_len + p.mt - 1) / p.mt;
   a.total_tiles = a.tiles_per_item * B * p.n_tiles;
   a.batch = B;
+  a.tm_boxes = 0;
+  if (tm && td) {
+    a.tm_boxes = p.stage_rows > 256 ? 2 : 1;
+    a.raw_stride = p.stage_rows;                                  // boxes are dense: no alignment slack, any start column
+    td->base = a.x.p;
+    td->dims[0] = a.x.cs; td->dims[1] = a.ci; td->dims[2] = B;
+    td->stride1 = (long long)a.x.cs * 4; td->stride2 = a.x.bs * 4;
+    td->box[0] = p.stage_rows / a.tm_boxes; td->box[1] = p.kc; td->box[2] = 1;
+  }
   return std::min(a.total_tiles, 148);
 }
 

@@ -29,6 +29,46 @@ __global__ void __launch_bounds__(conv2::C2_THREADS, 1) conv2_kernel(const __gri
   conv2::conv2_body<DevPrim, PREC, MT>(a, cx, smem, bar, &tmem_base_s);
 }
 
+// Tensor-map variant (PIPER_B200_V2_TM=1): the activation window of a channel chunk is one cp.async.bulk.tensor copy.
+// The dynamic shared memory is re-aligned to 128 bytes by hand (tensor copies require it; the launcher adds the slack).
+template <int PREC, int MT>
+__global__ void __launch_bounds__(conv2::C2_THREADS, 1) conv2_tm_kernel(const __grid_constant__ MmaConvArgs a,
+                                                                        const __grid_constant__ CUtensorMap tmx) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) conv2::Barriers<uint64_t> bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
+  DevPrim::Ctx cx;
+  conv2::conv2_body<DevPrim, PREC, MT, true>(a, cx, smem, bar, &tmem_base_s, &tmx);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+bool encode_tmap(const TmapDesc& d, CUtensorMap* out) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)d.dims[0], (cuuint64_t)d.dims[1], (cuuint64_t)d.dims[2]};
+  const cuuint64_t strides[2] = {(cuuint64_t)d.stride1, (cuuint64_t)d.stride2};
+  const cuuint32_t box[3] = {(cuuint32_t)d.box[0], (cuuint32_t)d.box[1], (cuuint32_t)d.box[2]};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d.base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 bool conv2_plan(int ci, int rows, int k, int dil, int prec, int chains, Conv2Layer& l) {
@@ -61,7 +101,19 @@ void conv2_pack(const float* wsrc, int ci, int k, int rows_p, const Conv2Layer& 
 bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaStream_t st) {
   if (B <= 0 || max_len <= 0) return true;
   const conv2::Plan p = to_plan(l);
-  const int grid = conv2::fill_args(a, p, B, max_len);
+  static int g_tm = -1;                                 // PIPER_B200_V2_TM: tensor-map TMA for the activation window
+  if (g_tm < 0) {
+    const char* e = std::getenv("PIPER_B200_V2_TM");
+    g_tm = (e && std::atoi(e) > 0) ? 1 : 0;
+  }
+  TmapDesc td;
+  CUtensorMap tmx;
+  bool tm = g_tm != 0;
+  int grid = conv2::fill_args(a, p, B, max_len, tm, &td);
+  if (tm && !encode_tmap(td, &tmx)) {                    // (a view the encoder refuses: fall back to per-row copies)
+    tm = false;
+    grid = conv2::fill_args(a, p, B, max_len);
+  }
   static int g_small_too = -1;                          // PIPER_B200_V2=2: also take launches with fewer tiles than SMs
   if (g_small_too < 0) {
     const char* e = std::getenv("PIPER_B200_V2");
@@ -77,7 +129,22 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
     cudaFuncSetAttribute(conv2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv2_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set[dev & 63] = true;
+  }
+  if (tm) {
+    const size_t sm = p.smem + 128;
+    if (p.prec == 1) conv2_tm_kernel<1, 128><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
+    else if (p.prec == 2 && p.mt == 256) conv2_tm_kernel<2, 256><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
+    else if (p.prec == 2) conv2_tm_kernel<2, 128><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
+    else if (p.mt == 256) conv2_tm_kernel<0, 256><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
+    else conv2_tm_kernel<0, 128><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
+    count_launch();
+    return true;
   }
   if (p.prec == 1) conv2_kernel<1, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
   else if (p.prec == 2 && p.mt == 256) conv2_kernel<2, 256><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);

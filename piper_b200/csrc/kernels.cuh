@@ -58,6 +58,16 @@ struct ConvArgs {
 // max_len = max over the batch of (len[b]*len_scale + q_extra): sizes the grid.
 void launch_conv1d(ConvArgs a, int B, int max_len, cudaStream_t st);
 
+// What a TMA tensor map over an activation view [B][C][pitch] is built from (conv_mma2.cu encodes the CUtensorMap from
+// it; the CPU model in tests/sim executes it directly): element (x = time, y = channel, z = item), fp32, out-of-bounds
+// elements of a box read as zero.
+struct TmapDesc {
+  const float* base = nullptr;
+  int dims[3] = {0, 0, 0};                  // pitch, channels, items
+  long long stride1 = 0, stride2 = 0;       // bytes between channels / items
+  int box[3] = {0, 0, 1};                   // floats per row, rows, 1
+};
+
 // ---- tensor-core (tcgen05) Conv1d / ConvTranspose1d with split precision (conv_mma.cu) ----------------------
 struct MmaConvArgs {
   View x, y, y2, r;
@@ -75,6 +85,7 @@ struct MmaConvArgs {
   int kc = 0, stage_rows = 0, n_tile = 0, acc_cols = 0, tmem_cols = 0, a_slots = 1, w_slots = 2;   // from the MmaPlan
   int chains = 1, sep_corr = 0, mh_stride = 0;
   int raw_stride = 0, tiles_per_item = 0, total_tiles = 0, batch = 0, t_slots = 1, tpu = 1;   // persistent kernel
+  int tm_boxes = 0;              // conv2 tensor-map mode: boxes per channel chunk (0 = per-row bulk copies)
   unsigned long long* prof = nullptr;   // optional: per-role stall cycle counters (tools/conv_diag.py)
 };
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);

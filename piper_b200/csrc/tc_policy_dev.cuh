@@ -2,6 +2,7 @@
 // written against: inline PTX for tcgen05 / TMA / mbarrier, in the same forms conv_mma.cu has exercised on hardware.
 // The CPU counterpart (a functional model used by tests) is tests/sim/sim_prim.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cstdint>
@@ -69,6 +70,18 @@ struct DevPrim {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_saddr),
                  "l"(gsrc), "r"(bytes), "r"(saddr(c, m))
                  : "memory");
+  }
+  // TMA tensor copy (tiled mode, 3-D): one box [box2][box1][box0] global -> shared, dense, out-of-bounds elements zero;
+  // the whole box is credited to the mbarrier.  SASS: UTMALDG.
+  using TensorMap = CUtensorMap;
+  static __device__ __forceinline__ void tma_load_3d(Ctx& c, uint32_t dst_saddr, const TensorMap* tm, int x, int y, int z, Mbar* m) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst_saddr),
+        "l"(tm), "r"(x), "r"(y), "r"(z), "r"(saddr(c, m))
+        : "memory");
+  }
+  static __device__ __forceinline__ void tma_prefetch_desc(const TensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(tm) : "memory");
   }
   static __device__ __forceinline__ void tmem_alloc(Ctx& c, uint32_t* slot, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(saddr(c, slot)), "r"(cols) : "memory");

@@ -56,7 +56,9 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
     a.ci = ci; a.rows = rows; a.k = k; a.dil = dil; a.pad = desc[4]; a.q_extra = desc[5];
     a.pre = desc[6]; a.slope = slope; a.epi = desc[7]; a.split = desc[8]; a.first = desc[9];
     a.up = desc[10]; a.up_pad = desc[11]; a.mrf = desc[12]; a.mrf_n = desc[13];
-    int grid = conv2::fill_args(a, p, B, max_len);
+    const bool tm = (desc[25] & 4) != 0;                 // opts bit 2: tensor-map TMA for the activation window
+    TmapDesc td;
+    int grid = conv2::fill_args(a, p, B, max_len, tm, &td);
     if (desc[23] > 0) grid = std::min(grid, desc[23]);
     if (info) {
       info[0] = p.n_tile; info[1] = p.n_tiles; info[2] = p.mt; info[3] = p.kc; info[4] = p.t_slots; info[5] = a.chains;
@@ -69,7 +71,13 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
       for (auto& row : cta->tmem) for (float& v : row) v = std::numeric_limits<float>::quiet_NaN();
       std::unique_ptr<conv2::Barriers<SimMbar>> bar(new conv2::Barriers<SimMbar>);
       const std::string e = run_cta(*cta, conv2::C2_THREADS, block, grid, [&](SimPrim::Ctx& cx) {
-        if (tf32) conv2::conv2_body<SimPrim, 1, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        if (tm) {
+          if (tf32) conv2::conv2_body<SimPrim, 1, 128, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else if (prec == 2 && p.mt == 256) conv2::conv2_body<SimPrim, 2, 256, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else if (prec == 2) conv2::conv2_body<SimPrim, 2, 128, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else if (p.mt == 256) conv2::conv2_body<SimPrim, 0, 256, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else conv2::conv2_body<SimPrim, 0, 128, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+        } else if (tf32) conv2::conv2_body<SimPrim, 1, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
         else if (prec == 2 && p.mt == 256) conv2::conv2_body<SimPrim, 2, 256>(a, cx, cta->smem, *bar, &cta->tmem_base);
         else if (prec == 2) conv2::conv2_body<SimPrim, 2, 128>(a, cx, cta->smem, *bar, &cta->tmem_base);
         else if (p.mt == 256) conv2::conv2_body<SimPrim, 0, 256>(a, cx, cta->smem, *bar, &cta->tmem_base);

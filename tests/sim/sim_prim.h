@@ -16,6 +16,8 @@
 #include <thread>
 #include <vector>
 
+#include "../../piper_b200/csrc/kernels.cuh"   // TmapDesc
+
 namespace simtc {
 
 struct SimAbort : std::runtime_error { using std::runtime_error::runtime_error; };
@@ -219,6 +221,32 @@ struct SimPrim {
       complete_tx(m, bytes);
     });
   }
+  // cp.async.bulk.tensor.3d (tiled): a dense box, elements outside the tensor read as zero, full box bytes credited
+  using TensorMap = pb200::TmapDesc;
+  static void tma_load_3d(Ctx& c, uint32_t dst, const TensorMap* tm, int x, int y, int z, Mbar* m) {
+    const TensorMap t = *tm;
+    const uint32_t bytes = uint32_t(t.box[0]) * t.box[1] * t.box[2] * 4u;
+    check(c, (dst & 127) == 0, "cp.async.bulk.tensor needs a 128-byte aligned shared-memory destination");
+    check(c, (reinterpret_cast<uintptr_t>(t.base) & 15) == 0 && (t.stride1 & 15) == 0 && (t.stride2 & 15) == 0,
+          "tensor map: base and strides must be 16-byte aligned");
+    check(c, t.box[0] > 0 && t.box[0] <= 256 && t.box[1] > 0 && t.box[1] <= 256 && (t.box[0] * 4) % 16 == 0, "tensor map: box limits");
+    check(c, dst + bytes <= (uint32_t)c.cta->smem_bytes, "cp.async.bulk.tensor writes past shared memory");
+    SimCta* cta = c.cta;
+    cta->tma.push([cta, dst, t, x, y, z, bytes, m] {
+      float* d = reinterpret_cast<float*>(cta->smem + dst);
+      for (int k = 0; k < t.box[2]; ++k)
+        for (int j = 0; j < t.box[1]; ++j)
+          for (int i = 0; i < t.box[0]; ++i) {
+            const int xi = x + i, yj = y + j, zk = z + k;
+            const bool in = xi >= 0 && xi < t.dims[0] && yj >= 0 && yj < t.dims[1] && zk >= 0 && zk < t.dims[2];
+            *d++ = in ? *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(t.base) + (long long)zk * t.stride2 +
+                                                        (long long)yj * t.stride1 + (long long)xi * 4)
+                      : 0.f;
+          }
+      complete_tx(m, bytes);
+    });
+  }
+  static void tma_prefetch_desc(const TensorMap*) {}
   static void tmem_alloc(Ctx& c, uint32_t* slot, uint32_t cols) {
     check(c, cols >= 32 && cols <= 512 && (cols & (cols - 1)) == 0, "tmem columns must be a power of two in [32, 512]");
     c.cta->tmem_cols = cols;

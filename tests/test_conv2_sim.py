@@ -299,3 +299,53 @@ def test_tall_tiles_for_two_chain_layers(sim):
         pre = _ref_conv(clean[b], w, bias, 1, 2, 0, 0.1)
         ref = torch.tanh(pre[0::2]) * torch.sigmoid(pre[1::2])
         assert float((torch.from_numpy(y[b, :, :L]) - ref).abs().max()) <= 2e-5, info
+
+
+@pytest.mark.parametrize("prec,ci,rows,k,dil,lens", [(0, 32, 32, 7, 12, (600, 37, 257)),     # 328-row window: two boxes per chunk
+                                                      (0, 64, 64, 5, 6, (300, 9)),            # one box, 256-row tiles
+                                                      (1, 192, 64, 5, 1, (259, 130)),         # tf32x3, several channel chunks
+                                                      (2, 96, 192, 1, 1, (131, 4))])          # fp16x3 1x1 (flow pre)
+def test_tensor_map_activation_loads(sim, prec, ci, rows, k, dil, lens):
+    """opts bit 2: the activation window arrives as cp.async.bulk.tensor boxes (any start column, zero fill outside the
+    tensor) instead of one bulk copy per channel row - same results as the per-row path, for negative window starts,
+    windows that run past the pitch, and stale data past each utterance."""
+    B = len(lens)
+    x, clean = _ragged(B, ci, lens, seed=11 + ci)
+    rng = np.random.default_rng(6)
+    w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+    bias = rng.standard_normal(rows).astype(np.float32)
+    r = rng.standard_normal((B, rows, x.shape[2])).astype(np.float32)
+    y_tm, _, info = _run(sim, x, w, bias, lens, dil=dil, pre=1, epi="RES", prec=prec, r=r, opts=4, grid=2)
+    y_row, _, _ = _run(sim, x, w, bias, lens, dil=dil, pre=1, epi="RES", prec=prec, r=r, opts=0, grid=2)
+    for b, L in enumerate(lens):
+        assert np.array_equal(y_tm[b, :, :L], y_row[b, :, :L]), (b, info)       # same operands, same instruction order
+        ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, 1, 0.1) + torch.from_numpy(r[b, :, :L])
+        e = float((torch.from_numpy(y_tm[b, :, :L]) - ref).abs().max())
+        assert e <= _tol(prec != 0) * max(1.0, float(ref.abs().max())), (b, e, info)
+        assert np.all(y_tm[b, :, L:] == 7e7), "stored outside the utterance"
+
+
+def test_tensor_map_conv_transpose_tail(sim):
+    """ConvTranspose lowering in tensor-map mode: the tail tile past the input length loads a window that lies wholly
+    outside the utterance (masked to zero by the converter)."""
+    up, ku = 8, 16
+    ci, co, lens = 64, 32, (256, 140)          # 256 = one full tile, so the q_extra tail is a tile of its own
+    B = len(lens)
+    x, clean = _ragged(B, ci, lens, seed=up)
+    rng = np.random.default_rng(4)
+    Wt = (rng.standard_normal((ci, co, ku)) / np.sqrt(ci * 2)).astype(np.float32)
+    bias_c = rng.standard_normal(co).astype(np.float32)
+    m = ku // up
+    w = np.zeros((co * up, ci, m), np.float32)
+    for j in range(m):
+        for phi in range(up):
+            w[phi::up, :, j] = Wt[:, :, phi + (m - 1 - j) * up].T
+    bias = np.repeat(bias_c, up)
+    y, _, info = _run(sim, x, w, bias, lens, pad=m - 1, pre=1, epi="UPSAMPLE", up=up, up_pad=up // 2, q_extra=m - 1,
+                      y_channels=co, opts=4)
+    for b, L in enumerate(lens):
+        ref = F.conv_transpose1d(F.leaky_relu(clean[b], 0.1)[None].double(), torch.from_numpy(Wt).double(),
+                                 torch.from_numpy(bias_c).double(), stride=up, padding=up // 2)[0].float()
+        e = float((torch.from_numpy(y[b, :, :L * up]) - ref).abs().max())
+        assert e <= 3e-4 * max(1.0, float(ref.abs().max())), (b, e, info)
+        assert np.all(y[b, :, L * up:] == 7e7)

@@ -106,7 +106,9 @@ print("RESULT " + json.dumps(out))
 
 
 @pytest.mark.parametrize("env", [{"PIPER_B200_UNI": "1"}, {"PIPER_B200_SMALL": "1"}, {"PIPER_B200_UNI": "1", "PIPER_B200_SMALL": "1"},
-                                 {"PIPER_B200_LN2": "1", "PIPER_B200_POST2": "1", "PIPER_B200_ATT2": "1"}, {"PIPER_B200_ATT3": "1"}, {"PIPER_B200_V2": "1"}, {"PIPER_B200_V2": "2"}, {"PIPER_B200_V2": "1", "PIPER_B200_V2_PREC": "f16"}, {"PIPER_B200_V2": "1", "PIPER_B200_MMA": "31"}])
+                                 {"PIPER_B200_LN2": "1", "PIPER_B200_POST2": "1", "PIPER_B200_ATT2": "1"}, {"PIPER_B200_ATT3": "1"}, {"PIPER_B200_V2": "1"}, {"PIPER_B200_V2": "2"}, {"PIPER_B200_V2": "1", "PIPER_B200_V2_PREC": "f16"}, {"PIPER_B200_V2": "1", "PIPER_B200_MMA": "31"},
+                                 {"PIPER_B200_V2": "1", "PIPER_B200_V2_TM": "1"},
+                                 {"PIPER_B200_V2": "2", "PIPER_B200_V2_TM": "1", "PIPER_B200_V2_PREC": "f16"}])
 def test_env_gated_variants_keep_parity(env):
     """PIPER_B200_UNI (uniform-issue TMA warps of the persistent conv kernel), PIPER_B200_SMALL (double-buffered plan for
     small one-tile-per-CTA launches) and PIPER_B200_V2 (second-generation conv kernel, conv_mma2.cu) are read once per

@@ -38,6 +38,8 @@ run ln2_post2_att2 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT2=1
 run att3 PIPER_B200_ATT3=1
 run v2 PIPER_B200_V2=1
 run v2_f16 PIPER_B200_V2=1 PIPER_B200_V2_PREC=f16
+run v2_tm PIPER_B200_V2=1 PIPER_B200_V2_TM=1
+run v2_f16_tm_graph PIPER_B200_V2=2 PIPER_B200_V2_PREC=f16 PIPER_B200_V2_TM=1 PIPER_B200_GRAPH=1
 run everything PIPER_B200_V2=2 PIPER_B200_V2_PREC=f16 PIPER_B200_MMA=31 PIPER_B200_LN2=1 PIPER_B200_POST2=1 PIPER_B200_ATT3=1   # v2 also for launches with < 148 tiles (batch-1 latency)
 PIPER_B200_UNI=1 timeout -k 10 200 python tools/layer_report.py > gpurun_out/ab_layer_report_uni.txt 2>&1
 tail -9 gpurun_out/ab_layer_report_uni.txt
