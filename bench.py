@@ -468,16 +468,16 @@ def run_engine(args):
 
     # ---------------- rooflines per conv family: CUDA events around every launch (profile mode), pipe-correct peaks
     peaks = measured_peaks()
-    pipe_peaks = measure_pipe_peaks(torch) if rank == 0 else {"tf32_tflops": 1.0, "fp32_fma_tflops": 1.0}
+    pipe_peaks = measure_pipe_peaks(torch) if (rank == 0 and not args.quick) else {"tf32_tflops": 1.0, "fp32_fma_tflops": 1.0}
     prec = engine_precision()
     roofline = conv_rooflines(voice, voice.run_staged, 2, peaks, pipe_peaks, prec)
 
     # ---------------- batch = 1 latency / real-time factor / time to first streamed chunk (BASELINE.json configs[1])
     b1 = batch1_latency(voice, ids_list[0])
-    streaming = time_to_first_chunk(voice, ids_list[0]) if (args.config == 2 or world == 1) else None
+    streaming = time_to_first_chunk(voice, ids_list[0]) if ((args.config == 2 or world == 1) and not args.quick) else None
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         th, procs = cpu_plan(cfg)
         utts = 1 if arch == "high" else 2
         v, n, secs = cpu_throughput(args.config, utts, th, procs)
@@ -605,6 +605,7 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--arch", default="medium", choices=["medium", "high"], help="decoder of the generator sweep (config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="developer A/B runs: no pipe-peak measurement, streaming leg or CPU baseline")
     ap.add_argument("--cpu-worker", type=int, default=0)
     ap.add_argument("--cpu-utts", type=int, default=2)
     ap.add_argument("--cpu-threads", type=int, default=8)

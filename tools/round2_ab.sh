@@ -15,12 +15,12 @@ set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 echo "== experimental parity tests" > gpurun_out/ab_tests.log
-PIPER_B200_EXPERIMENTAL=1 timeout -k 10 1200 python -m pytest tests/test_gpu_experimental.py -m gpu -q --timeout 600 >> gpurun_out/ab_tests.log 2>&1
+PIPER_B200_EXPERIMENTAL=1 timeout -k 10 900 python -m pytest tests/test_gpu_experimental.py -m gpu -q --timeout 600 >> gpurun_out/ab_tests.log 2>&1
 echo "rc=$?" >> gpurun_out/ab_tests.log
 tail -25 gpurun_out/ab_tests.log
 run() {  # name, env...
   local name=$1; shift
-  env "$@" timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_bench_$name.json 2> gpurun_out/ab_bench_$name.err
+  env "$@" timeout -k 10 300 python bench.py --steps 10 --warmup 3 --quick > gpurun_out/ab_bench_$name.json 2> gpurun_out/ab_bench_$name.err
   python - "$name" <<'PY'
 import json, sys
 try:
