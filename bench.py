@@ -399,8 +399,8 @@ def batch1_latency(voice, ids, reps=10):
 
 def engine_precision() -> dict:
     """Split-precision scheme per family as the library is configured."""
-    f16 = os.environ.get("PIPER_B200_PREC", "")
-    return {"generator": "bf16x3", "front": "tf32x3"} if f16 != "f16" else {"generator": "f16x3", "front": "f16x3"}
+    std = os.environ.get("PIPER_B200_V2_PREC", "f16") != "f16" or os.environ.get("PIPER_B200_V2", "2") == "0"
+    return {"generator": "bf16x3", "front": "tf32x3"} if std else {"generator": "f16x3", "front": "f16x3"}
 
 
 def run_engine(args):

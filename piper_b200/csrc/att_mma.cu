@@ -34,12 +34,18 @@ bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float
   a.qkv = qkv; a.out = out; a.rel_k = rel_k; a.rel_v = rel_v; a.len = len;
   a.H = H; a.dk = dk; a.n_heads = n_heads; a.q_tiles = (Tmax + att::A_QT - 1) / att::A_QT;
   const int smem = att::smem_bytes(dk);
-  static bool attr_set[64] = {};
+  // The opt-in limit (227 KB per block) covers static + dynamic shared memory, so asking for 227 KB of dynamic memory is
+  // refused: ask for what this head width needs (found on the first GPU run: the launch failed with "invalid argument").
+  static int attr_bytes[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set[dev & 63] = true;
+  if (attr_bytes[dev & 63] < smem) {
+    const cudaError_t e = cudaFuncSetAttribute(att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return false;                              // head width too large for one CTA: keep the CUDA-core kernel
+    }
+    attr_bytes[dev & 63] = smem;
   }
   att_kernel<<<a.q_tiles * n_heads * B, att::A_THREADS, smem, st>>>(a);
   count_launch();

@@ -292,6 +292,26 @@ int pb200_debug_conv1d(int32_t backend, const float* x, int32_t B, int32_t ci, i
       a.pre = pre_slope != 0.f ? PRE_LRELU : PRE_NONE; a.slope = pre_slope;
       a.epi = resid ? EPI_RES : EPI_BIAS;
       launch_conv1d(a, B, L, nullptr);
+    } else if (backend >= 3) {
+      // second-generation kernel (conv_mma2.cu): 3 = bf16x3, 4 = tf32x3 (2 chains), 5 = fp16x3 (1 chain), 6 = fp16x3 (2 chains)
+      const int prec = backend == 3 ? 0 : backend == 4 ? 1 : 2;
+      Conv2Layer l;
+      if (!conv2_plan(ci, co, k, dil, prec, (backend == 4 || backend == 6) ? 2 : 1, l))
+        throw std::runtime_error("shape not supported by the second-generation tensor-core conv");
+      std::vector<float> pk(size_t(ci) * k * rows_p, 0.f);
+      for (int i = 0; i < ci; ++i)
+        for (int j = 0; j < k; ++j)
+          for (int o = 0; o < co; ++o) pk[(size_t(i) * k + j) * rows_p + o] = w[(size_t(o) * ci + i) * k + j];
+      std::vector<uint8_t> packed(l.w_bytes);
+      conv2_pack(pk.data(), ci, k, rows_p, l, packed.data());
+      CK(cudaMalloc(&dw16, packed.size()));
+      CK(cudaMemcpy(dw16, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+      MmaConvArgs a;
+      a.x = vx; a.y = vy; a.r = vr; a.w = dw16; a.bias = db; a.len = dlen; a.len_scale = 1;
+      a.ci = ci; a.rows = co; a.k = k; a.dil = dil; a.pad = pad;
+      a.pre = pre_slope != 0.f ? PRE_LRELU : PRE_NONE; a.slope = pre_slope;
+      a.epi = resid ? EPI_RES : EPI_BIAS;
+      if (!launch_conv2(a, l, B, L, nullptr)) throw std::runtime_error("launch too small for conv2 (set PIPER_B200_V2=2)");
     } else {
       MmaPlan plan;
       if (!mma_plan(ci, co, k, dil, backend == 2, plan)) throw std::runtime_error("shape not supported by the tensor-core conv");

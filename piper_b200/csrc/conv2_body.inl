@@ -130,7 +130,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     // ---------------------------------------------------------------------- raw activation window via tensor-map TMA
     if (P::elect_one(cx)) P::tma_prefetch_desc(tmx);
     P::syncwarp();
-    const int n_box = a.tm_boxes, Wb = R / n_box;
+    const int n_box = a.tm_boxes, Wb = RS / n_box;
     const uint32_t box_bytes = (uint32_t)KC * (uint32_t)Wb * 4u;
     uint32_t it = 0;
     for (int tile = block; tile < total; tile += grid) {
@@ -138,15 +138,15 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       bool ok = decode(tile, nt, b, t0, L, Lq);
       ok = P::bcast0(cx, (int)ok) != 0;
       if (!ok) continue;
-      const int t_lo = t0 - a.pad;                                     // may be negative: the box is zero filled there
+      const int t_base = (t0 - a.pad) & ~3;                            // 16-byte aligned start (may be negative: zero fill)
       for (int kc = 0; kc < n_kc; ++kc, ++it) {
         const int s = it % C2_RAW_SLOTS;
         if (it >= C2_RAW_SLOTS) P::mbar_wait(cx, &bar.raw_empty[s], ((it / C2_RAW_SLOTS) - 1) & 1);
         if (P::elect_one(cx)) {
           P::mbar_expect_tx(cx, &bar.raw_full[s], box_bytes * (uint32_t)n_box);
           const uint32_t d = P::saddr(cx, RAW_ring + size_t(s) * raw_bytes);
-          P::tma_load_3d(cx, d, tmx, t_lo, kc * KC, b, &bar.raw_full[s]);
-          if (n_box == 2) P::tma_load_3d(cx, d + box_bytes, tmx, t_lo + Wb, kc * KC, b, &bar.raw_full[s]);
+          P::tma_load_3d(cx, d, tmx, t_base, kc * KC, b, &bar.raw_full[s]);
+          if (n_box == 2) P::tma_load_3d(cx, d + box_bytes, tmx, t_base + Wb, kc * KC, b, &bar.raw_full[s]);
         }
         P::syncwarp();
       }
@@ -246,6 +246,26 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
           uint32_t wb = desc_lo(P::saddr(cx, W_ring + size_t(ws) * unit_bytes), w_lbo);
 #pragma unroll 1
           for (int kb = 0; kb < KC / KSTEP; ++kb) {
+            if (a.mma3) {
+              // three instructions, every accumulator region addressed with one fixed (base, N): main = hi*hi,
+              // correction = hi*lo + lo*hi.  (The stacked form below writes [0, 2N) and then accumulates into [N, 2N):
+              // two PARTIALLY overlapping destinations in flight, which raced on hardware - see DESIGN.md.)
+              for (int mh = 0; mh < (MH == 2 && mh_live == 2 ? 2 : 1); ++mh) {
+                const uint32_t dm = d_pair + (uint32_t)(mh * a.mh_stride), ro = (uint32_t)mh * 128u;
+                if (P::elect_one(cx)) {
+                  if (TF32) {
+                    P::mma_tf32(cx, dm, ah + ro, wb, idesc1, acc);
+                    P::mma_tf32(cx, dm + (uint32_t)NT, ah + ro, wb + (uint32_t)NT, idesc1, acc);
+                    P::mma_tf32(cx, dm + (uint32_t)NT, al + ro, wb, idesc1, 1u);
+                  } else {
+                    P::mma_f16(cx, dm, ah + ro, wb, idesc1, acc);
+                    P::mma_f16(cx, dm + (uint32_t)NT, ah + ro, wb + (uint32_t)NT, idesc1, acc);
+                    P::mma_f16(cx, dm + (uint32_t)NT, al + ro, wb, idesc1, 1u);
+                  }
+                }
+                P::syncwarp();
+              }
+            } else {
             if (P::elect_one(cx)) {
               if (TF32) {
                 P::mma_tf32(cx, d_pair, ah, wb, idesc2, acc);                            // main | hi*lo
@@ -265,6 +285,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
                   P::mma_f16(cx, d_pair + (uint32_t)(a.mh_stride + NT), al + 128u, wb, idesc1, 1u);
                 }
               }
+            }
             }
             P::syncwarp();
             acc = 1u;
@@ -288,8 +309,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       int nt, b, t0, L, Lq;
       if (!decode(tile, nt, b, t0, L, Lq)) continue;
       const int t_lo = t0 - a.pad;
-      const int off = TM ? 0 : t_lo - (t_lo & ~3);                      // smem column of stage row 0
-      const int Wb = TM ? R / a.tm_boxes : RS;                          // TM: dense boxes [box][KC][Wb]
+      const int off = t_lo - (t_lo & ~3);                               // smem column of stage row 0
+      const int Wb = TM ? RS / a.tm_boxes : RS;                         // TM: dense boxes [box][KC][Wb]
       for (int kc = 0; kc < n_kc; ++kc, ++raw_it, ++a_it) {
         const int rs = raw_it % C2_RAW_SLOTS, as = a_it % C2_A_SLOTS;
         P::mbar_wait(cx, &bar.raw_full[rs], (raw_it / C2_RAW_SLOTS) & 1);
@@ -297,26 +318,47 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         const float* raw = reinterpret_cast<const float*>(RAW_ring + size_t(rs) * raw_bytes) + off;
         uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
         uint8_t* A_lo = A_hi + a_part;
-        for (int g = 0; g < KC / E; ++g) {
-          for (int r = ctid; r < R; r += C2_CONV_THREADS) {
-            const int t = t_lo + r;
-            const bool live = t >= 0 && t < L;                          // outside the utterance: zeros, whatever the
-            float v[E];                                                 // (unwritten / stale) smem holds
-            const int bx = (TM && r >= Wb) ? 1 : 0;
-            const float* rg = raw + (size_t)bx * KC * Wb + (size_t)(g * E) * Wb + (r - bx * Wb);
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-              float x = live ? rg[(size_t)e * Wb] : 0.f;
-              if (a.pre == PRE_LRELU) x = x > 0.f ? x : x * a.slope;
-              v[e] = x;
+        // One staged row (time step) per thread, channel groups in the inner loop: the addresses advance by constants, the
+        // in / out-of-utterance test is hoisted, and four groups are in flight per thread (the first version walked the
+        // groups in the outer loop - ~19 instructions per element, one load latency at a time; on the B200 the four
+        // converter warps, not the TMA issue or the tensor pipe, paced every small launch: profiles/r02_*.txt).
+        const int G = KC / E;
+        // work item = (row, share of the channel groups): with R = 136 rows and 128 threads a row-only split would leave
+        // 120 threads idle in the second pass
+        const int S = (G % 4 == 0 && G >= 16) ? 4 : (G % 2 == 0 && G >= 8) ? 2 : 1, GS = G / S;
+        for (int item = ctid; item < R * S; item += C2_CONV_THREADS) {
+          const int sg = item / R, r = item - sg * R;
+          const int t = t_lo + r;
+          const bool live = t >= 0 && t < L;                            // outside the utterance: zeros, whatever the
+          const int bx = (TM && off + r >= Wb) ? 1 : 0;                  // (unwritten / stale) smem holds
+          const size_t g_src = (size_t)E * Wb, g_dst = (size_t)R * 16;
+          const float* src = raw + (size_t)bx * KC * Wb + (r - bx * Wb) + (size_t)(sg * GS) * g_src;   // (raw points at column `off`)
+          uint8_t* dh = A_hi + r * 16 + (size_t)(sg * GS) * g_dst;
+          uint8_t* dl = A_lo + r * 16 + (size_t)(sg * GS) * g_dst;
+          if (!live) {
+            for (int g = 0; g < GS; ++g) {
+              *reinterpret_cast<uint4*>(dh + g * g_dst) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(dl + g * g_dst) = make_uint4(0u, 0u, 0u, 0u);
             }
-            const int o = (g * R + r) * 16;
+            continue;
+          }
+          const bool lrelu = a.pre == PRE_LRELU;
+          const float slope = a.slope;
+#pragma unroll 4
+          for (int g = 0; g < GS; ++g) {
+            float v[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[e] = src[g * g_src + (size_t)e * Wb];
+            if (lrelu) {
+#pragma unroll
+              for (int e = 0; e < E; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+            }
             if (TF32) {
               float h[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) h[e] = P::to_tf32(v[e % E]);
-              *reinterpret_cast<float4*>(A_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<float4*>(A_lo + o) =
+              *reinterpret_cast<float4*>(dh + g * g_dst) = make_float4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<float4*>(dl + g * g_dst) =
                   make_float4(v[0] - h[0], v[1 % E] - h[1], v[2 % E] - h[2], v[3 % E] - h[3]);
             } else {
               uint32_t hi[4], lo[4];
@@ -332,8 +374,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
                   lo[e >> 1] = P::pack_bf16(v[e % E] - ph, v[(e + 1) % E] - qh);
                 }
               }
-              *reinterpret_cast<uint4*>(A_hi + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(A_lo + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              *reinterpret_cast<uint4*>(dh + g * g_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(dl + g * g_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
           }
         }
@@ -344,19 +386,24 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     }
   } else {
     // ---------------------------------------------------------------------- epilogue
+    // The tensors an epilogue READS from global memory (the residual, the MRF / WaveNet-skip running sums) do not depend
+    // on the accumulator, so their loads are issued one work item ahead - the first item's before the accumulator is even
+    // waited for.  Measured on the B200 (profiles/r02_ncu_*): with the loads issued after tcgen05.ld, the 8 epilogue warps
+    // kept 16 KB in flight per SM and sat in `long scoreboard` for 45 % of all samples of the generator's 32-channel convs,
+    // holding the TMEM set (and through it the MMA warp and the converters) - 2.4 TB/s where HBM gives 6.5.
     const int ew = warp - C2_EPI_WARP0;                 // 0..7
     const int q = warp & 3, half = ew >> 2;             // TMEM lane quadrant is fixed by warp id % 4
     uint32_t t_it = 0;
     const int n_chunks = NT / 16;
     const int n_acc = 2 * a.chains;                     // (main | correction) per chain, NT columns apart
+    const int epi = a.epi;
+    const bool r_all = epi == EPI_RES || epi == EPI_MRF || epi == EPI_SUBFROM;     // residual for every row
+    const bool o_all = epi == EPI_MRF && a.mrf != 0;                               // running MRF sum for every row
     for (int tile = block; tile < total; tile += grid) {
       int nt, b, t0, L, Lq;
       if (!decode(tile, nt, b, t0, L, Lq)) continue;
       const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
       const int ts = t_it % t_slots;
-      P::mbar_wait(cx, &bar.t_full[ts], (t_it / t_slots) & 1);
-      P::fence_tc_after();
-      const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
       float* yb = a.y.p ? a.y.p + (long long)b * a.y.bs : nullptr;
       float* y2b = a.y2.p ? a.y2.p + (long long)b * a.y2.bs : nullptr;
       const float* rb = a.r.p ? a.r.p + (long long)b * a.r.bs : nullptr;
@@ -364,9 +411,36 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       // this thread's share of the tile: chunks c = half, half+2, ... of each live row half
       const int my_chunks = (n_chunks - half + 1) / 2;
       const int work = mh_live * my_chunks;
+      // kind of auxiliary read of a 16-row chunk: bit 0 = residual rows (r), bit 1 = running-sum rows (y2)
+      auto aux_kind = [&](int row0) -> int {
+        if (epi == EPI_WN) return row0 + 16 <= a.split ? 1 : (row0 >= a.split && !a.first ? 2 : 0);
+        return (r_all ? 1 : 0) | (o_all ? 2 : 0);
+      };
+      auto aux_issue = [&](int wi, float (&rv)[16], float (&ov)[16]) {
+        const int mh = wi / my_chunks, c = half + 2 * (wi - mh * my_chunks);
+        const int t = t0 + mh * 128 + q * 32 + lane;
+        if (t >= Lq) return;
+        const int row0 = n0 + c * 16, kind = aux_kind(row0);
+        if (kind & 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rv[i] = rb[(long long)(row0 + i) * a.r.cs + t];
+        }
+        if (kind & 2) {
+          const int o0 = epi == EPI_WN ? row0 - a.split : row0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ov[i] = y2b[(long long)(o0 + i) * a.y2.cs + t];
+        }
+      };
+      float rv[16], ov[16];
+      if (work > 0) aux_issue(0, rv, ov);
+      P::mbar_wait(cx, &bar.t_full[ts], (t_it / t_slots) & 1);
+      P::fence_tc_after();
+      const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
       for (int wi = 0; wi < work; ++wi) {
         const int mh = wi / my_chunks, c = half + 2 * (wi - mh * my_chunks);
         const int t = t0 + mh * 128 + q * 32 + lane;
+        float rn[16], on[16];
+        if (wi + 1 < work) aux_issue(wi + 1, rn, on);    // the next item's reads fly while this one is finished
         float v[16];
         const uint32_t tbase = d_set + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * a.mh_stride + c * 16);
         P::tmem_ld16(cx, tbase, v);
@@ -380,87 +454,80 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
           P::fence_tc_before();
           P::mbar_arrive(cx, &bar.t_empty[ts]);
         }
-        if (t >= Lq) continue;
-        const int row0 = n0 + c * 16;
-        if (a.bias) {
+        if (t < Lq) {
+          const int row0 = n0 + c * 16;
+          if (a.bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias + row0 + i);
-        }
-        if (a.bias_item) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias_item + (long long)b * a.bias_item_stride + row0 + i);
-        }
-        if (a.epi == EPI_GATE) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 2)
-            yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = wn_gate(v[i], v[i + 1]);
-          continue;
-        }
-        if (a.epi == EPI_RES || a.epi == EPI_MRF || a.epi == EPI_SUBFROM) {
-          float rv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) rv[i] = rb[(long long)(row0 + i) * a.r.cs + t];   // 16 loads in flight
-          if (a.epi == EPI_SUBFROM) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = rv[i] - v[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += rv[i];
+            for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias + row0 + i);
           }
-        }
-        if (a.epi == EPI_UPSAMPLE && (a.up == 8 || a.up == 4 || a.up == 2)) {
-          if (a.up == 8) store_upsampled<8>(v, yb, a.y.cs, row0, t, a.up_pad, L * 8);
-          else if (a.up == 4) store_upsampled<4>(v, yb, a.y.cs, row0, t, a.up_pad, L * 4);
-          else store_upsampled<2>(v, yb, a.y.cs, row0, t, a.up_pad, L * 2);
-          continue;
-        }
-        if (a.epi == EPI_MRF) {
-          if (a.mrf == 0) {
+          if (a.bias_item) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = v[i];
-          } else {
-            float ov[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ov[i] = y2b[(long long)(row0 + i) * a.y2.cs + t];
-            const float n_f = (float)a.mrf_n;
-            if (a.mrf == 1) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = ov[i] + v[i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = (ov[i] + v[i]) / n_f;
-            }
+            for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias_item + (long long)b * a.bias_item_stride + row0 + i);
           }
-          continue;
-        }
-        switch (a.epi) {
-          case EPI_RELU:
+          if (epi == EPI_GATE) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i] > 0.f ? v[i] : 0.f;
-            break;
-          case EPI_WN:
-            for (int i = 0; i < 16; ++i) {
-              const int row = row0 + i;
-              if (row < a.split) yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + v[i];
-              else {
-                float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
-                *o = a.first ? v[i] : *o + v[i];
+            for (int i = 0; i < 16; i += 2)
+              yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = wn_gate(v[i], v[i + 1]);
+          } else if (epi == EPI_UPSAMPLE) {
+            if (a.up == 8) store_upsampled<8>(v, yb, a.y.cs, row0, t, a.up_pad, L * 8);
+            else if (a.up == 4) store_upsampled<4>(v, yb, a.y.cs, row0, t, a.up_pad, L * 4);
+            else if (a.up == 2) store_upsampled<2>(v, yb, a.y.cs, row0, t, a.up_pad, L * 2);
+            else {
+              for (int i = 0; i < 16; ++i) {               // generic stride
+                const int row = row0 + i;
+                const int co = row / a.up, phi = row - co * a.up;
+                const int to = t * a.up + phi - a.up_pad;
+                if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = v[i];
               }
             }
-            break;
-          case EPI_UPSAMPLE:                              // generic stride (the common ones took the vector path above)
-            for (int i = 0; i < 16; ++i) {
-              const int row = row0 + i;
-              const int co = row / a.up, phi = row - co * a.up;
-              const int to = t * a.up + phi - a.up_pad;
-              if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = v[i];
+          } else if (epi == EPI_MRF) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += rv[i];
+            if (a.mrf == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += ov[i];
+            } else if (a.mrf != 0) {
+              const float n_f = (float)a.mrf_n;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = (ov[i] + v[i]) / n_f;
             }
-            break;
-          default:                                        // EPI_BIAS, and EPI_RES / EPI_SUBFROM after the residual fold
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = v[i];
+          } else if (epi == EPI_WN) {
+            const int kind = aux_kind(row0);
+            if (kind == 1) {                               // residual stream, in place
+#pragma unroll
+              for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = rv[i] + v[i];
+            } else if (row0 >= a.split) {                  // skip sum
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 - a.split + i) * a.y2.cs + t] = kind == 2 ? ov[i] + v[i] : v[i];
+            } else {                                       // a chunk that straddles the split (no real layer has one)
+              for (int i = 0; i < 16; ++i) {
+                const int row = row0 + i;
+                if (row < a.split) yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + v[i];
+                else {
+                  float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
+                  *o = a.first ? v[i] : *o + v[i];
+                }
+              }
+            }
+          } else {
+            if (epi == EPI_RES) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += rv[i];
+            } else if (epi == EPI_SUBFROM) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = rv[i] - v[i];
+            } else if (epi == EPI_RELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i];
-            break;
+          }
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { rv[i] = rn[i]; ov[i] = on[i]; }
       }
       if (work == 0) {                                   // a 16-row tile leaves the odd half of the warps without a chunk:
         P::fence_tc_before();                            // they still owe the accumulator set their arrival

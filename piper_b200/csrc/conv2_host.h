@@ -174,14 +174,35 @@ inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm 
   a.tiles_per_item = (max_len + p.mt - 1) / p.mt;
   a.total_tiles = a.tiles_per_item * B * p.n_tiles;
   a.batch = B;
+  {
+    // Launches with one or two tiles per CTA are a latency chain (load -> convert -> MMA -> epilogue): with the whole
+    // reduction in one channel chunk nothing overlaps.  Cut it into about four chunks so the stages pipeline within a
+    // tile.  (The packed weights do not depend on the chunk size; a smaller chunk only uses less of the planned smem.)
+    const int grid = std::min(a.total_tiles, 148);
+    const int per_cta = grid > 0 ? (a.total_tiles + grid - 1) / grid : 0;
+    const int kstep = p.tf32 ? 8 : 16;
+    if (per_cta <= 2 && a.ci / p.kc < 4) {
+      int pick = 0;
+      for (int c = p.kc; c >= kstep; c -= kstep) {
+        if (a.ci % c) continue;
+        if (c < 32 && pick) break;
+        pick = c;
+        if (a.ci / c >= 4) break;
+      }
+      if (pick) a.kc = pick;
+    }
+    a.chains = std::min(p.chains, (a.ci / a.kc) * a.k);
+  }
   a.tm_boxes = 0;
   if (tm && td) {
-    a.tm_boxes = p.stage_rows > 256 ? 2 : 1;
-    a.raw_stride = p.stage_rows;                                  // boxes are dense: no alignment slack, any start column
+    // the innermost start coordinate of a tiled tensor copy must be 16-byte aligned (an unaligned one is an illegal
+    // instruction on the B200: tools/probe/tma_probe.cu), so the window starts at t_lo rounded down to 4 floats and is
+    // raw_stride = stage_rows + 8 wide, like the per-row path
+    a.tm_boxes = p.raw_stride > 256 ? 2 : 1;
     td->base = a.x.p;
     td->dims[0] = a.x.cs; td->dims[1] = a.ci; td->dims[2] = B;
     td->stride1 = (long long)a.x.cs * 4; td->stride2 = a.x.bs * 4;
-    td->box[0] = p.stage_rows / a.tm_boxes; td->box[1] = p.kc; td->box[2] = 1;
+    td->box[0] = p.raw_stride / a.tm_boxes; td->box[1] = a.kc; td->box[2] = 1;
   }
   return std::min(a.total_tiles, 148);
 }

@@ -104,8 +104,14 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   static int g_tm = -1;                                 // PIPER_B200_V2_TM: tensor-map TMA for the activation window
   if (g_tm < 0) {
     const char* e = std::getenv("PIPER_B200_V2_TM");
-    g_tm = (e && std::atoi(e) > 0) ? 1 : 0;
+    g_tm = (e ? std::atoi(e) > 0 : true) ? 1 : 0;       // default on (0 = one bulk copy per channel row)
   }
+  static int g_mma3 = -1;                               // PIPER_B200_V2_MMA3: non-overlapping three-instruction k-step
+  if (g_mma3 < 0) {
+    const char* e = std::getenv("PIPER_B200_V2_MMA3");
+    g_mma3 = (e && std::atoi(e) > 0) ? 1 : 0;
+  }
+  a.mma3 = g_mma3;
   TmapDesc td;
   CUtensorMap tmx;
   bool tm = g_tm != 0;
@@ -117,7 +123,7 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   static int g_small_too = -1;                          // PIPER_B200_V2=2: also take launches with fewer tiles than SMs
   if (g_small_too < 0) {
     const char* e = std::getenv("PIPER_B200_V2");
-    g_small_too = (e && std::atoi(e) >= 2) ? 1 : 0;
+    g_small_too = (e ? std::atoi(e) >= 2 : true) ? 1 : 0;   // default: every launch (1 = only launches with >= 148 tiles)
   }
   if (a.total_tiles < 148 && !g_small_too) return false;   // small launches stay on the one-tile-per-CTA kernel
   static bool attr_set[64] = {};

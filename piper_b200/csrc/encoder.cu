@@ -520,7 +520,7 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
   static int g_att2 = -1;
   if (g_att2 < 0) {
     const char* e = std::getenv("PIPER_B200_ATT2");
-    g_att2 = e ? std::atoi(e) : 0;
+    g_att2 = e ? std::atoi(e) : 1;                       // default since round 2 (measured +; 0 = first version)
     if (g_att2) cudaFuncSetAttribute(rel_attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
   if (g_att2) rel_attention_kernel2<<<grid, 256, smem, st>>>(qkv, out, rel_k, rel_v, H, dk, window, len);
@@ -543,7 +543,7 @@ void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st) {
   static int g_ln2 = -1;                                  // experimental batched-load variant (see layernorm_kernel2)
   if (g_ln2 < 0) {
     const char* e = std::getenv("PIPER_B200_LN2");
-    g_ln2 = e ? std::atoi(e) : 0;
+    g_ln2 = e ? std::atoi(e) : 1;                        // default since round 2 (0 = first version)
     if (g_ln2) cudaFuncSetAttribute(layernorm_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
   if (g_ln2) layernorm_kernel2<<<grid, 256, smem, st>>>(a);

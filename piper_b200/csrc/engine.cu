@@ -69,12 +69,13 @@ Engine::Engine(const std::string& onnx_path, int device, bool upload) : device_(
   for (auto& ev : ev_) CUDA_CHECK(cudaEventCreate(&ev));
   weights_.ensure(voice_.blob.size() * sizeof(float));
   if (upload)
-    CUDA_CHECK(cudaMemcpy(weights_.p, voice_.blob.data(), voice_.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpyAsync(weights_.p, voice_.blob.data(), voice_.blob.size() * sizeof(float), cudaMemcpyHostToDevice, stream_));
   if (!voice_.blob_mma.empty()) {
     weights_mma_.ensure(voice_.blob_mma.size());
     if (upload)
-      CUDA_CHECK(cudaMemcpy(weights_mma_.p, voice_.blob_mma.data(), voice_.blob_mma.size(), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpyAsync(weights_mma_.p, voice_.blob_mma.data(), voice_.blob_mma.size(), cudaMemcpyHostToDevice, stream_));
   }
+  CUDA_CHECK(cudaStreamSynchronize(stream_));    // uploads from pageable memory: complete before the first kernel reads them
   if (const char* e = std::getenv("PIPER_B200_MMA")) mma_mask_ = std::atoi(e);
 }
 
@@ -127,7 +128,7 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   }
   if (v2_ < 0) {
     const char* e = std::getenv("PIPER_B200_V2");
-    v2_ = e ? std::atoi(e) : 0;
+    v2_ = e ? std::atoi(e) : 2;                        // default since round 2: the second-generation kernel for every launch (0 = first generation)
   }
   auto go = [&] {
     if (mma && v2_) {                                  // experimental kernel first; it declines small launches
@@ -174,14 +175,18 @@ const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a) {
     static int g_f16 = -1;
     if (g_f16 < 0) {
       const char* e = std::getenv("PIPER_B200_V2_PREC");
-      g_f16 = (e && std::string(e) == "f16") ? 1 : 0;
+      g_f16 = (e ? std::string(e) == "f16" : true) ? 1 : 0;      // default fp16x3 (PIPER_B200_V2_PREC=std: bf16x3 generator, tf32x3 elsewhere)
     }
     const int prec = g_f16 ? 2 : (w.plan.tf32 ? 1 : 0);
     if (conv2_plan(a.ci, a.rows, a.k, a.dil, prec, w.plan.tf32 ? 2 : 1, l)) {
       std::vector<uint8_t> host(l.w_bytes);
       conv2_pack(voice_.blob.data() + w.w, a.ci, a.k, a.rows_p, l, host.data());
       CUDA_CHECK(cudaMalloc(&l.w_dev, l.w_bytes));
-      CUDA_CHECK(cudaMemcpy(l.w_dev, host.data(), l.w_bytes, cudaMemcpyHostToDevice));
+      // On the engine's own stream and waited for: a synchronous cudaMemcpy from pageable memory may return before the DMA
+      // has landed and orders only against the legacy stream, which this (non-blocking) stream does not synchronise with -
+      // the first launch then raced the upload of its own weights (found on hardware: wrong first call, right ever after).
+      CUDA_CHECK(cudaMemcpyAsync(l.w_dev, host.data(), l.w_bytes, cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
     it = v2_layers_.emplace(&w, l).first;
   }
@@ -414,7 +419,7 @@ const HostTap* Engine::tap(const std::string& name) const {
 bool Engine::graphs_on() {
   if (graph_mode_ < 0) {
     const char* e = std::getenv("PIPER_B200_GRAPH");
-    graph_mode_ = e ? std::atoi(e) : 0;
+    graph_mode_ = e ? std::atoi(e) : 1;               // default on (PIPER_B200_GRAPH=0: direct launches)
   }
   return graph_mode_ > 0;
 }
@@ -755,7 +760,8 @@ void Engine::prepare_mrf_fused() {
   }
   if (!host.empty()) {
     mrf_w_.ensure(host.size());
-    CUDA_CHECK(cudaMemcpy(mrf_w_.p, host.data(), host.size(), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpyAsync(mrf_w_.p, host.data(), host.size(), cudaMemcpyHostToDevice, stream_));   // (see v2_layer)
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
   }
   mrf_ready_ = true;
 }

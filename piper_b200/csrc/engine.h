@@ -146,7 +146,7 @@ class Engine {
   MrfFusedPlan mrf_plan_post_;        // last stage with conv_post + tanh fused behind it (used when taps are off)
   std::vector<size_t> mrf_w_off_, mrf_b_off_;
   DeviceBuf mrf_w_;
-  int mma_mask_ = 15;  // generator bf16x3; flow, encoder, duration predictor tf32x3 with chained accumulators
+  int mma_mask_ = 31;  // generator bf16x3; flow, encoder, duration predictor tf32x3 with chained accumulators
 
   // request state
   int B_ = 0, Tmax_ = 0, Tp_ = 0, Fmax_ = 0, Fp_ = 0;

@@ -86,6 +86,7 @@ struct MmaConvArgs {
   int chains = 1, sep_corr = 0, mh_stride = 0;
   int raw_stride = 0, tiles_per_item = 0, total_tiles = 0, batch = 0, t_slots = 1, tpu = 1;   // persistent kernel
   int tm_boxes = 0;              // conv2 tensor-map mode: boxes per channel chunk (0 = per-row bulk copies)
+  int mma3 = 0;                  // conv2: three instructions per k-step on exactly matching accumulator regions (see conv2_body.inl)
   unsigned long long* prof = nullptr;   // optional: per-role stall cycle counters (tools/conv_diag.py)
 };
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);

@@ -136,8 +136,8 @@ void launch_conv_post(View x, const float* w, int C, int k, float slope, float* 
   }
   static int g_post2 = -1;                                // experimental batched-load variant (see conv_post_kernel2)
   if (g_post2 < 0) {
-    const char* e = std::getenv("PIPER_B200_POST2");
-    g_post2 = e ? std::atoi(e) : 0;
+    const char* e = std::getenv("PIPER_B200_POST2");   // default on since round 2
+    g_post2 = e ? std::atoi(e) : 1;
     if (g_post2) cudaFuncSetAttribute(conv_post_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
   if (g_post2) conv_post_kernel2<<<grid, 256, smem, st>>>(x, w, C, k, slope, out, out_off, len, len_scale);

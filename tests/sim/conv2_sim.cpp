@@ -57,6 +57,7 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
     a.pre = desc[6]; a.slope = slope; a.epi = desc[7]; a.split = desc[8]; a.first = desc[9];
     a.up = desc[10]; a.up_pad = desc[11]; a.mrf = desc[12]; a.mrf_n = desc[13];
     const bool tm = (desc[25] & 4) != 0;                 // opts bit 2: tensor-map TMA for the activation window
+    a.mma3 = (desc[25] & 8) ? 1 : 0;                     // opts bit 3: three instructions per k-step on matching accumulator regions
     TmapDesc td;
     int grid = conv2::fill_args(a, p, B, max_len, tm, &td);
     if (desc[23] > 0) grid = std::min(grid, desc[23]);

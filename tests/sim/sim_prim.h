@@ -227,6 +227,7 @@ struct SimPrim {
     const TensorMap t = *tm;
     const uint32_t bytes = uint32_t(t.box[0]) * t.box[1] * t.box[2] * 4u;
     check(c, (dst & 127) == 0, "cp.async.bulk.tensor needs a 128-byte aligned shared-memory destination");
+    check(c, ((x * 4) & 15) == 0, "cp.async.bulk.tensor: innermost start coordinate must be 16-byte aligned (illegal instruction on hardware)");
     check(c, (reinterpret_cast<uintptr_t>(t.base) & 15) == 0 && (t.stride1 & 15) == 0 && (t.stride2 & 15) == 0,
           "tensor map: base and strides must be 16-byte aligned");
     check(c, t.box[0] > 0 && t.box[0] <= 256 && t.box[1] > 0 && t.box[1] <= 256 && (t.box[0] * 4) % 16 == 0, "tensor map: box limits");

@@ -317,8 +317,10 @@ def test_tensor_map_activation_loads(sim, prec, ci, rows, k, dil, lens):
     r = rng.standard_normal((B, rows, x.shape[2])).astype(np.float32)
     y_tm, _, info = _run(sim, x, w, bias, lens, dil=dil, pre=1, epi="RES", prec=prec, r=r, opts=4, grid=2)
     y_row, _, _ = _run(sim, x, w, bias, lens, dil=dil, pre=1, epi="RES", prec=prec, r=r, opts=0, grid=2)
+    y_m3, _, _ = _run(sim, x, w, bias, lens, dil=dil, pre=1, epi="RES", prec=prec, r=r, opts=12, grid=2)   # + three-instruction k-step
     for b, L in enumerate(lens):
         assert np.array_equal(y_tm[b, :, :L], y_row[b, :, :L]), (b, info)       # same operands, same instruction order
+        assert np.abs(y_m3[b, :, :L] - y_row[b, :, :L]).max() <= 1e-5 * max(1.0, np.abs(y_row[b, :, :L]).max()), (b, info)
         ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, 1, 0.1) + torch.from_numpy(r[b, :, :L])
         e = float((torch.from_numpy(y_tm[b, :, :L]) - ref).abs().max())
         assert e <= _tol(prec != 0) * max(1.0, float(ref.abs().max())), (b, e, info)

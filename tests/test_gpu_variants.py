@@ -1,7 +1,8 @@
-"""GPU tests of EXPERIMENTAL, off-by-default kernels.  Skipped unless PIPER_B200_EXPERIMENTAL=1: these paths were written
-without GPU access at the end of round 1 and are not part of the product path until they pass here.
-
-  PIPER_B200_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q
+"""GPU tests of the kernel variants behind the environment switches.  The defaults since round 2 (second-generation conv
+kernel for every launch, fp16x3 operands, tensor-map TMA, CUDA graphs, fused MRF stage, batched-load LayerNorm / conv_post /
+attention) are what every other GPU test runs; here the first-generation paths they replaced are kept honest, the fused
+MRF stage is compared with the layer-wise path it replaces, and graph replay is compared with direct launches.
+The tensor-core attention (PIPER_B200_ATT3) is still experimental (it hung on its first hardware run): opt-in only.
 """
 import os
 
@@ -10,8 +11,7 @@ import pytest
 
 from piper_b200 import voicegen
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PIPER_B200_EXPERIMENTAL") != "1", reason="experimental kernels are opt-in")]
+pytestmark = pytest.mark.gpu
 SCALES = (0.667, 1.0, 0.8)
 
 
@@ -110,14 +110,19 @@ print("RESULT " + json.dumps(out))
 """
 
 
-@pytest.mark.parametrize("env", [{"PIPER_B200_UNI": "1"}, {"PIPER_B200_SMALL": "1"}, {"PIPER_B200_UNI": "1", "PIPER_B200_SMALL": "1"},
-                                 {"PIPER_B200_LN2": "1", "PIPER_B200_POST2": "1", "PIPER_B200_ATT2": "1"}, {"PIPER_B200_ATT3": "1"}, {"PIPER_B200_V2": "1"}, {"PIPER_B200_V2": "2"}, {"PIPER_B200_V2": "1", "PIPER_B200_V2_PREC": "f16"}, {"PIPER_B200_V2": "1", "PIPER_B200_MMA": "31"},
-                                 {"PIPER_B200_V2": "1", "PIPER_B200_V2_TM": "1"},
-                                 {"PIPER_B200_V2": "2", "PIPER_B200_V2_TM": "1", "PIPER_B200_V2_PREC": "f16"}])
+@pytest.mark.parametrize("env", [{"PIPER_B200_V2": "0"},                                  # first-generation conv kernels
+                                 {"PIPER_B200_V2": "0", "PIPER_B200_UNI": "1", "PIPER_B200_SMALL": "1"},
+                                 {"PIPER_B200_V2": "1"},                                  # second generation only for >= 148 tiles
+                                 {"PIPER_B200_V2_PREC": "std"},                           # bf16x3 generator, tf32x3 elsewhere
+                                 {"PIPER_B200_V2_TM": "0"},                               # one bulk copy per channel row
+                                 {"PIPER_B200_V2_MMA3": "1"},                             # three instructions per k-step
+                                 {"PIPER_B200_GRAPH": "0"},
+                                 {"PIPER_B200_LN2": "0", "PIPER_B200_POST2": "0", "PIPER_B200_ATT2": "0"},
+                                 {"PIPER_B200_MMA": "15"},                                # layer-wise MRF stage
+                                 {"PIPER_B200_V2_PREC": "std", "PIPER_B200_V2_TM": "0", "PIPER_B200_GRAPH": "0", "PIPER_B200_MMA": "15"}])
 def test_env_gated_variants_keep_parity(env):
-    """PIPER_B200_UNI (uniform-issue TMA warps of the persistent conv kernel), PIPER_B200_SMALL (double-buffered plan for
-    small one-tile-per-CTA launches) and PIPER_B200_V2 (second-generation conv kernel, conv_mma2.cu) are read once per
-    process, so the check runs in a child process."""
+    """Every non-default path keeps the 1e-3 waveform bar (the switches are read once per process, so each runs in a
+    child process)."""
     import json, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     e = dict(os.environ, **env)
