@@ -1,6 +1,6 @@
-// EXPERIMENTAL - OFF BY DEFAULT (PIPER_B200_ATT3=1).  Relative-position multi-head attention of the text encoder
-// (attentions.py:225-272) on the tensor cores, written against the primitive policy P (tc_policy_dev.cuh on the GPU,
-// tests/sim/sim_prim.h on the CPU) and checked by tests/test_att_sim.py without a GPU.  NOT yet run on hardware.
+// Relative-position multi-head attention of the text encoder (attentions.py:225-272) on the tensor cores (PIPER_B200_ATT3),
+// written against the primitive policy P (tc_policy_dev.cuh on the GPU, tests/sim/sim_prim.h on the CPU) and checked by
+// tests/test_att_sim.py without a GPU.
 //
 // One CTA per (utterance, head, tile of 128 queries).  Keys / values are walked in blocks of 64, twice:
 //   pass 1   S~ = Q_hi K_hi^T (one product, enough to place the softmax offset)        -> row maximum m
@@ -83,6 +83,7 @@ MRF_FN void split8(uint8_t* hi_row, uint8_t* lo_row, const float* v) {
 
 template <class P>
 MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers<typename P::Mbar>& bar, uint32_t* tmem_base_s) {
+  P::pdl_launch();
   const int tid = cx.tid(), lane = tid & 31, warp = P::bcast0(cx, tid >> 5);
   const int dk = a.dk, G = dk / 8;
   const int unit = cx.block();
@@ -112,6 +113,7 @@ MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers
   P::syncthreads(cx);
   P::fence_tc_after();
   const uint32_t tmem_d = *tmem_base_s;
+  P::pdl_sync();                                       // programmatic dependent launch: the prologue above overlapped the previous grid
   const float* base = a.qkv.p + (long long)b * a.qkv.bs;
   const float* qg = base + (long long)(h * dk) * a.qkv.cs;
   const float* kg = base + (long long)(a.H + h * dk) * a.qkv.cs;
@@ -345,7 +347,10 @@ MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers
     // ---- O = (main + correction) + banded relative values, normalised, stored channel-major
     P::mbar_wait(cx, &bar.kv_free, (it - 1) & 1);
     P::fence_tc_after();
-    if (i < T) {
+    {
+      // tcgen05.ld is .sync.aligned: the WHOLE warp must execute it, also the lanes whose query lies past the utterance
+      // (a ragged tile end) - only the stores are predicated.  (The first hardware run hung here: the loads sat inside
+      // `if (i < T)`; the CPU model executes lanes independently and cannot see a partial-warp collective.)
       const float inv_l = 1.f / l_run;
       float* ob = a.out.p + (long long)b * a.out.bs + (long long)(h * dk) * a.out.cs + i;
 #pragma unroll 1
@@ -353,12 +358,14 @@ MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers
         float o[16], cr[16];
         P::tmem_ld16(cx, tmem_d + lane_addr + A_TM_O + (uint32_t)(c * 16), o);
         P::tmem_ld16(cx, tmem_d + lane_addr + A_TM_O + (uint32_t)(dk + c * 16), cr);
+        if (i < T) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float acc = o[e] + cr[e];
+          for (int e = 0; e < 16; ++e) {
+            float acc = o[e] + cr[e];
 #pragma unroll
-          for (int k = 0; k < A_NREL; ++k) acc = fmaf(u[k], Ev[k * dk + c * 16 + e], acc);
-          ob[(long long)(c * 16 + e) * a.out.cs] = acc * inv_l;
+            for (int k = 0; k < A_NREL; ++k) acc = fmaf(u[k], Ev[k * dk + c * 16 + e], acc);
+            ob[(long long)(c * 16 + e) * a.out.cs] = acc * inv_l;
+          }
         }
       }
     }

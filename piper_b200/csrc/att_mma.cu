@@ -2,6 +2,7 @@
 // the body is att_body.inl (design notes there), the primitives tc_policy_dev.cuh.  The same body runs on the CPU model of
 // the primitives in tests/test_att_sim.py; it has NOT yet run on a GPU.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -47,7 +48,7 @@ bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float
     }
     attr_bytes[dev & 63] = smem;
   }
-  att_kernel<<<a.q_tiles * n_heads * B, att::A_THREADS, smem, st>>>(a);
+  launch_k(att_kernel, dim3(a.q_tiles * n_heads * B), dim3(att::A_THREADS), smem, st, a);
   count_launch();
   return true;
 }

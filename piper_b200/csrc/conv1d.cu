@@ -17,6 +17,7 @@
 // Reference ops covered: every Conv / ConvTranspose node of the exported graph except the depthwise
 // ones (modules.py:184-209,301-314,355-364; models.py:348-368; attentions.py:386-407).
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <atomic>
 #include <stdexcept>
@@ -46,6 +47,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // the copy itself (src-size < 16), which is what gives every utterance its own zero padding.
 template <int CPT, int WR, int TPT>
 __global__ void __launch_bounds__(256) conv1d_kernel(const ConvArgs a) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   constexpr int WT = 8 / WR;
   constexpr int ROWS = CPT * WR;
   constexpr int TT = WT * 32 * TPT;
@@ -244,7 +247,7 @@ void launch_cfg(ConvArgs& a, int B, int max_len, cudaStream_t st) {
     attr_set[dev & 63] = true;
   }
   dim3 grid((max_len + TT - 1) / TT, (a.rows + ROWS - 1) / ROWS, B);
-  conv1d_kernel<CPT, WR, TPT><<<grid, 256, smem, st>>>(a);
+  launch_k(conv1d_kernel<CPT, WR, TPT>, dim3(grid), dim3(256), smem, st, a);
   count_launch();
 }
 

@@ -86,6 +86,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   constexpr int KSTEP = 2 * E;
   constexpr int MH = MT / 128;
 
+  P::pdl_launch();
   const int tid = cx.tid(), lane = tid & 31, warp = P::bcast0(cx, tid >> 5);
   const int block = cx.block(), grid = cx.grid();
   const int KC = a.kc, R = a.stage_rows, RS = a.raw_stride, NT = a.n_tile;
@@ -113,6 +114,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   P::syncthreads(cx);
   P::fence_tc_after();
   const uint32_t tmem_d = *tmem_base_s;
+  P::pdl_sync();                                       // programmatic dependent launch: the prologue above overlapped the previous grid
 
   // tile id -> (output-row tile, item, time block); every role walks the same list and skips the same tiles
   auto decode = [&](int tile, int& nt, int& b, int& t0, int& L, int& Lq) {
@@ -349,9 +351,9 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
             float v[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) v[e] = src[g * g_src + (size_t)e * Wb];
-            if (lrelu) {
+            if (lrelu) {                                               // 0 < slope < 1: leaky_relu(x) = max(x, slope x)
 #pragma unroll
-              for (int e = 0; e < E; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+              for (int e = 0; e < E; ++e) v[e] = fmaxf(v[e], v[e] * slope);
             }
             if (TF32) {
               float h[4];
@@ -364,15 +366,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 8; e += 2) {
-                if (PREC == PREC_F16) {
-                  const float ph = P::f16_round(v[e % E]), qh = P::f16_round(v[(e + 1) % E]);
-                  hi[e >> 1] = P::pack_f16(ph, qh);
-                  lo[e >> 1] = P::pack_f16(v[e % E] - ph, v[(e + 1) % E] - qh);
-                } else {
-                  const float ph = P::bf16_round(v[e % E]), qh = P::bf16_round(v[(e + 1) % E]);
-                  hi[e >> 1] = P::pack_bf16(ph, qh);
-                  lo[e >> 1] = P::pack_bf16(v[e % E] - ph, v[(e + 1) % E] - qh);
-                }
+                if (PREC == PREC_F16) P::split2_f16(v[e % E], v[(e + 1) % E], hi[e >> 1], lo[e >> 1]);
+                else P::split2_bf16(v[e % E], v[(e + 1) % E], hi[e >> 1], lo[e >> 1]);
               }
               *reinterpret_cast<uint4*>(dh + g * g_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(dl + g * g_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

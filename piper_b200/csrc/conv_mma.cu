@@ -27,6 +27,7 @@
 // Reference ops: modules.py:184-209 (WN), 301-314 / 355-364 (ResBlock1/2), models.py:348-368 (Generator),
 // attentions.py:215-223,386-407 (1x1 projections, FFN), all lowered by voice.cc.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 
@@ -268,6 +269,7 @@ struct Barriers {
 // dynamic shared memory: A ring  A_SLOTS x { hi [KC/E][R][16 B], lo same }  |  W ring  W_SLOTS x { hi [KC/E][N][16 B], lo }
 template <bool TF32, int MT>
 __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs a) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh)
   constexpr int ES = TF32 ? 4 : 2;         // operand element bytes
   constexpr int E = 16 / ES;               // elements per 16-byte K chunk
   constexpr int KSTEP = 2 * E;             // K per MMA (32 bytes): 16 (bf16) / 8 (tf32)
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(MMA_THREADS) conv_mma_kernel(const MmaConvArgs
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
+  pdl_wait();                // the prologue above overlapped the previous grid; nothing below runs before it has completed
 
   if (warp >= 8) {
     // =========================== control warps: weight TMA (warp 9) and MMA issue (warp 8), one lane each ===
@@ -586,6 +589,7 @@ struct PBarriers {
 // profiles/r01_layer_report.txt (tiles per CTA x C_in x ~76 ns) - see DESIGN.md section 8.
 template <bool TF32, int MT, bool UNI = false>
 __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const MmaConvArgs a) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh)
   constexpr int ES = TF32 ? 4 : 2;
   constexpr int E = 16 / ES;
   constexpr int KSTEP = 2 * E;
@@ -626,6 +630,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_mma_persist_kernel(const Mm
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
+  pdl_wait();                // the prologue above overlapped the previous grid; nothing below runs before it has completed
 
   // tile id -> (output-row tile, item, time block); every role walks the same list and skips the same tiles
   auto decode = [&](int tile, int& nt, int& b, int& t0, int& L, int& Lq) {
@@ -1019,6 +1024,7 @@ __global__ void __launch_bounds__(128) mma_bench_kernel(int N, int tf32, int n_a
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
+  pdl_wait();                // the prologue above overlapped the previous grid; nothing below runs before it has completed
   if (warp == 0) {
     // whole warp runs the loop; only the tcgen05 instructions are predicated on the elected lane
     const int mode = a_rows_shift;
@@ -1180,12 +1186,12 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
         }
       }
       if (g_uni) {
-        if (p.tf32) conv_mma_persist_kernel<true, 128, true><<<grid, P_THREADS, smem, st>>>(a);
-        else if (mt == 256) conv_mma_persist_kernel<false, 256, true><<<grid, P_THREADS, smem, st>>>(a);
-        else conv_mma_persist_kernel<false, 128, true><<<grid, P_THREADS, smem, st>>>(a);
-      } else if (p.tf32) conv_mma_persist_kernel<true, 128><<<grid, P_THREADS, smem, st>>>(a);
-      else if (mt == 256) conv_mma_persist_kernel<false, 256><<<grid, P_THREADS, smem, st>>>(a);
-      else conv_mma_persist_kernel<false, 128><<<grid, P_THREADS, smem, st>>>(a);
+        if (p.tf32) launch_k(conv_mma_persist_kernel<true, 128, true>, dim3(grid), dim3(P_THREADS), smem, st, a);
+        else if (mt == 256) launch_k(conv_mma_persist_kernel<false, 256, true>, dim3(grid), dim3(P_THREADS), smem, st, a);
+        else launch_k(conv_mma_persist_kernel<false, 128, true>, dim3(grid), dim3(P_THREADS), smem, st, a);
+      } else if (p.tf32) launch_k(conv_mma_persist_kernel<true, 128>, dim3(grid), dim3(P_THREADS), smem, st, a);
+      else if (mt == 256) launch_k(conv_mma_persist_kernel<false, 256>, dim3(grid), dim3(P_THREADS), smem, st, a);
+      else launch_k(conv_mma_persist_kernel<false, 128>, dim3(grid), dim3(P_THREADS), smem, st, a);
       count_launch();
       return;
     }
@@ -1229,11 +1235,11 @@ void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaSt
   }
   dim3 grid((max_len + mt - 1) / mt, B, p.n_tiles);
   if (p.tf32) {
-    if (mt == 256) conv_mma_kernel<true, 256><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
-    else conv_mma_kernel<true, 128><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
+    if (mt == 256) launch_k(conv_mma_kernel<true, 256>, dim3(grid), dim3(MMA_THREADS), smem_bytes, st, a);
+    else launch_k(conv_mma_kernel<true, 128>, dim3(grid), dim3(MMA_THREADS), smem_bytes, st, a);
   } else {
-    if (mt == 256) conv_mma_kernel<false, 256><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
-    else conv_mma_kernel<false, 128><<<grid, MMA_THREADS, smem_bytes, st>>>(a);
+    if (mt == 256) launch_k(conv_mma_kernel<false, 256>, dim3(grid), dim3(MMA_THREADS), smem_bytes, st, a);
+    else launch_k(conv_mma_kernel<false, 128>, dim3(grid), dim3(MMA_THREADS), smem_bytes, st, a);
   }
   count_launch();
 }
@@ -1242,7 +1248,7 @@ void run_mma_bench(int N, int tf32, int n_acc, int iters, int shift, unsigned lo
   unsigned long long* d = nullptr;
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  mma_bench_kernel<<<1, 128, 48 * 1024>>>(N, tf32, n_acc, iters, shift, d);
+  launch_k(mma_bench_kernel, dim3(1), dim3(128), 48 * 1024, nullptr, N, tf32, n_acc, iters, shift, d);
   cudaDeviceSynchronize();
   cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
   cudaFree(d);

@@ -3,6 +3,7 @@
 // in tc_policy_dev.cuh, plan / pack / argument fill in conv2_host.h.  The same body runs on a CPU model of the primitives
 // in tests/test_conv2_sim.py (every epilogue, both split precisions, ragged batches); it has NOT yet run on a GPU.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 
@@ -144,19 +145,19 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   }
   if (tm) {
     const size_t sm = p.smem + 128;
-    if (p.prec == 1) conv2_tm_kernel<1, 128><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
-    else if (p.prec == 2 && p.mt == 256) conv2_tm_kernel<2, 256><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
-    else if (p.prec == 2) conv2_tm_kernel<2, 128><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
-    else if (p.mt == 256) conv2_tm_kernel<0, 256><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
-    else conv2_tm_kernel<0, 128><<<grid, conv2::C2_THREADS, sm, st>>>(a, tmx);
+    if (p.prec == 1) launch_k(conv2_tm_kernel<1, 128>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else if (p.prec == 2 && p.mt == 256) launch_k(conv2_tm_kernel<2, 256>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else if (p.prec == 2) launch_k(conv2_tm_kernel<2, 128>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else if (p.mt == 256) launch_k(conv2_tm_kernel<0, 256>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else launch_k(conv2_tm_kernel<0, 128>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
     count_launch();
     return true;
   }
-  if (p.prec == 1) conv2_kernel<1, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
-  else if (p.prec == 2 && p.mt == 256) conv2_kernel<2, 256><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
-  else if (p.prec == 2) conv2_kernel<2, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
-  else if (p.mt == 256) conv2_kernel<0, 256><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
-  else conv2_kernel<0, 128><<<grid, conv2::C2_THREADS, p.smem, st>>>(a);
+  if (p.prec == 1) launch_k(conv2_kernel<1, 128>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
+  else if (p.prec == 2 && p.mt == 256) launch_k(conv2_kernel<2, 256>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
+  else if (p.prec == 2) launch_k(conv2_kernel<2, 128>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
+  else if (p.mt == 256) launch_k(conv2_kernel<0, 256>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
+  else launch_k(conv2_kernel<0, 128>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
   count_launch();
   return true;
 }

@@ -6,6 +6,7 @@
 // regulator of SynthesizerTrn.infer (models.py:702-718) with generate_path (commons.py:116-129)
 // restated as a searchsorted gather instead of the [T',T] one-hot matmul.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace pb200 {
 void count_launch();
@@ -38,6 +39,8 @@ __device__ float philox_normal(unsigned long long seed, uint32_t stream, uint32_
 __global__ void __launch_bounds__(256) speaker_cond_kernel(const float* __restrict__ w, const float* __restrict__ bias,
                                                            const float* __restrict__ emb_g, const int* __restrict__ sid,
                                                            float* __restrict__ cond, int rows, int gin) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const int b = blockIdx.y;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -52,6 +55,8 @@ __global__ void __launch_bounds__(256) speaker_cond_kernel(const float* __restri
 
 __global__ void dp_noise_kernel(View z, const float* __restrict__ eps, const long long* __restrict__ eps_off,
                                 const CallParams* __restrict__ cp, const int* __restrict__ len) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const unsigned long long seed = cp->seed;
   const float noise_w = cp->noise_w;
   const int b = blockIdx.z, ch = blockIdx.y;
@@ -66,6 +71,8 @@ __global__ void dp_noise_kernel(View z, const float* __restrict__ eps, const lon
 
 __global__ void cf_pre_kernel(View z, int x0_ch, const float* __restrict__ w, const float* __restrict__ bias, View g,
                               View h, int C, const int* __restrict__ len) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const int b = blockIdx.z;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= len[b]) return;
@@ -82,6 +89,8 @@ __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log
 // One thread per (b, t).  Mirrors rational_quadratic_spline(inverse=True) with tails="linear".
 __global__ void spline_inverse_kernel(View z, int x1_ch, View h, int nb, float inv_sqrt_c, float bound,
                                       const int* __restrict__ len) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const int b = blockIdx.z;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= len[b]) return;
@@ -154,6 +163,8 @@ __global__ void __launch_bounds__(256) durations_kernel(View z, float ea_m, floa
                                                         const int* __restrict__ w_override, int w_override_pitch,
                                                         int* __restrict__ cum, int cum_pitch, int* __restrict__ y_len,
                                                         float* __restrict__ logw_out, const int* __restrict__ len) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   __shared__ int warp_tot[8];
   __shared__ int carry_s;
   const float length_scale = cp->length_scale;
@@ -200,6 +211,8 @@ __global__ void __launch_bounds__(256) expand_kernel(View stats, int inter, cons
                                                      const int* __restrict__ len, const int* __restrict__ y_len, View zp,
                                                      const float* __restrict__ eps, long long eps_bs, int eps_cs,
                                                      const CallParams* __restrict__ cp) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const unsigned long long seed = cp->seed;
   const float noise_scale = cp->noise_scale;
   const int b = blockIdx.z;
@@ -236,7 +249,7 @@ void launch_speaker_cond(const float* w, const float* bias, const float* emb_g, 
                          int gin, int B, cudaStream_t st) {
   if (B <= 0 || rows <= 0) return;
   dim3 grid((rows + 7) / 8, B);
-  speaker_cond_kernel<<<grid, 256, 0, st>>>(w, bias, emb_g, sid, cond, rows, gin);
+  launch_k(speaker_cond_kernel, dim3(grid), dim3(256), 0, st, w, bias, emb_g, sid, cond, rows, gin);
   count_launch();
 }
 
@@ -244,7 +257,7 @@ void launch_dp_noise(View z, const float* eps, const long long* eps_off, const C
                      const int* len, int B, int Tmax, cudaStream_t st) {
   if (B <= 0 || Tmax <= 0) return;
   dim3 grid((Tmax + 127) / 128, 2, B);
-  dp_noise_kernel<<<grid, 128, 0, st>>>(z, eps, eps_off, cp, len);
+  launch_k(dp_noise_kernel, dim3(grid), dim3(128), 0, st, z, eps, eps_off, cp, len);
   count_launch();
 }
 
@@ -252,7 +265,7 @@ void launch_cf_pre(View z, int x0_ch, const float* w, const float* b, View g, Vi
                    int Tmax, cudaStream_t st) {
   if (B <= 0 || Tmax <= 0) return;
   dim3 grid((Tmax + 127) / 128, 8, B);
-  cf_pre_kernel<<<grid, 128, 0, st>>>(z, x0_ch, w, b, g, h, C, len);
+  launch_k(cf_pre_kernel, dim3(grid), dim3(128), 0, st, z, x0_ch, w, b, g, h, C, len);
   count_launch();
 }
 
@@ -260,7 +273,7 @@ void launch_spline_inverse(View z, int x1_ch, View h, int bins, float inv_sqrt_c
                            int Tmax, cudaStream_t st) {
   if (B <= 0 || Tmax <= 0) return;
   dim3 grid((Tmax + 63) / 64, 1, B);
-  spline_inverse_kernel<<<grid, 64, 0, st>>>(z, x1_ch, h, bins, inv_sqrt_c, bound, len);
+  launch_k(spline_inverse_kernel, dim3(grid), dim3(64), 0, st, z, x1_ch, h, bins, inv_sqrt_c, bound, len);
   count_launch();
 }
 
@@ -269,7 +282,7 @@ void launch_durations(View z, float ea_m, float ea_scale, const CallParams* cp, 
                       int B, int Tmax, cudaStream_t st) {
   if (B <= 0) return;
   (void)Tmax;
-  durations_kernel<<<B, 256, 0, st>>>(z, ea_m, ea_scale, cp, w_override, w_override_pitch, cum, cum_pitch,
+  launch_k(durations_kernel, dim3(B), dim3(256), 0, st, z, ea_m, ea_scale, cp, w_override, w_override_pitch, cum, cum_pitch,
                                       y_len, logw_out, len);
   count_launch();
 }
@@ -279,7 +292,7 @@ void launch_expand(View stats, int inter, const int* cum, int cum_pitch, const i
                    int Fmax, cudaStream_t st) {
   if (B <= 0 || Fmax <= 0) return;
   dim3 grid((Fmax + 255) / 256, 8, B);
-  expand_kernel<<<grid, 256, 0, st>>>(stats, inter, cum, cum_pitch, len, y_len, zp, eps, eps_bs, eps_cs, cp);
+  launch_k(expand_kernel, dim3(grid), dim3(256), 0, st, stats, inter, cum, cum_pitch, len, y_len, zp, eps, eps_bs, eps_cs, cp);
   count_launch();
 }
 

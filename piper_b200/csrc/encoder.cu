@@ -7,6 +7,7 @@
 //     O_i     = sum_j P[i,j] v_j      +  sum_{|j-i|<=w} P[i,j] emb_rel_v[j-i+w]
 // and modules.LayerNorm (modules.py:23-26): LayerNorm over the CHANNEL axis, eps 1e-5.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cstdlib>
 
@@ -19,6 +20,8 @@ namespace {
 
 __global__ void embed_kernel(const int* __restrict__ ids, int ids_pitch, const float* __restrict__ emb, int H,
                              float scale, View x, const int* __restrict__ len, int Tmax) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const int b = blockIdx.z;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= len[b]) return;
@@ -39,6 +42,8 @@ constexpr int ATT_MAXR = 4;
 __global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, const float* __restrict__ rel_k,
                                                             const float* __restrict__ rel_v, int H, int dk, int window,
                                                             const int* __restrict__ len) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];
   const int b = blockIdx.z, h = blockIdx.y;
   const int T = len[b];
@@ -180,6 +185,8 @@ static_assert(ATT_QPW == 4, "rel_attention_kernel2 packs the four queries of a w
 __global__ void __launch_bounds__(256) rel_attention_kernel2(View qkv, View out, const float* __restrict__ rel_k,
                                                             const float* __restrict__ rel_v, int H, int dk, int window,
                                                             const int* __restrict__ len) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];
   const int b = blockIdx.z, h = blockIdx.y;
   const int T = len[b];
@@ -323,6 +330,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // LayerNorm over channels for a tile of 32 time steps; 8 warps split the channel axis.
 // Values are staged in shared memory [C][33] so the (optional) depthwise conv is evaluated once.
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];
   __shared__ float red[8][32];
   const int b = blockIdx.z;
@@ -391,6 +400,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
 // (36 launches per step) looks like: ~2 x 24 exposed L2 / DRAM latencies with only 16 warps per SM to hide them.
 constexpr int LN_U = 8;
 __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];  // [C][33]
   __shared__ float red[8][32];
   const int b = blockIdx.z;
@@ -492,7 +503,7 @@ void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float 
                   int Tmax, cudaStream_t st) {
   if (B <= 0 || Tmax <= 0) return;
   dim3 grid((Tmax + 127) / 128, 8, B);
-  embed_kernel<<<grid, 128, 0, st>>>(ids, ids_pitch, emb, H, scale, x, len, Tmax);
+  launch_k(embed_kernel, dim3(grid), dim3(128), 0, st, ids, ids_pitch, emb, H, scale, x, len, Tmax);
   count_launch();
 }
 
@@ -514,7 +525,7 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
   static int g_att3 = -1;                                 // experimental tensor-core attention (att_mma.cu)
   if (g_att3 < 0) {
     const char* e = std::getenv("PIPER_B200_ATT3");
-    g_att3 = e ? std::atoi(e) : 0;
+    g_att3 = e ? std::atoi(e) : 1;                       // default since round 2: tcgen05 attention (0 = CUDA-core kernel)
   }
   if (g_att3 && launch_rel_attention_tc(qkv, out, rel_k, rel_v, H, n_heads, window, len, B, Tmax, st)) return;
   static int g_att2 = -1;
@@ -523,8 +534,8 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
     g_att2 = e ? std::atoi(e) : 1;                       // default since round 2 (measured +; 0 = first version)
     if (g_att2) cudaFuncSetAttribute(rel_attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
-  if (g_att2) rel_attention_kernel2<<<grid, 256, smem, st>>>(qkv, out, rel_k, rel_v, H, dk, window, len);
-  else rel_attention_kernel<<<grid, 256, smem, st>>>(qkv, out, rel_k, rel_v, H, dk, window, len);
+  if (g_att2) launch_k(rel_attention_kernel2, dim3(grid), dim3(256), smem, st, qkv, out, rel_k, rel_v, H, dk, window, len);
+  else launch_k(rel_attention_kernel, dim3(grid), dim3(256), smem, st, qkv, out, rel_k, rel_v, H, dk, window, len);
   count_launch();
 }
 
@@ -546,8 +557,8 @@ void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st) {
     g_ln2 = e ? std::atoi(e) : 1;                        // default since round 2 (0 = first version)
     if (g_ln2) cudaFuncSetAttribute(layernorm_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
-  if (g_ln2) layernorm_kernel2<<<grid, 256, smem, st>>>(a);
-  else layernorm_kernel<<<grid, 256, smem, st>>>(a);
+  if (g_ln2) launch_k(layernorm_kernel2, dim3(grid), dim3(256), smem, st, a);
+  else launch_k(layernorm_kernel, dim3(grid), dim3(256), smem, st, a);
   count_launch();
 }
 

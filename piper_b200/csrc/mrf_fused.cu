@@ -33,6 +33,7 @@
 // TMEM columns: [0,256) two accumulator sets x two 128-row tiles x (32 main + 32 correction);
 //               [256,448) carriers, chain c / row tile m at 256 + 64 c + 32 m.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 
@@ -135,7 +136,7 @@ void launch_mrf_fused(MrfFusedArgs a, const MrfFusedPlan& p, int B, int max_len,
   mrf_fill_args(a, p, B, max_len);
   const long long total = a.total_tiles;
   const int grid = (int)std::min<long long>(total, 148);
-  mrf_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(a);
+  launch_k(mrf_fused_kernel, dim3(grid), dim3(F_THREADS), F_SMEM, st, a);
   count_launch();
 }
 

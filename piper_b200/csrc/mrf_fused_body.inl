@@ -68,6 +68,7 @@ MRF_FN void store_split8(uint8_t* hi_row, uint8_t* lo_row, const float* v) {
 template <class P>
 MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* smem, FBarriers<typename P::Mbar>& bar,
                            uint32_t* tmem_base_s) {
+  P::pdl_launch();
   const int tid = cx.tid(), lane = tid & 31, warp = P::bcast0(cx, tid >> 5);
   float* xs = reinterpret_cast<float*>(smem);
   uint8_t* A0 = smem + F_OFF_A0;
@@ -99,6 +100,7 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
   P::syncthreads(cx);
   P::fence_tc_after();
   const uint32_t tmem_d = *tmem_base_s;
+  P::pdl_sync();                                       // programmatic dependent launch: the prologue above overlapped the previous grid
 
   // tile id -> (item, first stored position); every role walks the same list and skips the same tiles
   auto decode = [&](int tile, int& b, int& t0, int& L) {

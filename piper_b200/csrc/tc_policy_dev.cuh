@@ -7,6 +7,8 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 
+#include "launch.cuh"
+
 namespace pb200 {
 namespace {
 
@@ -35,6 +37,8 @@ struct DevPrim {
         : "r"(0xFFFFFFFFu));
     return pred != 0;
   }
+  static __device__ __forceinline__ void pdl_launch() { pdl_launch_dependents(); }
+  static __device__ __forceinline__ void pdl_sync() { pdl_wait(); }
   static __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
   static __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
   static __device__ __forceinline__ void fence_tc_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -139,6 +143,20 @@ struct DevPrim {
         : "memory");
   }
   static __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+  // (a, b) -> packed hi pair and packed lo pair of the two-term split x = hi + lo: one cvt.rn.f16x2.f32 for the hi pair, two
+  // cvt.f32.f16 to get it back, two subtractions, one cvt for the lo pair (the element-wise form spent 10 conversions here)
+  static __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);           // .x = a (low half)
+    const __half2 l = __floats2half2_rn(a - __low2float(h), b - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  static __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
   static __device__ __forceinline__ float f16_round(float v) { return __half2float(__float2half_rn(v)); }
   static __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);                 // .x = a (low half), .y = b

@@ -2,6 +2,7 @@
 //   conv_post: leaky_relu(slope 0.01) -> Conv1d(C -> 1, k=7, no bias) -> tanh      (models.py:364-366)
 //   int16 epilogue: per-utterance peak, scale 32767 / max(0.01, peak), clamp, truncate  (piper.cpp:411-431)
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cstdlib>
 #include <stdexcept>
@@ -17,6 +18,8 @@ constexpr int POST_MAXK = 15;
 __global__ void __launch_bounds__(256) conv_post_kernel(View x, const float* __restrict__ w, int C, int k, float slope,
                                                         float* __restrict__ out, const long long* __restrict__ out_off,
                                                         const int* __restrict__ len, int len_scale) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];   // weights [C][k] | activated input tile [C][POST_TT + k - 1]
   const int b = blockIdx.z;
   const int L = len[b] * len_scale;
@@ -54,6 +57,8 @@ __global__ void __launch_bounds__(256) conv_post_kernel(View x, const float* __r
 __global__ void __launch_bounds__(256) conv_post_kernel2(View x, const float* __restrict__ w, int C, int k, float slope,
                                                          float* __restrict__ out, const long long* __restrict__ out_off,
                                                          const int* __restrict__ len, int len_scale) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];   // weights [C][k] | activated input tile [C][POST_TT + k - 1]
   const int b = blockIdx.z;
   const int L = len[b] * len_scale;
@@ -92,6 +97,8 @@ __global__ void __launch_bounds__(256) conv_post_kernel2(View x, const float* __
 __global__ void __launch_bounds__(256) peak_kernel(const float* __restrict__ audio, const long long* __restrict__ off,
                                                    const int* __restrict__ len, int len_scale,
                                                    unsigned int* __restrict__ peak) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const int b = blockIdx.z;
   const int L = len[b] * len_scale;
   const float* a = audio + off[b];
@@ -106,6 +113,8 @@ __global__ void __launch_bounds__(256) to_int16_kernel(const float* __restrict__
                                                        const long long* __restrict__ off, const int* __restrict__ len,
                                                        int len_scale, const unsigned int* __restrict__ peak,
                                                        int16_t* __restrict__ out) {
+  pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
+  pdl_wait();                // nothing below runs before the previous grid has completed
   const int b = blockIdx.z;
   const int L = len[b] * len_scale;
   const float mx = fmaxf(0.01f, __uint_as_float(peak[b]));   // maxAudioValue starts at 0.01f
@@ -140,8 +149,8 @@ void launch_conv_post(View x, const float* w, int C, int k, float slope, float* 
     g_post2 = e ? std::atoi(e) : 1;
     if (g_post2) cudaFuncSetAttribute(conv_post_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
-  if (g_post2) conv_post_kernel2<<<grid, 256, smem, st>>>(x, w, C, k, slope, out, out_off, len, len_scale);
-  else conv_post_kernel<<<grid, 256, smem, st>>>(x, w, C, k, slope, out, out_off, len, len_scale);
+  if (g_post2) launch_k(conv_post_kernel2, dim3(grid), dim3(256), smem, st, x, w, C, k, slope, out, out_off, len, len_scale);
+  else launch_k(conv_post_kernel, dim3(grid), dim3(256), smem, st, x, w, C, k, slope, out, out_off, len, len_scale);
   count_launch();
 }
 
@@ -151,7 +160,7 @@ void launch_peak(const float* audio, const long long* off, const int* len, int l
   int gx = (max_len + 256 * 8 - 1) / (256 * 8);
   if (gx < 1) gx = 1;
   dim3 grid(gx, 1, B);
-  peak_kernel<<<grid, 256, 0, st>>>(audio, off, len, len_scale, peak);
+  launch_k(peak_kernel, dim3(grid), dim3(256), 0, st, audio, off, len, len_scale, peak);
   count_launch();
 }
 
@@ -161,7 +170,7 @@ void launch_to_int16(const float* audio, const long long* off, const int* len, i
   int gx = (max_len + 256 * 8 - 1) / (256 * 8);
   if (gx < 1) gx = 1;
   dim3 grid(gx, 1, B);
-  to_int16_kernel<<<grid, 256, 0, st>>>(audio, off, len, len_scale, peak, out);
+  launch_k(to_int16_kernel, dim3(grid), dim3(256), 0, st, audio, off, len, len_scale, peak, out);
   count_launch();
 }
 

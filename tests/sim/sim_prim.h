@@ -95,6 +95,7 @@ struct SimCta {
   CtaBarrier sync;
   AsyncEngine tensor_core, tma;       // in-order, asynchronous (see AsyncEngine)
   CtaBarrier named[16];               // bar.sync id, count (count set on first use)
+  int aligned_ops[1024] = {};         // per thread: .sync.aligned collectives executed (tcgen05.ld / st) - must agree per warp
   std::atomic<bool> abort{false};
   std::mutex err_m;
   std::string err;
@@ -166,6 +167,8 @@ struct SimPrim {
     b.arrive_and_wait(c.cta->abort);
   }
   static bool elect_one(Ctx& c) { return (c.tid_ & 31) == 0; }
+  static void pdl_launch() {}
+  static void pdl_sync() {}
   static void fence_mbar_init() {}
   static void fence_async_proxy() {}
   static void fence_tc_before() {}
@@ -318,15 +321,27 @@ struct SimPrim {
     const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFFu;
     check(c, lane0 == 32u * ((c.tid_ >> 5) & 3), "tcgen05.ld outside the warp's TMEM lane quadrant (warp id % 4)");
     check(c, col + 16 <= c.cta->tmem_cols, "tcgen05.ld column range");
+    ++c.cta->aligned_ops[c.tid_];
     for (int i = 0; i < 16; ++i) v[i] = c.cta->tmem[lane0 + (c.tid_ & 31)][col + i];
   }
   static void tmem_st16(Ctx& c, uint32_t taddr, const float* v) {
     const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFFu;
     check(c, lane0 == 32u * ((c.tid_ >> 5) & 3), "tcgen05.st outside the warp's TMEM lane quadrant (warp id % 4)");
     check(c, col + 16 <= c.cta->tmem_cols, "tcgen05.st column range");
+    ++c.cta->aligned_ops[c.tid_];
     for (int i = 0; i < 16; ++i) c.cta->tmem[lane0 + (c.tid_ & 31)][col + i] = v[i];
   }
   static void tmem_wait_st() {}
+  static void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const uint16_t ha = f2h(a), hb = f2h(b);
+    hi = uint32_t(ha) | (uint32_t(hb) << 16);
+    lo = uint32_t(f2h(a - h2f(ha))) | (uint32_t(f2h(b - h2f(hb))) << 16);
+  }
+  static void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const uint16_t ha = f2bf(a), hb = f2bf(b);
+    hi = uint32_t(ha) | (uint32_t(hb) << 16);
+    lo = uint32_t(f2bf(a - bf2f(ha))) | (uint32_t(f2bf(b - bf2f(hb))) << 16);
+  }
   static float f16_round(float v) { return h2f(f2h(v)); }
   static uint32_t pack_f16(float a, float b) { return uint32_t(f2h(a)) | (uint32_t(f2h(b)) << 16); }
   static float bf16_round(float v) { return bf2f(f2bf(v)); }
@@ -354,6 +369,16 @@ inline std::string run_cta(SimCta& cta, int threads, int block, int grid, Body b
   for (auto& t : th) t.join();
   cta.tensor_core.finish();
   cta.tma.finish();
+  // tcgen05.ld / st are .sync.aligned: every lane of a warp must execute the same sequence (a lane that skips one hangs the
+  // warp on hardware).  Lanes run as independent threads here, so compare their counts afterwards.
+  if (cta.err.empty())
+    for (int w = 0; w * 32 < threads; ++w)
+      for (int l = 1; l < 32 && w * 32 + l < threads; ++l)
+        if (cta.aligned_ops[w * 32 + l] != cta.aligned_ops[w * 32]) {
+          cta.err = "warp " + std::to_string(w) + ": lanes executed different numbers of tcgen05.ld/st (.sync.aligned): lane 0 " +
+                    std::to_string(cta.aligned_ops[w * 32]) + ", lane " + std::to_string(l) + " " + std::to_string(cta.aligned_ops[w * 32 + l]);
+          return cta.err;
+        }
   return cta.err;
 }
 
