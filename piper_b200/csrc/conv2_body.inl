@@ -392,6 +392,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const int n_chunks = NT / 16;
     const int n_acc = 2 * a.chains;                     // (main | correction) per chain, NT columns apart
     const int epi = a.epi;
+    const bool bias_vec = a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0;
     const bool r_all = epi == EPI_RES || epi == EPI_MRF || epi == EPI_SUBFROM;     // residual for every row
     const bool o_all = epi == EPI_MRF && a.mrf != 0;                               // running MRF sum for every row
     for (int tile = block; tile < total; tile += grid) {
@@ -452,8 +453,16 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         if (t < Lq) {
           const int row0 = n0 + c * 16;
           if (a.bias) {
+            if (bias_vec) {                                  // 16-byte aligned bias vector: four 128-bit loads
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias + row0 + i);
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(a.bias + row0 + i);
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias + row0 + i);
+            }
           }
           if (a.bias_item) {
 #pragma unroll
@@ -482,9 +491,11 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] += ov[i];
             } else if (a.mrf != 0) {
-              const float n_f = (float)a.mrf_n;
+              // xs / num_kernels (models.py:363) as a multiplication by the rounded reciprocal: <= 1 ulp from the division,
+              // and 16 fp32 divisions per item were 14 % of this kernel's issue slots on the 64-channel stage
+              const float inv_n = 1.f / (float)a.mrf_n;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = (ov[i] + v[i]) / n_f;
+              for (int i = 0; i < 16; ++i) v[i] = (ov[i] + v[i]) * inv_n;
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = v[i];

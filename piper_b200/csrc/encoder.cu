@@ -402,7 +402,7 @@ constexpr int LN_U = 8;
 __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
   pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
   pdl_wait();                // nothing below runs before the previous grid has completed
-  extern __shared__ float sm[];  // [C][33]
+  extern __shared__ float sm[];  // [C][33] | gamma [C] | beta [C] | dw_b [C] | dw_w [C][dw_k]
   __shared__ float red[8][32];
   const int b = blockIdx.z;
   const int T = a.len[b];
@@ -413,6 +413,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
   const bool live = t < T;
   const int C = a.C;
   const float* ab = a.a.p + (long long)b * a.a.bs;
+  // Per-channel parameters go to shared memory once: read through __ldg inside the loops they were 24 dependent L2 round
+  // trips per warp in the output pass alone (39 % of this kernel's stall samples, profiles/r02_ncu_ln.txt).
+  float* gs = sm + C * 33;
+  float* bs = gs + C;
+  float* dwb = bs + C;
+  float* dww = dwb + C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    gs[c] = a.gamma[c];
+    bs[c] = a.beta[c];
+  }
+  if (a.mode == LN_DW_GELU) {
+    for (int c = threadIdx.x; c < C; c += 256) dwb[c] = a.dw_b[c];
+    for (int i = threadIdx.x; i < C * a.dw_k; i += 256) dww[i] = a.dw_w[i];
+    __syncthreads();                                     // (uniform branch) the depthwise taps are used in the load phase
+  }
   for (int c0 = warp; c0 < C; c0 += 8 * LN_U) {
     float v[LN_U];
     if (a.mode == LN_DW_GELU) {
@@ -423,10 +438,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
         v[u] = 0.f;
         if (live && c < C) {
           const float* ar = ab + (long long)c * a.a.cs;
-          float acc = __ldg(a.dw_b + c);
+          float acc = dwb[c];
           for (int j = 0; j < a.dw_k; ++j) {
             const int tt = t + (j - half) * a.dw_dil;
-            if (tt >= 0 && tt < T) acc = fmaf(__ldg(a.dw_w + c * a.dw_k + j), ar[tt], acc);
+            if (tt >= 0 && tt < T) acc = fmaf(dww[c * a.dw_k + j], ar[tt], acc);
           }
           v[u] = acc;
         }
@@ -489,7 +504,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
     for (int u = 0; u < LN_U; ++u) {
       const int c = c0 + 8 * u;
       if (c >= C) continue;
-      float v = (sm[c * 33 + lane] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
+      float v = (sm[c * 33 + lane] - mean) * rstd * gs[c] + bs[c];
       if (a.mode == LN_GELU_RES || a.mode == LN_DW_GELU) v = gelu_erf(v);
       if (a.mode == LN_GELU_RES) v += rv[u];
       yb[(long long)c * a.y.cs + t] = v;
@@ -541,7 +556,7 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
 
 void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st) {
   if (B <= 0 || Tmax <= 0) return;
-  const size_t smem = size_t(a.C) * 33 * sizeof(float);
+  const size_t smem = (size_t(a.C) * 33 + size_t(a.C) * (3 + (a.mode == LN_DW_GELU ? a.dw_k : 0))) * sizeof(float);
   if (smem > 96 * 1024) throw std::runtime_error("layernorm: channel count too large");
   static bool attr_set[64] = {};
   int dev = 0;

@@ -56,11 +56,7 @@ template <class P>
 MRF_FN void store_split8(uint8_t* hi_row, uint8_t* lo_row, const float* v) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int e = 0; e < 8; e += 2) {
-    const float ph = P::f16_round(v[e]), qh = P::f16_round(v[e + 1]);
-    hi[e >> 1] = P::pack_f16(ph, qh);
-    lo[e >> 1] = P::pack_f16(v[e] - ph, v[e + 1] - qh);
-  }
+  for (int e = 0; e < 8; e += 2) P::split2_f16(v[e], v[e + 1], hi[e >> 1], lo[e >> 1]);   // 3 conversions per pair instead of 5
   *reinterpret_cast<uint4*>(hi_row) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(lo_row) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
@@ -238,7 +234,7 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           float x = live ? xs[(g * 8 + e) * F_XS + off + rho] : 0.f;
-          v[e] = x > 0.f ? x : x * a.slope;
+          v[e] = fmaxf(x, x * a.slope);
         }
         store_split8<P>(A0 + (g * F_R0 + rho) * 16, A0 + F_A0_PART + (g * F_R0 + rho) * 16, v);
       }
@@ -252,7 +248,7 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
     const int q = warp & 3, m = ew >> 2;               // TMEM lane quadrant is fixed by warp id % 4; m = 128-row tile
     const int r = m * 128 + q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const float n_f = (float)n_chains;
+    const float inv_n = 1.f / (float)n_chains;          // xs / num_kernels as a multiplication (<= 1 ulp; 32 divisions per row saved)
     uint32_t g_it = 0;
     for (int tile = block; tile < total; tile += grid) {
       int b, t0, L;
@@ -315,7 +311,7 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
                 if (stored) {
                   float* yb = a.y.p + (long long)b * a.y.bs + pos;
 #pragma unroll
-                  for (int i = 0; i < F_C; ++i) yb[(long long)i * a.y.cs] = sum[i] / n_f;
+                  for (int i = 0; i < F_C; ++i) yb[(long long)i * a.y.cs] = sum[i] * inv_n;
                 }
               } else {
                 // Fused generator tail (models.py:364-366): the stage output never goes to HBM.  y -> leaky-relu, zero outside
@@ -326,8 +322,8 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
                   float w4[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const float yv = sum[bi * 4 + e] / n_f;
-                    w4[e] = inside ? (yv > 0.f ? yv : yv * a.post_slope) : 0.f;
+                    const float yv = sum[bi * 4 + e] * inv_n;
+                    w4[e] = inside ? fmaxf(yv, yv * a.post_slope) : 0.f;
                   }
                   uint8_t* blk = AC + (bi < 4 ? bi * F_RA * 16 : F_AC_PART + (bi - 4) * F_RA * 16) + F_GA * 16;
                   *reinterpret_cast<float4*>(blk + r * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
@@ -359,15 +355,21 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
             }
             // operand of this chain's next conv: lrelu, zero outside the utterance (every conv pads its own input)
             uint8_t* hi = AC + c * 2 * F_AC_PART + (F_GA + r) * 16;
+            if (inside) {
+              const float slope = a.slope;                   // 0 < slope < 1: leaky_relu(x) = max(x, slope x)
 #pragma unroll
-            for (int g = 0; g < F_C / 8; ++g) {
-              float w[8];
+              for (int g = 0; g < F_C / 8; ++g) {
+                float w[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float x = v[g * 8 + e];
-                w[e] = inside ? (x > 0.f ? x : x * a.slope) : 0.f;
+                for (int e = 0; e < 8; ++e) w[e] = fmaxf(v[g * 8 + e], v[g * 8 + e] * slope);
+                store_split8<P>(hi + g * F_RA * 16, hi + F_AC_PART + g * F_RA * 16, w);
               }
-              store_split8<P>(hi + g * F_RA * 16, hi + F_AC_PART + g * F_RA * 16, w);
+            } else {
+#pragma unroll
+              for (int g = 0; g < F_C / 8; ++g) {
+                *reinterpret_cast<uint4*>(hi + g * F_RA * 16) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(hi + F_AC_PART + g * F_RA * 16) = make_uint4(0u, 0u, 0u, 0u);
+              }
             }
             P::fence_async_proxy();
             P::mbar_arrive(cx, &bar.a_full[c]);
