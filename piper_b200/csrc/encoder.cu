@@ -399,11 +399,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
 // walks its 24 rows (C = 192) one dependent load -> store at a time in both passes, which is what its ~28 us per launch
 // (36 launches per step) looks like: ~2 x 24 exposed L2 / DRAM latencies with only 16 warps per SM to hide them.
 constexpr int LN_U = 8;
-__global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
+// NW warps per CTA: 24 for C >= 96 (each warp then owns <= 8 channel rows: ONE batch of loads per pass instead of three)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) layernorm_kernel2(const LnArgs a) {
   pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
   pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];  // [C][33] | gamma [C] | beta [C] | dw_b [C] | dw_w [C][dw_k]
-  __shared__ float red[8][32];
+  __shared__ float red[NW][32];
   const int b = blockIdx.z;
   const int T = a.len[b];
   const int t0 = blockIdx.x * 32;
@@ -419,22 +421,22 @@ __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
   float* bs = gs + C;
   float* dwb = bs + C;
   float* dww = dwb + C;
-  for (int c = threadIdx.x; c < C; c += 256) {
+  for (int c = threadIdx.x; c < C; c += NW * 32) {
     gs[c] = a.gamma[c];
     bs[c] = a.beta[c];
   }
   if (a.mode == LN_DW_GELU) {
-    for (int c = threadIdx.x; c < C; c += 256) dwb[c] = a.dw_b[c];
-    for (int i = threadIdx.x; i < C * a.dw_k; i += 256) dww[i] = a.dw_w[i];
+    for (int c = threadIdx.x; c < C; c += NW * 32) dwb[c] = a.dw_b[c];
+    for (int i = threadIdx.x; i < C * a.dw_k; i += NW * 32) dww[i] = a.dw_w[i];
     __syncthreads();                                     // (uniform branch) the depthwise taps are used in the load phase
   }
-  for (int c0 = warp; c0 < C; c0 += 8 * LN_U) {
+  for (int c0 = warp; c0 < C; c0 += NW * LN_U) {
     float v[LN_U];
     if (a.mode == LN_DW_GELU) {
       const int half = (a.dw_k - 1) / 2;
 #pragma unroll
       for (int u = 0; u < LN_U; ++u) {
-        const int c = c0 + 8 * u;
+        const int c = c0 + NW * u;
         v[u] = 0.f;
         if (live && c < C) {
           const float* ar = ab + (long long)c * a.a.cs;
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
       float w2[LN_U];
 #pragma unroll
       for (int u = 0; u < LN_U; ++u) {
-        const int c = c0 + 8 * u;
+        const int c = c0 + NW * u;
         v[u] = 0.f;
         w2[u] = 0.f;
         if (live && c < C) {
@@ -465,22 +467,22 @@ __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
     }
 #pragma unroll
     for (int u = 0; u < LN_U; ++u) {
-      const int c = c0 + 8 * u;
+      const int c = c0 + NW * u;
       if (c < C) sm[c * 33 + lane] = v[u];
     }
   }
   __syncthreads();
   float s = 0.f;
-  for (int c = warp; c < C; c += 8) s += sm[c * 33 + lane];
+  for (int c = warp; c < C; c += NW) s += sm[c * 33 + lane];
   red[warp][lane] = s;
   __syncthreads();
   float mean = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) mean += red[w][lane];
+  for (int w = 0; w < NW; ++w) mean += red[w][lane];
   mean /= (float)C;
   __syncthreads();
   float q = 0.f;
-  for (int c = warp; c < C; c += 8) {
+  for (int c = warp; c < C; c += NW) {
     const float d = sm[c * 33 + lane] - mean;
     q = fmaf(d, d, q);
   }
@@ -488,21 +490,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel2(const LnArgs a) {
   __syncthreads();
   float var = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) var += red[w][lane];
+  for (int w = 0; w < NW; ++w) var += red[w][lane];
   var /= (float)C;
   const float rstd = 1.f / sqrtf(var + 1e-5f);
   if (!live) return;
   float* yb = a.y.p + (long long)b * a.y.bs;
-  for (int c0 = warp; c0 < C; c0 += 8 * LN_U) {
+  for (int c0 = warp; c0 < C; c0 += NW * LN_U) {
     float rv[LN_U];
 #pragma unroll
     for (int u = 0; u < LN_U; ++u) {                      // the residual loads of the whole batch first
-      const int c = c0 + 8 * u;
+      const int c = c0 + NW * u;
       rv[u] = (a.mode == LN_GELU_RES && c < C) ? a.r.p[(long long)b * a.r.bs + (long long)c * a.r.cs + t] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < LN_U; ++u) {
-      const int c = c0 + 8 * u;
+      const int c = c0 + NW * u;
       if (c >= C) continue;
       float v = (sm[c * 33 + lane] - mean) * rstd * gs[c] + bs[c];
       if (a.mode == LN_GELU_RES || a.mode == LN_DW_GELU) v = gelu_erf(v);
@@ -570,9 +572,21 @@ void launch_layernorm(const LnArgs& a, int B, int Tmax, cudaStream_t st) {
   if (g_ln2 < 0) {
     const char* e = std::getenv("PIPER_B200_LN2");
     g_ln2 = e ? std::atoi(e) : 1;                        // default since round 2 (0 = first version)
-    if (g_ln2) cudaFuncSetAttribute(layernorm_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (g_ln2) {
+      cudaFuncSetAttribute(layernorm_kernel2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(layernorm_kernel2<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    }
   }
-  if (g_ln2) launch_k(layernorm_kernel2, dim3(grid), dim3(256), smem, st, a);
+  static int g_ln_warps = -1;                             // PIPER_B200_LN_WARPS: 8 / 24 warps per CTA (default: by problem size)
+  if (g_ln_warps < 0) {
+    const char* e = std::getenv("PIPER_B200_LN_WARPS");
+    g_ln_warps = e ? std::atoi(e) : 0;
+  }
+  // 24 warps (one batch of loads per pass) shorten a latency-bound launch; with several CTAs per SM already resident the
+  // 8-warp form has the same loads in flight and less barrier traffic (measured: batch 1 prefers 24, batch 32 prefers 8)
+  const bool wide = g_ln_warps ? g_ln_warps == 24 : (long long)grid.x * B <= 148;
+  if (g_ln2 && a.C >= 96 && wide) launch_k(layernorm_kernel2<24>, dim3(grid), dim3(24 * 32), smem, st, a);
+  else if (g_ln2) launch_k(layernorm_kernel2<8>, dim3(grid), dim3(256), smem, st, a);
   else launch_k(layernorm_kernel, dim3(grid), dim3(256), smem, st, a);
   count_launch();
 }

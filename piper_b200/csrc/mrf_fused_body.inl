@@ -29,8 +29,12 @@ constexpr int F_OFF_POST = F_OFF_BIAS + MRF_MAX_CHAINS * MRF_MAX_STEPS * F_C * 4
 constexpr int F_POST_MAXK = 7;
 constexpr int F_SMEM = F_OFF_POST + F_C * 8 * 4;
 static_assert(F_SMEM <= 227 * 1024, "fused MRF stage does not fit shared memory");
-constexpr int F_CONV_WARP0 = 3, F_EPI_WARP0 = 5, F_CONV_THREADS = 64, F_EPI_THREADS = 256;
-constexpr int F_THREADS = 13 * 32;        // 416 threads
+// 16 epilogue warps: two per (TMEM lane quadrant, 128-row tile), each owning 16 of the 32 channels of its row.  With 8 warps
+// (one thread = one row x 32 channels) the epilogue executed ~3000 instructions per row per tile and was the kernel's
+// bottleneck at 38 % issue utilisation (tensor pipe 24 % active): twice the warps = twice the latency hiding.
+constexpr int F_CONV_WARP0 = 3, F_EPI_WARP0 = 5, F_CONV_THREADS = 64, F_EPI_THREADS = 512;
+constexpr int F_HC = F_C / 2;             // channels per epilogue thread
+constexpr int F_THREADS = 21 * 32;        // 672 threads
 constexpr uint32_t F_TMEM_CARRIER = 256;
 
 template <class Mbar>
@@ -243,12 +247,13 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
       ++ti;
     }
   } else {
-    // ---------------------------------------------------------------------- epilogue: one position per thread
-    const int ew = warp - F_EPI_WARP0;                 // 0..7 (any four consecutive warps cover the four lane quadrants)
-    const int q = warp & 3, m = ew >> 2;               // TMEM lane quadrant is fixed by warp id % 4; m = 128-row tile
+    // ---------------------------------------------------------------------- epilogue: one (position, channel half) per thread
+    const int ew = warp - F_EPI_WARP0;                 // 0..15 (any four consecutive warps cover the four lane quadrants)
+    const int q = warp & 3, m = (ew >> 2) & 1, hc = ew >> 3;   // TMEM lane quadrant (fixed by warp id % 4), 128-row tile, channel half
     const int r = m * 128 + q * 32 + lane;
+    const int c0 = hc * F_HC;                          // first channel of this thread
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const float inv_n = 1.f / (float)n_chains;          // xs / num_kernels as a multiplication (<= 1 ulp; 32 divisions per row saved)
+    const float inv_n = 1.f / (float)n_chains;          // xs / num_kernels as a multiplication (<= 1 ulp; the divisions were 6 % of the kernel)
     uint32_t g_it = 0;
     for (int tile = block; tile < total; tile += grid) {
       int b, t0, L;
@@ -257,10 +262,10 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
       const int pos = p0 + r;
       const bool inside = pos >= 0 && pos < L;
       const int t_lo = p0 - F_G0;
-      const float* xrow = xs + (t_lo - (t_lo & ~3)) + F_G0 + r;           // this position in the staged input
-      float sum[F_C];
+      const float* xrow = xs + (t_lo - (t_lo & ~3)) + F_G0 + r + c0 * F_XS;   // this position, first own channel, in the staged input
+      float sum[F_HC];
 #pragma unroll
-      for (int i = 0; i < F_C; ++i) sum[i] = 0.f;
+      for (int i = 0; i < F_HC; ++i) sum[i] = 0.f;
       for (int s = 0; s < n_steps; ++s) {
         const bool closes = (s % pair) == pair - 1;                      // this conv ends a residual unit
         const bool last = s == n_steps - 1;
@@ -268,68 +273,66 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
           const uint32_t slot = g_it & 1;
           P::mbar_wait(cx, &bar.acc_full[slot], (g_it >> 1) & 1);
           P::fence_tc_after();
-          const uint32_t tb = tmem_d + lane_addr + slot * 128u + (uint32_t)m * 64u;
-          float v[F_C];
+          const uint32_t tb = tmem_d + lane_addr + slot * 128u + (uint32_t)m * 64u + (uint32_t)c0;
+          float v[F_HC];
           {
-            float p[16], qv[16];
-            P::tmem_ld16(cx, tb, p);
-            P::tmem_ld16(cx, tb + 32u, qv);
+            float qv[16];
+            P::tmem_ld16(cx, tb, v);                                     // main
+            P::tmem_ld16(cx, tb + 32u, qv);                              // correction (hi*lo + lo*hi)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = p[i] + qv[i];
-            P::tmem_ld16(cx, tb + 16u, p);
-            P::tmem_ld16(cx, tb + 48u, qv);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[16 + i] = p[i] + qv[i];
+            for (int i = 0; i < 16; ++i) v[i] += qv[i];
           }
           P::fence_tc_before();
           P::mbar_arrive(cx, &bar.acc_empty[slot]);
-          const float* bs = bias_s + (s * n_chains + c) * F_C;
+          const float* bs = bias_s + (s * n_chains + c) * F_C + c0;
 #pragma unroll
-          for (int i = 0; i < F_C; ++i) v[i] += bs[i];
-          const uint32_t carrier = tmem_d + lane_addr + F_TMEM_CARRIER + (uint32_t)c * 64u + (uint32_t)m * 32u;
+          for (int i = 0; i < F_HC; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+          const uint32_t carrier = tmem_d + lane_addr + F_TMEM_CARRIER + (uint32_t)c * 64u + (uint32_t)m * 32u + (uint32_t)c0;
           if (closes) {
             if (s == pair - 1) {                                         // residual = the stage input
 #pragma unroll
-              for (int i = 0; i < F_C; ++i) v[i] += xrow[i * F_XS];
+              for (int i = 0; i < F_HC; ++i) v[i] += xrow[i * F_XS];
             } else {                                                     // residual = the value parked by the last unit
               float p[16];
               P::tmem_ld16(cx, carrier, p);
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] += p[i];
-              P::tmem_ld16(cx, carrier + 16u, p);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[16 + i] += p[i];
             }
           }
           if (s == pair - 1 && c == n_chains - 1) P::mbar_arrive(cx, &bar.raw_free);   // last read of the staged input
           if (last) {
 #pragma unroll
-            for (int i = 0; i < F_C; ++i) sum[i] += v[i];
+            for (int i = 0; i < F_HC; ++i) sum[i] += v[i];
             if (c == n_chains - 1) {
               const bool stored = r >= a.hv && r < a.hv + a.to && pos < L;
               if (a.post_w == nullptr) {
                 if (stored) {
-                  float* yb = a.y.p + (long long)b * a.y.bs + pos;
+                  float* yb = a.y.p + (long long)b * a.y.bs + (long long)c0 * a.y.cs + pos;
 #pragma unroll
-                  for (int i = 0; i < F_C; ++i) yb[(long long)i * a.y.cs] = sum[i] * inv_n;
+                  for (int i = 0; i < F_HC; ++i) yb[(long long)i * a.y.cs] = sum[i] * inv_n;
                 }
               } else {
                 // Fused generator tail (models.py:364-366): the stage output never goes to HBM.  y -> leaky-relu, zero outside
                 // the utterance (conv_post pads its own input) -> the payload rows of chain 0's operand buffer, free until the
                 // next tile's first epilogue and never its zero guard rows: 8 blocks [256 rows][4 channels] of 16-byte rows.
+                // Each thread parks its 16 channels (4 blocks); the channel-half-0 thread of a row then sums all 32.
 #pragma unroll
-                for (int bi = 0; bi < F_C / 4; ++bi) {
+                for (int bj = 0; bj < F_HC / 4; ++bj) {
+                  const int bi = hc * (F_HC / 4) + bj;
                   float w4[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const float yv = sum[bi * 4 + e] * inv_n;
+                    const float yv = sum[bj * 4 + e] * inv_n;
                     w4[e] = inside ? fmaxf(yv, yv * a.post_slope) : 0.f;
                   }
                   uint8_t* blk = AC + (bi < 4 ? bi * F_RA * 16 : F_AC_PART + (bi - 4) * F_RA * 16) + F_GA * 16;
                   *reinterpret_cast<float4*>(blk + r * 16) = make_float4(w4[0], w4[1], w4[2], w4[3]);
                 }
                 P::bar_sync(cx, 1, F_EPI_THREADS);
-                if (stored) {
+                if (stored && hc == 0) {
                   const int half_k = (a.post_k - 1) / 2;
                   float acc = 0.f;
                   for (int j = 0; j < a.post_k; ++j) {
@@ -350,15 +353,15 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
           } else {
             if (closes) {
               P::tmem_st16(cx, carrier, v);
-              P::tmem_st16(cx, carrier + 16u, v + 16);
               P::tmem_wait_st();
             }
-            // operand of this chain's next conv: lrelu, zero outside the utterance (every conv pads its own input)
-            uint8_t* hi = AC + c * 2 * F_AC_PART + (F_GA + r) * 16;
+            // operand of this chain's next conv: lrelu, zero outside the utterance (every conv pads its own input);
+            // this thread's 16 channels are operand groups 2 hc and 2 hc + 1
+            uint8_t* hi = AC + c * 2 * F_AC_PART + (F_GA + r) * 16 + (2 * hc) * F_RA * 16;
             if (inside) {
               const float slope = a.slope;                   // 0 < slope < 1: leaky_relu(x) = max(x, slope x)
 #pragma unroll
-              for (int g = 0; g < F_C / 8; ++g) {
+              for (int g = 0; g < F_HC / 8; ++g) {
                 float w[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) w[e] = fmaxf(v[g * 8 + e], v[g * 8 + e] * slope);
@@ -366,7 +369,7 @@ MRF_FN void mrf_fused_body(const MrfFusedArgs& a, typename P::Ctx& cx, uint8_t* 
               }
             } else {
 #pragma unroll
-              for (int g = 0; g < F_C / 8; ++g) {
+              for (int g = 0; g < F_HC / 8; ++g) {
                 *reinterpret_cast<uint4*>(hi + g * F_RA * 16) = make_uint4(0u, 0u, 0u, 0u);
                 *reinterpret_cast<uint4*>(hi + F_AC_PART + g * F_RA * 16) = make_uint4(0u, 0u, 0u, 0u);
               }
