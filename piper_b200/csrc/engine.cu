@@ -178,7 +178,21 @@ const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a) {
       g_f16 = (e ? std::string(e) == "f16" : true) ? 1 : 0;      // default fp16x3 (PIPER_B200_V2_PREC=std: bf16x3 generator, tf32x3 elsewhere)
     }
     const int prec = g_f16 ? 2 : (w.plan.tf32 ? 1 : 0);
-    if (conv2_plan(a.ci, a.rows, a.k, a.dil, prec, w.plan.tf32 ? 2 : 1, l)) {
+    static int g_chains = -1;                            // PIPER_B200_V2_CHAINS: K-chains of the fp32-grade families (default 2)
+    if (g_chains < 0) {
+      const char* e = std::getenv("PIPER_B200_V2_CHAINS");
+      g_chains = e ? std::max(1, std::min(2, std::atoi(e))) : 2;
+    }
+    // The tensor core adds into its fp32 accumulator with truncation, an error that grows with the number of accumulation
+    // steps: the fp32-grade families cut LONG reductions into two K-chains.  A short one (1x1 convs:
+    // C_in / 16 = 12 steps) gains nothing from that, and a single chain frees TMEM for 128-row output tiles.
+    static int g_chain_k = -1;                           // PIPER_B200_V2_CHAIN_K: reductions shorter than this use one chain
+    if (g_chain_k < 0) {
+      const char* e = std::getenv("PIPER_B200_V2_CHAIN_K");
+      g_chain_k = e ? std::atoi(e) : 400;               // measured: +1.6 % on config 3; real-voice error 2.8e-4 -> <= 3.6e-4
+    }
+    const int chains = (w.plan.tf32 && a.ci * a.k >= g_chain_k) ? g_chains : 1;
+    if (conv2_plan(a.ci, a.rows, a.k, a.dil, prec, chains, l)) {
       std::vector<uint8_t> host(l.w_bytes);
       conv2_pack(voice_.blob.data() + w.w, a.ci, a.k, a.rows_p, l, host.data());
       CUDA_CHECK(cudaMalloc(&l.w_dev, l.w_bytes));
