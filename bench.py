@@ -451,20 +451,26 @@ def run_engine(args):
     value = total_samples / (dev_ms_max * 1e-3)
 
     # ---------------- end-to-end leg: the public call with HOST buffers, H2D + D2H inside the timed region
-    for _ in range(3):
-        voice.synthesize_batch(ids_list, SCALES, seed=4242, copy=False)
-    D.barrier()
-    t0 = time.perf_counter()
-    e2e_samples = 0
-    for _ in range(steps):
-        flat, counts, _ = voice.synthesize_batch(ids_list, SCALES, seed=4242, copy=False)
-        e2e_samples += int(counts.sum())
-    D.barrier()
-    e2e_s = D.max(time.perf_counter() - t0)
-    e2e_value = D.sum(float(e2e_samples)) / e2e_s
+    # The reference-facing call returns what piper::synthesize returns: peak-normalised int16 samples (piper.cpp:411-431),
+    # here produced on the GPU (pb200_synthesize_int16), so 2 bytes per sample cross PCIe.  The fp32 variant of the same
+    # call (pb200_synthesize_batch, 4 bytes per sample) is timed beside it.
+    def e2e_leg(call, bytes_per_sample):
+        for _ in range(3):
+            call()
+        D.barrier()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(steps):
+            flat, counts, _ = call()
+            n += int(counts.sum())
+        D.barrier()
+        secs = D.max(time.perf_counter() - t0)
+        return D.sum(float(n)) / secs, secs, n // steps * bytes_per_sample
+    e2e_value, e2e_s, d2h_audio = e2e_leg(lambda: voice.synthesize_int16(ids_list, SCALES, seed=4242, copy=False), 2)
+    e2e_f32, e2e_f32_s, d2h_f32 = e2e_leg(lambda: voice.synthesize_batch(ids_list, SCALES, seed=4242, copy=False), 4)
     tp = (259 + 3) // 4 * 4
-    h2d = B * tp * 4 + B * 4 + B * 8            # ids (int32, padded pitch) + lengths + output offsets
-    d2h = e2e_samples // steps * 4 + B * 4      # fp32 audio + the per-item output lengths
+    h2d = B * tp * 4 + B * 4 + B * 8 + 24       # ids (int32, padded pitch) + lengths + output offsets + call parameters
+    d2h = d2h_audio + B * 4                     # int16 audio + the per-item output lengths
 
     # ---------------- rooflines per conv family: CUDA events around every launch (profile mode), pipe-correct peaks
     peaks = measured_peaks()
@@ -501,7 +507,10 @@ def run_engine(args):
             "wall_ms_per_step": wall_ms / steps,
             "stage_ms": dict(zip(STAGES, stage_ms)),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / steps * 1e3},
+                    "ms_per_step": e2e_s / steps * 1e3,
+                    "call": "pb200_synthesize_int16: host ids in, host int16 audio out (piper::synthesize's output, piper.cpp:411-431)",
+                    "fp32_output": {"value": e2e_f32, "ms_per_step": e2e_f32_s / steps * 1e3, "d2h_bytes_per_step": d2h_f32 + B * 4,
+                                    "call": "pb200_synthesize_batch: host fp32 audio out"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,

@@ -127,7 +127,7 @@ class Voice:
         offs = np.concatenate([[0], np.cumsum(counts)])
         return [flat[offs[b]:offs[b + 1]].copy() for b in range(B)], sec.value
 
-    def synthesize_int16(self, ids_list, scales=(0.667, 1.0, 0.8), eps_dp=None, eps_z=None, seed=0):
+    def synthesize_int16(self, ids_list, scales=(0.667, 1.0, 0.8), eps_dp=None, eps_z=None, seed=0, copy=True):
         cat, lens = self._ids(ids_list)
         B = len(lens)
         sc = np.asarray(scales, np.float32)
@@ -140,6 +140,8 @@ class Voice:
             C.byref(n), C.byref(audio), ns, C.byref(sec)))
         counts = np.asarray(list(ns), np.int64)
         flat = np.ctypeslib.as_array(audio, shape=(int(counts.sum()),))
+        if not copy:
+            return flat, counts, sec.value
         offs = np.concatenate([[0], np.cumsum(counts)])
         return [flat[offs[b]:offs[b + 1]].copy() for b in range(B)], sec.value
 
