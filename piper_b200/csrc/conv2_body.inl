@@ -117,15 +117,22 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   P::pdl_sync();                                       // programmatic dependent launch: the prologue above overlapped the previous grid
 
   // tile id -> (output-row tile, item, time block); every role walks the same list and skips the same tiles
+  const int flat_tg = a.flat_tg;                       // > 0: tiles on the concatenated time axis (see MmaConvArgs)
   auto decode = [&](int tile, int& nt, int& b, int& t0, int& L, int& Lq) {
     const int tb = tile % tpi;
     const int rest = tile / tpi;
     b = rest % a.batch;
     nt = rest / a.batch;
     t0 = tb * MT;
-    L = a.len[b] * a.len_scale;
+    L = flat_tg ? a.flat_n * flat_tg : a.len[b] * a.len_scale;
     Lq = L + a.q_extra;
     return t0 < Lq;
+  };
+  // flat mode: is concatenated position g inside an utterance, and whose?
+  auto flat_live = [&](int g, int& item) -> bool {
+    if (g < 0) return false;
+    item = g / flat_tg;
+    return item < a.flat_n && g - item * flat_tg < a.len[item] * a.len_scale;
   };
 
   if (TM && warp == 0) {
@@ -331,7 +338,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         for (int item = ctid; item < R * S; item += C2_CONV_THREADS) {
           const int sg = item / R, r = item - sg * R;
           const int t = t_lo + r;
-          const bool live = t >= 0 && t < L;                            // outside the utterance: zeros, whatever the
+          int item_unused = 0;
+          const bool live = flat_tg ? flat_live(t, item_unused) : (t >= 0 && t < L);   // outside the utterance: zeros, whatever the
           const int bx = (TM && off + r >= Wb) ? 1 : 0;                  // (unwritten / stale) smem holds
           const size_t g_src = (size_t)E * Wb, g_dst = (size_t)R * 16;
           const float* src = raw + (size_t)bx * KC * Wb + (r - bx * Wb) + (size_t)(sg * GS) * g_src;   // (raw points at column `off`)
@@ -415,7 +423,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       auto aux_issue = [&](int wi, float (&rv)[16], float (&ov)[16]) {
         const int mh = wi / my_chunks, c = half + 2 * (wi - mh * my_chunks);
         const int t = t0 + mh * 128 + q * 32 + lane;
-        if (t >= Lq) return;
+        int item = b;
+        if (flat_tg ? !flat_live(t, item) : t >= Lq) return;
         const int row0 = n0 + c * 16, kind = aux_kind(row0);
         if (kind & 1) {
 #pragma unroll
@@ -450,7 +459,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
           P::fence_tc_before();
           P::mbar_arrive(cx, &bar.t_empty[ts]);
         }
-        if (t < Lq) {
+        int item = b;
+        if (flat_tg ? flat_live(t, item) : t < Lq) {
           const int row0 = n0 + c * 16;
           if (a.bias) {
             if (bias_vec) {                                  // 16-byte aligned bias vector: four 128-bit loads
@@ -466,7 +476,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
           }
           if (a.bias_item) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias_item + (long long)b * a.bias_item_stride + row0 + i);
+            for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias_item + (long long)item * a.bias_item_stride + row0 + i);
           }
           if (epi == EPI_GATE) {
 #pragma unroll

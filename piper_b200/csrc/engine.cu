@@ -51,6 +51,24 @@ void PinnedBuf::release() {
 
 static int round4(int v) { return (v + 3) & ~3; }
 
+// Flat layout (PIPER_B200_FLAT, default on): phoneme- and frame-rate activations are stored [channel][item][slot] instead of
+// [item][channel][pitch] - the same View struct with bs = slot and cs = items * slot - so that the conv kernel can cut its
+// tiles on the concatenated time axis (T = 259 costs 3 x 128-row tiles per utterance, but 32 utterances x 264 = 66 tiles
+// instead of 96).  The slot is the pitch plus a gap >= the largest one-sided conv halo, so a window never reaches live
+// data of a neighbouring utterance.
+bool Engine::flat_on() {
+  if (flat_ < 0) {
+    const char* e = std::getenv("PIPER_B200_FLAT");
+    flat_ = e ? (std::atoi(e) != 0) : 1;
+  }
+  return flat_ != 0;
+}
+int Engine::slot(int max_len) { return round4(max_len) + (flat_on() ? 4 : 0); }
+View Engine::fview(float* p, int C, int pitch) const {
+  if (flat_ > 0) return View{p, (long long)pitch, B_ * pitch};
+  return View{p, (long long)C * pitch, pitch};
+}
+
 Engine::Engine(const std::string& onnx_path, int device, bool upload) : device_(device) {
   load_voice_file(onnx_path, voice_);
   int n_dev = 0;
@@ -135,6 +153,16 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
       if (const Conv2Layer* l = v2_layer(*w, a)) {
         MmaConvArgs m2 = m;
         m2.w = static_cast<const uint8_t*>(l->w_dev);
+        // flat layout views (bs = slot < cs): one launch item of length items x slot, tiles on the concatenated time axis
+        auto same_layout = [&](const View& v) { return v.p == nullptr || (v.bs == a.x.bs && v.cs == a.x.cs); };
+        const bool flat = flat_ > 0 && a.len_scale == 1 && a.q_extra == 0 && a.x.bs < (long long)a.x.cs && a.x.bs * B_ == a.x.cs &&
+                          same_layout(a.y) && same_layout(a.y2) && same_layout(a.r);   // (conv_pre writes an item-major generator buffer)
+        if (flat) {
+          m2.flat_tg = int(a.x.bs);
+          m2.flat_n = B_;
+          if (launch_conv2(m2, *l, 1, B_ * int(a.x.bs), stream_)) return;
+          m2.flat_tg = m2.flat_n = 0;
+        }
         if (launch_conv2(m2, *l, B_, max_len, stream_)) return;
       }
     }
@@ -253,7 +281,7 @@ std::string Engine::profile_launches_json() {
 
 void Engine::ensure_front(int B, int Tmax) {
   const VoiceSpec& s = voice_.spec;
-  const int Tp = round4(Tmax);
+  const int Tp = slot(Tmax);
   const size_t n = size_t(B) * Tp;
   ids_d_.ensure(n * 4); len_d_.ensure(size_t(B) * 4); ylen_d_.ensure(size_t(B) * 4);
   cum_d_.ensure(n * 4); logw_d_.ensure(n * 4); off_d_.ensure(size_t(B) * 8); epsoff_d_.ensure(size_t(B) * 8);
@@ -266,7 +294,7 @@ void Engine::ensure_front(int B, int Tmax) {
 
 void Engine::ensure_back(int B, int Fmax) {
   const VoiceSpec& s = voice_.spec;
-  const int Fp = round4(Fmax);
+  const int Fp = slot(Fmax);
   const size_t n = size_t(B) * Fp;
   z_.ensure(n * s.inter * 4); fh_.ensure(n * s.hidden * 4); facts_.ensure(n * s.hidden * 4); fout_.ensure(n * s.hidden * 4);
   size_t per_frame = size_t(s.up_initial);
@@ -296,7 +324,7 @@ void Engine::upload_inputs(const int64_t* ids_concat, const int64_t* lens, int B
     total += lens[b];
   }
   Tmax = bucket_ids(Tmax);                 // shape bucket (identity unless CUDA graphs are on): every kernel masks by len[b]
-  B_ = B; Tmax_ = Tmax; Tp_ = round4(Tmax);
+  B_ = B; Tmax_ = Tmax; Tp_ = slot(Tmax);
   sum_T_ = double(total);
   for (int i = 0; i < 3; ++i) scales_[i] = scales[i];
   seed_ = noise.seed;
@@ -413,14 +441,16 @@ void Engine::dds(const DDSW& d, View h, View u, View v, int C) {
 
 void Engine::save_tap(const std::string& name, View v, int C, const int* len_host, int scale) {
   CUDA_CHECK(cudaStreamSynchronize(stream_));
+  // host copy is always [item][channel][pitch]; the device view may be that or the flat layout [channel][item][slot]
+  const int pitch = v.bs < (long long)v.cs ? int(v.bs) : v.cs;
   HostTap t;
-  t.B = B_; t.C = C; t.pitch = v.cs;
+  t.B = B_; t.C = C; t.pitch = pitch;
   t.len.resize(B_);
   for (int b = 0; b < B_; ++b) t.len[b] = len_host[b] * scale;
-  t.data.resize(size_t(B_) * C * v.cs);
+  t.data.resize(size_t(B_) * C * pitch);
   for (int b = 0; b < B_; ++b)
-    CUDA_CHECK(cudaMemcpy(t.data.data() + size_t(b) * C * v.cs, v.p + (long long)b * v.bs, size_t(C) * v.cs * 4,
-                          cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy2D(t.data.data() + size_t(b) * C * pitch, size_t(pitch) * 4, v.p + (long long)b * v.bs, size_t(v.cs) * 4,
+                            size_t(pitch) * 4, size_t(C), cudaMemcpyDeviceToHost));
   taps_[name] = std::move(t);
 }
 
@@ -534,9 +564,9 @@ void Engine::enqueue_front() {
   const int H = s.hidden, I = s.inter, Tp = Tp_, B = B_, T = Tmax_;
   const int* len = len_d_.as<int>();
   const CallParams* cp = params_d_.as<CallParams>();
-  View x = view(x_.as<float>(), H, Tp), t1 = view(t1_.as<float>(), H, Tp), qkv = view(qkv_.as<float>(), 3 * H, Tp),
-       att = view(att_.as<float>(), H, Tp), ffn = view(ffn_.as<float>(), s.filter, Tp),
-       stats = view(stats_.as<float>(), 2 * I, Tp);
+  View x = fview(x_.as<float>(), H, Tp), t1 = fview(t1_.as<float>(), H, Tp), qkv = fview(qkv_.as<float>(), 3 * H, Tp),
+       att = fview(att_.as<float>(), H, Tp), ffn = fview(ffn_.as<float>(), s.filter, Tp),
+       stats = fview(stats_.as<float>(), 2 * I, Tp);
   // ---- text encoder (models.py:198-209)
   launch_embed(ids_d_.as<int>(), Tp, W(voice_.emb), H, std::sqrt(float(H)), x, len, B, T, stream_);
   for (const EncLayerW& e : voice_.enc) {
@@ -570,10 +600,10 @@ void Engine::enqueue_front() {
     save_tap("stats", stats, 2 * I, len_h_.data(), 1);
   }
   // ---- stochastic duration predictor, reverse (models.py:63-70,108-117)
-  View g = view(g_.as<float>(), H, Tp), h = view(h_.as<float>(), H, Tp), u = view(u_.as<float>(), H, Tp),
-       v = view(v_.as<float>(), H, Tp), z2 = view(z2_.as<float>(), 2, Tp);
+  View g = fview(g_.as<float>(), H, Tp), h = fview(h_.as<float>(), H, Tp), u = fview(u_.as<float>(), H, Tp),
+       v = fview(v_.as<float>(), H, Tp), z2 = fview(z2_.as<float>(), 2, Tp);
   const int pr_rows = 3 * s.spline_bins - 1;
-  View pr = view(pr_.as<float>(), pr_rows, Tp);
+  View pr = fview(pr_.as<float>(), pr_rows, Tp);
   {
     ConvArgs c = conv_args(voice_.dp_pre, x, len, 1);
     c.y = h;
@@ -625,7 +655,7 @@ void Engine::plan_back() {
   sum_F_ = double(off) / s.hop;
   Fmax = bucket_frames(Fmax);              // shape bucket (identity unless CUDA graphs are on)
   Fmax_ = Fmax;
-  Fp_ = round4(Fmax);
+  Fp_ = slot(Fmax);
   ensure_back(B_, Fmax);
   // tight audio layout: item b starts at off[b]
   audio_d_.ensure(size_t(std::max<long long>(off, 1)) * 4);
@@ -638,7 +668,7 @@ void Engine::run_generator() {
   const VoiceSpec& s = voice_.spec;
   const int B = B_, Fp = Fp_, F = Fmax_;
   const int* ylen = ylen_d_.as<int>();
-  View z = view(z_.as<float>(), s.inter, Fp);
+  View z = fview(z_.as<float>(), s.inter, Fp);
   int ch = s.up_initial;
   View S = view(gs_.as<float>(), ch, Fp);
   {
@@ -784,9 +814,9 @@ void Engine::run_flow() {
   const VoiceSpec& s = voice_.spec;
   const int B = B_, H = s.hidden, I = s.inter, Fp = Fp_, F = Fmax_;
   const int* ylen = ylen_d_.as<int>();
-  View z = view(z_.as<float>(), I, Fp);
+  View z = fview(z_.as<float>(), I, Fp);
   // ---- flow, reverse (models.py:251-253; modules.py:447-466,184-209)
-  View fh = view(fh_.as<float>(), H, Fp), acts = view(facts_.as<float>(), H, Fp), out = view(fout_.as<float>(), H, Fp);
+  View fh = fview(fh_.as<float>(), H, Fp), acts = fview(facts_.as<float>(), H, Fp), out = fview(fout_.as<float>(), H, Fp);
   const int half = I / 2;
   for (const CouplingW& cw : voice_.flow) {
     View x0 = cw.flipped ? z.offset_channels(half) : z;
@@ -819,8 +849,8 @@ void Engine::enqueue_back() {
   const int B = B_, I = s.inter, Fp = Fp_, F = Fmax_;
   const int* ylen = ylen_d_.as<int>();
   const int* len = len_d_.as<int>();
-  View stats = view(stats_.as<float>(), 2 * I, Tp_);
-  View z = view(z_.as<float>(), I, Fp);
+  View stats = fview(stats_.as<float>(), 2 * I, Tp_);
+  View z = fview(z_.as<float>(), I, Fp);
   launch_expand(stats, I, cum_d_.as<int>(), Tp_, len, ylen, z, have_eps_z_ ? epsz_d_.as<float>() : nullptr,
                 (long long)I * z_stride_, int(z_stride_), params_d_.as<CallParams>(), B, F, stream_);
   if (debug_) save_tap("z_p", z, I, ylen_h_.data(), 1);
@@ -928,14 +958,14 @@ const float* Engine::encode(const int64_t* ids, int64_t n_ids, const float scale
   run_front();
   plan_back();
   const VoiceSpec& s = voice_.spec;
-  View stats = view(stats_.as<float>(), 2 * s.inter, Tp_);
-  View z = view(z_.as<float>(), s.inter, Fp_);
+  View stats = fview(stats_.as<float>(), 2 * s.inter, Tp_);
+  View z = fview(z_.as<float>(), s.inter, Fp_);
   launch_expand(stats, s.inter, cum_d_.as<int>(), Tp_, len_d_.as<int>(), ylen_d_.as<int>(), z,
                 have_eps_z_ ? epsz_d_.as<float>() : nullptr, (long long)s.inter * z_stride_, int(z_stride_),
                 params_d_.as<CallParams>(), 1, Fmax_, stream_);
   const int F = ylen_h_[0];
   audio_pin_.ensure(size_t(s.inter) * F * 4);
-  CUDA_CHECK(cudaMemcpy2DAsync(audio_pin_.p, size_t(F) * 4, z.p, size_t(Fp_) * 4, size_t(F) * 4, size_t(s.inter),
+  CUDA_CHECK(cudaMemcpy2DAsync(audio_pin_.p, size_t(F) * 4, z.p, size_t(z.cs) * 4, size_t(F) * 4, size_t(s.inter),
                                cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   if (frames) *frames = F;
@@ -949,6 +979,12 @@ const float* Engine::vocode(const float* z, int B, int64_t frames, bool with_flo
   if (frames > max_frames_) throw std::runtime_error("vocode: too many frames");
   const auto t0 = std::chrono::steady_clock::now();
   CUDA_CHECK(cudaSetDevice(device_));
+  // Generator only: nothing here cuts tiles on a concatenated axis, and the host tensor is item-major - keep the per-item
+  // layout so the upload stays ONE 2-D copy.  (With the flow - the streaming decoder - the flat layout is used; for B = 1
+  // the two coincide.)
+  flat_on();
+  struct FlatGuard { int& f; int saved; ~FlatGuard() { f = saved; } } flat_guard{flat_, flat_};
+  if (!with_flow) flat_ = 0;
   B_ = B; Tmax_ = 1; Tp_ = 4;
   ensure_front(B, 1);
   ylen_h_.assign(B, int(frames));
@@ -962,12 +998,21 @@ const float* Engine::vocode(const float* z, int B, int64_t frames, bool with_flo
   plan_back();
   upload_speakers(B);
   if (debug_) taps_.clear();
-  // z host [B][inter][frames] -> device [B][inter][Fp]
-  CUDA_CHECK(cudaMemcpy2DAsync(z_.p, size_t(Fp_) * 4, z, size_t(frames) * 4, size_t(frames) * 4, size_t(B) * s.inter,
-                               cudaMemcpyHostToDevice, stream_));
+  // z host [B][inter][frames] -> the device view (per item: [inter] rows of `frames` floats at the view's channel stride)
+  {
+    const View zv = fview(z_.as<float>(), s.inter, Fp_);
+    if (zv.bs == (long long)s.inter * zv.cs) {           // item-major device layout: one copy of B * inter rows
+      CUDA_CHECK(cudaMemcpy2DAsync(zv.p, size_t(zv.cs) * 4, z, size_t(frames) * 4, size_t(frames) * 4, size_t(B) * s.inter,
+                                   cudaMemcpyHostToDevice, stream_));
+    } else {
+      for (int b = 0; b < B; ++b)
+        CUDA_CHECK(cudaMemcpy2DAsync(zv.p + (long long)b * zv.bs, size_t(zv.cs) * 4, z + size_t(b) * s.inter * frames,
+                                     size_t(frames) * 4, size_t(frames) * 4, size_t(s.inter), cudaMemcpyHostToDevice, stream_));
+    }
+  }
   {
     const unsigned long long key = (3ull << 60) | ((unsigned long long)B << 36) | ((unsigned long long)Fmax_ << 8) |
-                                   (unsigned long long)(mma_mask_ & 0x7f) | (with_flow ? 0x80ull : 0ull);
+                                   (unsigned long long)(mma_mask_ & 0x7f) | (with_flow ? 0x80ull : 0ull);   // (layout follows with_flow)
     run_graphed(key, [this, with_flow] {
       if (with_flow) run_flow();             // decoder half of the reference's streaming split (flow + generator)
       record(4);

@@ -126,6 +126,11 @@ class Engine {
   void save_tap(const std::string& name, View v, int C, const int* len_host, int scale);
 
   View view(float* p, int C, int pitch) const { return View{p, (long long)C * pitch, pitch}; }
+  // phoneme- / frame-rate activations: [item][channel][pitch], or the flat layout [channel][item][slot] (engine.cu: flat_on)
+  View fview(float* p, int C, int pitch) const;
+  bool flat_on();
+  int slot(int max_len);
+  int flat_ = -1;
   const float* W(int64_t off) const { return off >= 0 ? weights_.as<float>() + off : nullptr; }
   ConvArgs conv_args(const ConvW& c, View x, const int* len, int len_scale) const;
   void dds(const DDSW& d, View h, View u, View v, int C);

@@ -87,6 +87,10 @@ struct MmaConvArgs {
   int raw_stride = 0, tiles_per_item = 0, total_tiles = 0, batch = 0, t_slots = 1, tpu = 1;   // persistent kernel
   int tm_boxes = 0;              // conv2 tensor-map mode: boxes per channel chunk (0 = per-row bulk copies)
   int mma3 = 0;                  // conv2: three instructions per k-step on exactly matching accumulator regions (see conv2_body.inl)
+  // conv2 flat mode: the views are laid out [channel][item][slot of flat_tg floats] (View.bs = flat_tg, View.cs = items *
+  // flat_tg), the launch sees ONE item of length flat_n * flat_tg and tiles are cut on that concatenated time axis; a row
+  // g belongs to item g / flat_tg at time g % flat_tg and is live while that is < len[item] * len_scale.
+  int flat_tg = 0, flat_n = 0;
   unsigned long long* prof = nullptr;   // optional: per-role stall cycle counters (tools/conv_diag.py)
 };
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);

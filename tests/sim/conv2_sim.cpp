@@ -56,10 +56,17 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
     a.ci = ci; a.rows = rows; a.k = k; a.dil = dil; a.pad = desc[4]; a.q_extra = desc[5];
     a.pre = desc[6]; a.slope = slope; a.epi = desc[7]; a.split = desc[8]; a.first = desc[9];
     a.up = desc[10]; a.up_pad = desc[11]; a.mrf = desc[12]; a.mrf_n = desc[13];
+    const bool flat = (desc[25] & 16) != 0;              // opts bit 4: flat mode - the caller passes [C][B][Tg] tensors (cs = B * Tg)
+    if (flat) {
+      a.flat_tg = desc[16] / B; a.flat_n = B;
+      a.x.bs = a.flat_tg; a.y.bs = desc[17] / B; a.y2.bs = desc[18] / B; a.r.bs = desc[19] / B;
+    }
+    const int launch_B = flat ? 1 : B;
+    if (flat) max_len = B * a.flat_tg;
     const bool tm = (desc[25] & 4) != 0;                 // opts bit 2: tensor-map TMA for the activation window
     a.mma3 = (desc[25] & 8) ? 1 : 0;                     // opts bit 3: three instructions per k-step on matching accumulator regions
     TmapDesc td;
-    int grid = conv2::fill_args(a, p, B, max_len, tm, &td);
+    int grid = conv2::fill_args(a, p, launch_B, max_len, tm, &td);
     if (desc[23] > 0) grid = std::min(grid, desc[23]);
     if (info) {
       info[0] = p.n_tile; info[1] = p.n_tiles; info[2] = p.mt; info[3] = p.kc; info[4] = p.t_slots; info[5] = a.chains;

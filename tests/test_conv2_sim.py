@@ -351,3 +351,58 @@ def test_tensor_map_conv_transpose_tail(sim):
         e = float((torch.from_numpy(y[b, :, :L * up]) - ref).abs().max())
         assert e <= 3e-4 * max(1.0, float(ref.abs().max())), (b, e, info)
         assert np.all(y[b, :, L * up:] == 7e7)
+
+
+@pytest.mark.parametrize("prec,ci,rows,k,dil,epi,lens", [(2, 192, 64, 1, 1, "RES", (259, 259, 259)),      # equal lengths: 3 x 264 = 792 rows -> 7 tiles instead of 9
+                                                          (2, 96, 192, 5, 1, "GATE", (131, 40, 259, 7)),   # halo across item boundaries, ragged
+                                                          (1, 64, 128, 3, 1, "RELU", (100, 1, 128)),
+                                                          (2, 192, 384, 1, 1, "WN", (70, 130))])
+def test_flat_mode_tiles_on_the_concatenated_time_axis(sim, prec, ci, rows, k, dil, epi, lens):
+    """opts bit 4: views laid out [channel][item][slot] and ONE launch item of length items x slot - a tile may cover the end
+    of one utterance and the start of the next; rows in the gaps are neither read as data nor written."""
+    B = len(lens)
+    Tg = ((max(lens) + 3) & ~3) + 4                          # slot = pitch + gap >= the largest one-sided halo
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((ci, B, Tg)).astype(np.float32) * 40.0      # stale data in the gaps
+    clean = []
+    for b, L in enumerate(lens):
+        v = rng.standard_normal((ci, L)).astype(np.float32)
+        x[:, b, :L] = v
+        clean.append(torch.from_numpy(v))
+    w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+    bias = rng.standard_normal(rows).astype(np.float32)
+    pad = (k - 1) // 2 * dil
+    C_y = rows // 2 if epi == "GATE" else (rows // 2 if epi == "WN" else rows)
+    split = rows // 2 if epi == "WN" else 0
+    y = np.full((C_y, B, Tg), 7e7, np.float32)
+    r = rng.standard_normal((C_y, B, Tg)).astype(np.float32)
+    y2 = rng.standard_normal((max(rows - split, 1), B, Tg)).astype(np.float32)
+    y2_0 = y2.copy()
+    if epi == "WN":
+        y[...] = r                                           # in-place residual stream (y == r in the engine)
+    lens_a = np.asarray(lens, np.int32)
+    desc = (C.c_int32 * 26)(ci, rows, k, dil, pad, 0, 1 if epi == "RELU" else 0, EPI[epi], split, 0, 1, 0, 0, 3, prec, 1,
+                           B * Tg, B * Tg, B * Tg, B * Tg, C_y, y2.shape[0], C_y, 2, 0, 16 | 4)
+    info = (C.c_int32 * 8)()
+    err = C.create_string_buffer(512)
+    rc = sim.conv2_sim_run(_fp(x), _fp(np.ascontiguousarray(w)), _fp(bias), None, 0, _fp(y), _fp(y2), _fp(y if epi == "WN" else r),
+                           lens_a.ctypes.data_as(C.POINTER(C.c_int32)), B, desc, C.c_float(0.1), int(lens_a.max()), info, err, len(err))
+    assert rc == 0, err.value.decode()
+    tol = (2e-5 if prec else 3e-4)
+    for b, L in enumerate(lens):
+        ref = _ref_conv(clean[b], w, bias, dil, pad, 1 if epi == "RELU" else 0, 0.1)
+        if epi == "RES":
+            want = ref + torch.from_numpy(r[:, b, :L])
+        elif epi == "RELU":
+            want = torch.relu(ref)
+        elif epi == "GATE":
+            want = torch.tanh(ref[0::2]) * torch.sigmoid(ref[1::2])
+        else:                                                # WN, not the first layer: residual rows in place, skip rows accumulate
+            want = torch.from_numpy(r[:, b, :L]) + ref[:split]
+            skip = torch.from_numpy(y2_0[:, b, :L]) + ref[split:]
+            assert float((torch.from_numpy(y2[:, b, :L]) - skip).abs().max()) <= tol * max(1.0, float(skip.abs().max())), (b, info[:])
+            assert np.array_equal(y2[:, b, L:], y2_0[:, b, L:]), "skip sum written in the gap"
+        e = float((torch.from_numpy(y[:, b, :L]) - want).abs().max())
+        assert e <= tol * max(1.0, float(want.abs().max())), (epi, b, e, list(info))
+        gap = y[:, b, L:]
+        assert np.all(gap == (r[:, b, L:] if epi == "WN" else 7e7)), "stored in the gap between utterances"
