@@ -150,7 +150,15 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   }
   auto go = [&] {
     if (mma && v2_) {                                  // experimental kernel first; it declines small launches
-      if (const Conv2Layer* l = v2_layer(*w, a)) {
+      const Conv2Layer* l = v2_layer(*w, a);
+      if (l && w->plan.tf32) {
+        // a launch of the throughput plan that would leave most SMs idle takes the latency plan instead (batch 1)
+        const long long rows = a.x.bs < (long long)a.x.cs ? (long long)B_ * a.x.bs : (long long)B_ * max_len;
+        const long long ctas = (rows + l->mt - 1) / l->mt * l->n_tiles;
+        if (ctas < 74)
+          if (const Conv2Layer* l1 = v2_layer(*w, a, 1)) l = l1;
+      }
+      if (l) {
         MmaConvArgs m2 = m;
         m2.w = static_cast<const uint8_t*>(l->w_dev);
         // flat layout views (bs = slot < cs): one launch item of length items x slot, tiles on the concatenated time axis
@@ -194,8 +202,10 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
   recs_.push_back(r);
 }
 
-const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a) {
-  auto it = v2_layers_.find(&w);
+// variant 0: the throughput plan (one K-chain for short reductions -> 128-row output tiles); variant 1: the latency plan for
+// launches that cannot fill the machine (two chains everywhere -> 64-row output tiles, i.e. more, lighter CTAs).
+const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a, int variant) {
+  auto it = v2_layers_.find({&w, variant});
   if (it == v2_layers_.end()) {
     Conv2Layer l;
     // precision: as the shipped path (bf16x3 generator, tf32x3 elsewhere) or, with PIPER_B200_V2_PREC=f16, fp16x3 for
@@ -219,7 +229,7 @@ const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a) {
       const char* e = std::getenv("PIPER_B200_V2_CHAIN_K");
       g_chain_k = e ? std::atoi(e) : 400;               // measured: +1.6 % on config 3; real-voice error 2.8e-4 -> <= 3.6e-4
     }
-    const int chains = (w.plan.tf32 && a.ci * a.k >= g_chain_k) ? g_chains : 1;
+    const int chains = (w.plan.tf32 && (variant == 1 || a.ci * a.k >= g_chain_k)) ? g_chains : 1;
     if (conv2_plan(a.ci, a.rows, a.k, a.dil, prec, chains, l)) {
       std::vector<uint8_t> host(l.w_bytes);
       conv2_pack(voice_.blob.data() + w.w, a.ci, a.k, a.rows_p, l, host.data());
@@ -230,7 +240,7 @@ const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a) {
       CUDA_CHECK(cudaMemcpyAsync(l.w_dev, host.data(), l.w_bytes, cudaMemcpyHostToDevice, stream_));
       CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
-    it = v2_layers_.emplace(&w, l).first;
+    it = v2_layers_.emplace(std::make_pair(&w, variant), l).first;
   }
   return it->second.w_dev ? &it->second : nullptr;
 }

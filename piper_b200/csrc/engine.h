@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <functional>
 #include <map>
+#include <utility>
 #include <memory>
 #include <string>
 #include <vector>
@@ -142,8 +143,8 @@ class Engine {
   DeviceBuf weights_, weights_mma_;
   // experimental second-generation conv kernel (PIPER_B200_V2=1, conv_mma2.cu): per-layer plan + stacked weights, lazily
   int v2_ = -1;
-  std::map<const ConvW*, Conv2Layer> v2_layers_;
-  const Conv2Layer* v2_layer(const ConvW& w, const ConvArgs& a);
+  std::map<std::pair<const ConvW*, int>, Conv2Layer> v2_layers_;      // (layer, variant): see v2_layer
+  const Conv2Layer* v2_layer(const ConvW& w, const ConvArgs& a, int variant = 0);
   // experimental fused MRF stage (mask bit 16, mrf_fused.cu): packed lazily on first use
   void prepare_mrf_fused();
   bool mrf_ready_ = false;
