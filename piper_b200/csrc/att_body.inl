@@ -43,7 +43,27 @@ struct Args {
   const float* rel_v = nullptr;           // [9][dk]
   const int* len = nullptr;
   int H = 0, dk = 0, n_heads = 0, q_tiles = 0;
+  int tm = 0;                             // 1: q / k / v windows by tensor-map TMA (tmq: box [dk][136], tmk: box [dk][72])
+  int flat = 0;                           // with tm: qkv is laid out [channel][item][slot] -> coordinates (t, item, channel)
 };
+
+// tensor-map descriptors of the qkv view for the two boxes (host side; shared with the CPU model)
+inline void att_tmaps(const Args& a, int B, TmapDesc& tq, TmapDesc& tk) {
+  for (TmapDesc* t : {&tq, &tk}) {
+    t->base = a.qkv.p;
+    if (a.flat) {                         // [3H][B][slot]: dims (t, item, channel)
+      t->dims[0] = int(a.qkv.bs); t->dims[1] = B; t->dims[2] = 3 * a.H;
+      t->stride1 = a.qkv.bs * 4; t->stride2 = (long long)a.qkv.cs * 4;
+      t->box[1] = 1; t->box[2] = a.dk;
+    } else {                              // [B][3H][pitch]: dims (t, channel, item)
+      t->dims[0] = a.qkv.cs; t->dims[1] = 3 * a.H; t->dims[2] = B;
+      t->stride1 = (long long)a.qkv.cs * 4; t->stride2 = a.qkv.bs * 4;
+      t->box[1] = a.dk; t->box[2] = 1;
+    }
+  }
+  tq.box[0] = A_QT + 8;
+  tk.box[0] = A_KB + 8;
+}
 
 // shared-memory map (bytes), G = dk / 8
 MRF_HD int off_raw(int) { return 0; }                                           // fp32 rows: q [dk][136] or k | v [2 dk][72]
@@ -82,7 +102,8 @@ MRF_FN void split8(uint8_t* hi_row, uint8_t* lo_row, const float* v) {
 }
 
 template <class P>
-MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers<typename P::Mbar>& bar, uint32_t* tmem_base_s) {
+MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers<typename P::Mbar>& bar, uint32_t* tmem_base_s,
+                     const typename P::TensorMap* tmq = nullptr, const typename P::TensorMap* tmk = nullptr) {
   P::pdl_launch();
   const int tid = cx.tid(), lane = tid & 31, warp = P::bcast0(cx, tid >> 5);
   const int dk = a.dk, G = dk / 8;
@@ -120,7 +141,34 @@ MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers
   const float* vg = base + (long long)(2 * a.H + h * dk) * a.qkv.cs;
   constexpr int RSQ = A_QT + 8, RSK = A_KB + 8;       // raw row strides (floats)
 
-  if (active && warp == 0) {
+  if (active && warp == 0 && a.tm) {
+    // ---------------------------------------------------------------------- TMA by tensor map: one box per window
+    // (the per-row form below issues dk .. 2 dk bulk copies of 256 bytes per block from one lane: ~3 us of a ~7 us block step)
+    const uint32_t rawa = P::saddr(cx, raw);
+    const int chq = h * dk, chk = a.H + h * dk, chv = 2 * a.H + h * dk;
+    auto box = [&](uint32_t dst, const typename P::TensorMap* tm, int x, int ch) {
+      if (a.flat) P::tma_load_3d(cx, dst, tm, x, b, ch, &bar.raw_full);
+      else P::tma_load_3d(cx, dst, tm, x, ch, b, &bar.raw_full);
+    };
+    uint32_t it = 0;
+    if (P::elect_one(cx)) {
+      P::mbar_expect_tx(cx, &bar.raw_full, (uint32_t)(dk * RSQ * 4));
+      box(rawa, tmq, q0, chq);
+    }
+    P::syncwarp();
+    ++it;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int blk = 0; blk < n_blk; ++blk, ++it) {
+        const int j0 = blk * A_KB;
+        P::mbar_wait(cx, &bar.raw_free, (it - 1) & 1);
+        if (P::elect_one(cx)) {
+          P::mbar_expect_tx(cx, &bar.raw_full, (uint32_t)((pass ? 2 : 1) * dk * RSK * 4));
+          box(rawa, tmk, j0, chk);
+          if (pass) box(rawa + (uint32_t)(dk * RSK * 4), tmk, j0, chv);
+        }
+        P::syncwarp();
+      }
+  } else if (active && warp == 0) {
     // ---------------------------------------------------------------------- TMA: the q tile, then k (and v) blocks
     uint32_t it = 0;                                   // raw buffer uses so far
     {

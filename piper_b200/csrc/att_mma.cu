@@ -16,12 +16,15 @@ namespace pb200 {
 void count_launch();
 
 namespace {
-__global__ void __launch_bounds__(att::A_THREADS, 1) att_kernel(const __grid_constant__ att::Args a) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(att::A_THREADS, 1) att_kernel(const __grid_constant__ att::Args a,
+                                                                 const __grid_constant__ CUtensorMap tmq,
+                                                                 const __grid_constant__ CUtensorMap tmk) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) att::Barriers<uint64_t> bar;
   __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);   // tensor copies: 128-byte aligned
   DevPrim::Ctx cx;
-  att::att_body<DevPrim>(a, cx, smem, bar, &tmem_base_s);
+  att::att_body<DevPrim>(a, cx, smem, bar, &tmem_base_s, &tmq, &tmk);
 }
 }  // namespace
 
@@ -34,7 +37,20 @@ bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float
   att::Args a;
   a.qkv = qkv; a.out = out; a.rel_k = rel_k; a.rel_v = rel_v; a.len = len;
   a.H = H; a.dk = dk; a.n_heads = n_heads; a.q_tiles = (Tmax + att::A_QT - 1) / att::A_QT;
-  const int smem = att::smem_bytes(dk);
+  const int smem = att::smem_bytes(dk) + 128;
+  static int g_tm = -1;                                   // PIPER_B200_ATT_TM: tensor-map loads of the q / k / v windows (default on)
+  if (g_tm < 0) {
+    const char* e = std::getenv("PIPER_B200_ATT_TM");
+    g_tm = e ? (std::atoi(e) != 0) : 1;
+  }
+  CUtensorMap tmq{}, tmk{};
+  if (g_tm) {
+    a.flat = qkv.bs < (long long)qkv.cs ? 1 : 0;
+    a.tm = 1;
+    TmapDesc dq, dk_;
+    att::att_tmaps(a, B, dq, dk_);
+    if (!encode_tmap(dq, &tmq) || !encode_tmap(dk_, &tmk)) a.tm = a.flat = 0;   // refused: per-row bulk copies
+  }
   // The opt-in limit (227 KB per block) covers static + dynamic shared memory, so asking for 227 KB of dynamic memory is
   // refused: ask for what this head width needs (found on the first GPU run: the launch failed with "invalid argument").
   static int attr_bytes[64] = {};
@@ -48,7 +64,7 @@ bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float
     }
     attr_bytes[dev & 63] = smem;
   }
-  launch_k(att_kernel, dim3(a.q_tiles * n_heads * B), dim3(att::A_THREADS), smem, st, a);
+  launch_k(att_kernel, dim3(a.q_tiles * n_heads * B), dim3(att::A_THREADS), smem, st, a, tmq, tmk);
   count_launch();
   return true;
 }

@@ -50,6 +50,7 @@ inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p
       // (every accumulator the shipped kernel has exercised on hardware is)
       int score = (n_tile % 32 == 0 ? 1000000 : 0) + slots * 100000 + n_tile * 5000 + mt / 128;
       if ((opts & 1) && chains > 1 && mt == 256) score += 500000;    // the option asks for the tall tile where it fits
+      if ((opts & 2) && mt == 128) score += 2;                       // option: prefer 128-row tiles (larger channel chunks fit)
       if (score > best_score) {
         best_score = score;
         p.n_tile = n_tile; p.n_tiles = nt; p.mt = mt; p.t_slots = slots;

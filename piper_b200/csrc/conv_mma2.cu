@@ -58,7 +58,11 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-bool encode_tmap(const TmapDesc& d, CUtensorMap* out) {
+
+}  // namespace
+
+bool encode_tmap(const TmapDesc& d, void* out_cutensormap) {
+  CUtensorMap* out = static_cast<CUtensorMap*>(out_cutensormap);
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)d.dims[0], (cuuint64_t)d.dims[1], (cuuint64_t)d.dims[2]};
@@ -69,8 +73,6 @@ bool encode_tmap(const TmapDesc& d, CUtensorMap* out) {
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-
-}  // namespace
 
 bool conv2_plan(int ci, int rows, int k, int dil, int prec, int chains, Conv2Layer& l) {
   static int g_opts = -1;                               // PIPER_B200_V2_OPTS: plan options (conv2_host.h)

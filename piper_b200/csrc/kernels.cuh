@@ -68,6 +68,9 @@ struct TmapDesc {
   int box[3] = {0, 0, 1};                   // floats per row, rows, 1
 };
 
+// CUtensorMap (128 bytes, 64-byte aligned) from a TmapDesc through cuTensorMapEncodeTiled; false = the driver refused it.
+bool encode_tmap(const TmapDesc& d, void* out_cutensormap);
+
 // ---- tensor-core (tcgen05) Conv1d / ConvTranspose1d with split precision (conv_mma.cu) ----------------------
 struct MmaConvArgs {
   View x, y, y2, r;

@@ -13,15 +13,19 @@ using namespace simtc;
 
 // qkv [B][3H][cs], out [B][H][cs], rel_k / rel_v [9][dk], len [B]
 extern "C" int att_sim_run(const float* qkv, float* out, const float* rel_k, const float* rel_v, const int* len, int B, int H,
-                           int n_heads, int cs, int Tmax, char* err, int errcap) {
+                           int n_heads, int cs, int Tmax, char* err, int errcap, int tm, int flat) {
   try {
     att::Args a;
-    a.qkv = View{const_cast<float*>(qkv), (long long)3 * H * cs, cs};
-    a.out = View{out, (long long)H * cs, cs};
+    // flat: the caller passes [channel][item][cs] tensors
+    a.qkv = flat ? View{const_cast<float*>(qkv), (long long)cs, B * cs} : View{const_cast<float*>(qkv), (long long)3 * H * cs, cs};
+    a.out = flat ? View{out, (long long)cs, B * cs} : View{out, (long long)H * cs, cs};
+    a.tm = tm; a.flat = flat;
     a.rel_k = rel_k; a.rel_v = rel_v; a.len = len;
     a.H = H; a.n_heads = n_heads; a.dk = H / n_heads; a.q_tiles = (Tmax + att::A_QT - 1) / att::A_QT;
     if (a.dk % 16 || a.dk > att::A_MAXDK) throw std::runtime_error("head width not handled");
     const int grid = a.q_tiles * n_heads * B, smem = att::smem_bytes(a.dk);
+    TmapDesc tq, tk;
+    if (tm) att::att_tmaps(a, B, tq, tk);
     for (int block = 0; block < grid; ++block) {
       std::unique_ptr<SimCta> cta(new SimCta);
       SmemBuf sm(smem);
@@ -29,7 +33,7 @@ extern "C" int att_sim_run(const float* qkv, float* out, const float* rel_k, con
       for (auto& row : cta->tmem) for (float& v : row) v = std::numeric_limits<float>::quiet_NaN();
       std::unique_ptr<att::Barriers<SimMbar>> bar(new att::Barriers<SimMbar>);
       const std::string e = run_cta(*cta, att::A_THREADS, block, grid, [&](SimPrim::Ctx& cx) {
-        att::att_body<SimPrim>(a, cx, cta->smem, *bar, &cta->tmem_base);
+        att::att_body<SimPrim>(a, cx, cta->smem, *bar, &cta->tmem_base, &tq, &tk);
       });
       if (!e.empty()) throw std::runtime_error("CTA " + std::to_string(block) + ": " + e);
     }

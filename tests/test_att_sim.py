@@ -41,14 +41,15 @@ def _reference(q, k, v, rel_k, rel_v, window=4):
     return O.t().float()
 
 
+@pytest.mark.parametrize("mode", ["rows", "tm", "tm_flat"])     # per-row bulk copies / tensor-map boxes / tensor map over the flat layout
 @pytest.mark.parametrize("H,n_heads,lens", [(192, 2, (259, 17)),       # medium: dk = 96, five key blocks, ragged
                                              (96, 2, (130,)),           # x-low: dk = 48
                                              (32, 2, (64, 1, 65)),      # dk = 16; exactly one block, one key, one past a block
                                              (64, 4, (600,))])          # four heads, five query tiles, ten key blocks
-def test_tensor_core_attention_on_cpu_model(sim, H, n_heads, lens):
+def test_tensor_core_attention_on_cpu_model(sim, H, n_heads, lens, mode):
     B, dk = len(lens), H // n_heads
     Tmax = max(lens)
-    cs = (Tmax + 3) & ~3
+    cs = ((Tmax + 3) & ~3) + (4 if mode == "tm_flat" else 0)
     rng = np.random.default_rng(H + Tmax)
     qkv = rng.standard_normal((B, 3 * H, cs)).astype(np.float32) * 30.0   # stale data past each item's length
     for b, T in enumerate(lens):
@@ -59,16 +60,21 @@ def test_tensor_core_attention_on_cpu_model(sim, H, n_heads, lens):
     lens_a = np.asarray(lens, np.int32)
     err = C.create_string_buffer(512)
     fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
-    rc = sim.att_sim_run(fp(qkv), fp(out), fp(rel_k), fp(rel_v), lens_a.ctypes.data_as(C.POINTER(C.c_int32)), B, H, n_heads, cs,
-                         Tmax, err, len(err))
+    flat = mode == "tm_flat"
+    qkv_dev = np.ascontiguousarray(qkv.transpose(1, 0, 2)) if flat else qkv          # [channel][item][slot]
+    out_dev = np.ascontiguousarray(out.transpose(1, 0, 2)) if flat else out
+    rc = sim.att_sim_run(fp(qkv_dev), fp(out_dev), fp(rel_k), fp(rel_v), lens_a.ctypes.data_as(C.POINTER(C.c_int32)), B, H, n_heads, cs,
+                         Tmax, err, len(err), 0 if mode == "rows" else 1, 1 if flat else 0)
     assert rc == 0, err.value.decode()
+    if flat:
+        out = out_dev.transpose(1, 0, 2)
     for b, T in enumerate(lens):
         for h in range(n_heads):
             q = torch.from_numpy(qkv[b, h * dk:(h + 1) * dk, :T])
             k = torch.from_numpy(qkv[b, H + h * dk:H + (h + 1) * dk, :T])
             v = torch.from_numpy(qkv[b, 2 * H + h * dk:2 * H + (h + 1) * dk, :T])
             ref = _reference(q, k, v, torch.from_numpy(rel_k), torch.from_numpy(rel_v))
-            got = torch.from_numpy(out[b, h * dk:(h + 1) * dk, :T])
+            got = torch.from_numpy(np.ascontiguousarray(out[b, h * dk:(h + 1) * dk, :T]))
             e = float((got - ref).abs().max())
             assert e <= 2e-5 * max(1.0, float(ref.abs().max())), (b, h, e)
         assert np.all(out[b, :, T:] == 7e7), "stored outside the utterance"
