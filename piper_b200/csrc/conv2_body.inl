@@ -118,11 +118,30 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
 
   // tile id -> (output-row tile, item, time block); every role walks the same list and skips the same tiles
   const int flat_tg = a.flat_tg;                       // > 0: tiles on the concatenated time axis (see MmaConvArgs)
+  // Tile walk.  Default: tile = (nt, item, time block) with the time block fastest, CTAs take tiles round-robin.
+  // A-stationary (a.astat): tile = (item, time block, nt) with nt fastest and every CTA takes a CONTIGUOUS range, so the
+  // output-row tiles of one position follow each other on one CTA: the activation roles (TMA, converters) work once per
+  // group of such tiles, the MMA warp waits for the operand once per group and releases it after the group's last tile.
+  const int astat = a.astat, n_nt = a.n_tiles;
+  const int per_cta = (total + grid - 1) / grid;
+  const int tile_lo = astat ? imin(block * per_cta, total) : block;
+  const int tile_hi = astat ? imin(tile_lo + per_cta, total) : total;
+  const int tile_step = astat ? 1 : grid;
+  auto group_first = [&](int tile) { return !astat || tile == tile_lo || tile % n_nt == 0; };
+  auto group_last = [&](int tile) { return !astat || tile + 1 == tile_hi || tile % n_nt == n_nt - 1; };
   auto decode = [&](int tile, int& nt, int& b, int& t0, int& L, int& Lq) {
-    const int tb = tile % tpi;
-    const int rest = tile / tpi;
-    b = rest % a.batch;
-    nt = rest / a.batch;
+    int tb;
+    if (astat) {
+      nt = tile % n_nt;
+      const int pos = tile / n_nt;
+      tb = pos % tpi;
+      b = pos / tpi;
+    } else {
+      tb = tile % tpi;
+      const int rest = tile / tpi;
+      b = rest % a.batch;
+      nt = rest / a.batch;
+    }
     t0 = tb * MT;
     L = flat_tg ? a.flat_n * flat_tg : a.len[b] * a.len_scale;
     Lq = L + a.q_extra;
@@ -142,11 +161,11 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const int n_box = a.tm_boxes, Wb = RS / n_box;
     const uint32_t box_bytes = (uint32_t)KC * (uint32_t)Wb * 4u;
     uint32_t it = 0;
-    for (int tile = block; tile < total; tile += grid) {
+    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
       bool ok = decode(tile, nt, b, t0, L, Lq);
       ok = P::bcast0(cx, (int)ok) != 0;
-      if (!ok) continue;
+      if (!ok || !group_first(tile)) continue;                         // one load per position
       const int t_base = (t0 - a.pad) & ~3;                            // 16-byte aligned start (may be negative: zero fill)
       for (int kc = 0; kc < n_kc; ++kc, ++it) {
         const int s = it % C2_RAW_SLOTS;
@@ -163,12 +182,12 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   } else if (warp == 0) {
     // ---------------------------------------------------------------------- raw activation rows via TMA, uniform issue
     uint32_t it = 0;
-    for (int tile = block; tile < total; tile += grid) {
+    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
       bool ok = decode(tile, nt, b, t0, L, Lq);
       L = P::bcast0(cx, L);                                            // loaded from global: make uniformity explicit
       ok = P::bcast0(cx, (int)ok) != 0;
-      if (!ok) continue;
+      if (!ok || !group_first(tile)) continue;
       const int t_lo = t0 - a.pad;
       const int t_base = t_lo & ~3;                                    // smem column 0 <-> time t_base
       const int g0 = imax(t_lo, 0) & ~3;                               // first / one-past-last float fetched
@@ -197,7 +216,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     // ---------------------------------------------------------------------- weight units via TMA: one copy per unit
     uint32_t it = 0;
     const size_t nt_bytes = size_t(a.k) * (a.ci / E) * 2 * NT * 16;    // all taps and chunks of one output-row tile
-    for (int tile = block; tile < total; tile += grid) {
+    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
       bool ok = decode(tile, nt, b, t0, L, Lq);
       ok = P::bcast0(cx, (int)ok) != 0;
@@ -223,7 +242,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const uint32_t idesc2 = make_idesc(PREC, 128, 2 * NT), idesc1 = make_idesc(PREC, 128, NT);
     const uint32_t a_step = 2u * (uint32_t)R, w_step = 4u * (uint32_t)NT;          // 16-byte units per k-step
     uint32_t a_it = 0, w_it = 0, t_it = 0;
-    for (int tile = block; tile < total; tile += grid) {
+    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
       bool ok = decode(tile, nt, b, t0, L, Lq);
       Lq = P::bcast0(cx, Lq);
@@ -236,9 +255,12 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       const uint32_t d_set = tmem_du + (uint32_t)(ts * set_cols);
       uint32_t started = 0;
       int u = 0;
-      for (int kc = 0; kc < n_kc; ++kc, ++a_it) {
-        const int as = a_it % C2_A_SLOTS;
-        P::mbar_wait(cx, &bar.a_full[as], (a_it / C2_A_SLOTS) & 1);
+      const bool g_first = group_first(tile), g_last = group_last(tile);
+      const uint32_t a_base = a_it;                                    // operand-ring position of this group's first chunk
+      for (int kc = 0; kc < n_kc; ++kc) {
+        const uint32_t a_idx = a_base + (uint32_t)kc;
+        const int as = a_idx % C2_A_SLOTS;
+        if (g_first) P::mbar_wait(cx, &bar.a_full[as], (a_idx / C2_A_SLOTS) & 1);   // (a later tile of the group: still resident)
         P::fence_tc_after();
         const uint32_t a_hi = P::saddr(cx, A_ring + size_t(as) * 2 * a_part);
         const uint32_t ah_base = desc_lo(a_hi, a_lbo), al_base = desc_lo(a_hi + a_part, a_lbo);
@@ -303,9 +325,12 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
           if (P::elect_one(cx)) P::mma_commit(cx, &bar.w_empty[ws]);
           P::syncwarp();
         }
-        if (P::elect_one(cx)) P::mma_commit(cx, &bar.a_empty[as]);
-        P::syncwarp();
+        if (g_last) {                                                  // the group's last tile releases the operand chunk
+          if (P::elect_one(cx)) P::mma_commit(cx, &bar.a_empty[as]);
+          P::syncwarp();
+        }
       }
+      if (g_last) a_it += (uint32_t)n_kc;
       if (P::elect_one(cx)) P::mma_commit(cx, &bar.t_full[ts]);
       P::syncwarp();
       ++t_it;
@@ -314,9 +339,9 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     // ---------------------------------------------------------------------- converters
     const int ctid = tid - C2_CONV_WARP0 * 32;
     uint32_t raw_it = 0, a_it = 0;
-    for (int tile = block; tile < total; tile += grid) {
+    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
-      if (!decode(tile, nt, b, t0, L, Lq)) continue;
+      if (!decode(tile, nt, b, t0, L, Lq) || !group_first(tile)) continue;   // one conversion per position
       const int t_lo = t0 - a.pad;
       const int off = t_lo - (t_lo & ~3);                               // smem column of stage row 0
       const int Wb = TM ? RS / a.tm_boxes : RS;                         // TM: dense boxes [box][KC][Wb]
@@ -403,7 +428,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const bool bias_vec = a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0;
     const bool r_all = epi == EPI_RES || epi == EPI_MRF || epi == EPI_SUBFROM;     // residual for every row
     const bool o_all = epi == EPI_MRF && a.mrf != 0;                               // running MRF sum for every row
-    for (int tile = block; tile < total; tile += grid) {
+    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
       if (!decode(tile, nt, b, t0, L, Lq)) continue;
       const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;

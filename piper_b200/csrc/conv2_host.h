@@ -168,7 +168,7 @@ inline void pack(const float* wsrc, int ci, int k, int rows_p, const Plan& p, ui
 // plan -> the tiling fields of the launch arguments; returns the grid size (0: nothing to do)
 // tm: stage the activation rows with one tensor-map TMA copy per channel chunk (two when the staged window is wider than
 // the 256-element box limit) instead of one bulk copy per channel row; `td` then describes the tensor and the box.
-inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm = false, TmapDesc* td = nullptr) {
+inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm = false, TmapDesc* td = nullptr, bool astat_ok = false) {
   a.n_tile = p.n_tile; a.acc_cols = p.n_tile; a.chains = p.chains; a.mh_stride = p.mh_stride; a.sep_corr = 0;
   a.kc = p.kc; a.stage_rows = p.stage_rows; a.raw_stride = p.raw_stride; a.t_slots = p.t_slots; a.tmem_cols = p.tmem_cols;
   a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);          // never more chains than weight units
@@ -194,6 +194,10 @@ inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm 
     }
     a.chains = std::min(p.chains, (a.ci / a.kc) * a.k);
   }
+  // A-stationary order where it pays and is possible: several output-row tiles per position, and every channel chunk of a
+  // position resident in the two-slot operand ring at once
+  a.n_tiles = p.n_tiles;
+  a.astat = (astat_ok && p.n_tiles > 1 && a.ci / a.kc <= 2) ? 1 : 0;
   a.tm_boxes = 0;
   if (tm && td) {
     // the innermost start coordinate of a tiled tensor copy must be 16-byte aligned (an unaligned one is an illegal

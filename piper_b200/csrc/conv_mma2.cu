@@ -118,10 +118,17 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   TmapDesc td;
   CUtensorMap tmx;
   bool tm = g_tm != 0;
-  int grid = conv2::fill_args(a, p, B, max_len, tm, &td);
+  // PIPER_B200_V2_ASTAT=1: A-stationary tile order (conv2_body.inl).  Measured on the B200: 447.9 vs 448.4 M samples/s -
+  // the layers with several output-row tiles per position are not bound by re-converting their activations - so off by default.
+  static int g_astat = -1;
+  if (g_astat < 0) {
+    const char* e = std::getenv("PIPER_B200_V2_ASTAT");
+    g_astat = e ? (std::atoi(e) != 0) : 0;
+  }
+  int grid = conv2::fill_args(a, p, B, max_len, tm, &td, g_astat != 0);
   if (tm && !encode_tmap(td, &tmx)) {                    // (a view the encoder refuses: fall back to per-row copies)
     tm = false;
-    grid = conv2::fill_args(a, p, B, max_len);
+    grid = conv2::fill_args(a, p, B, max_len, false, nullptr, g_astat != 0);
   }
   static int g_small_too = -1;                          // PIPER_B200_V2=2: also take launches with fewer tiles than SMs
   if (g_small_too < 0) {

@@ -94,6 +94,10 @@ struct MmaConvArgs {
   // flat_tg), the launch sees ONE item of length flat_n * flat_tg and tiles are cut on that concatenated time axis; a row
   // g belongs to item g / flat_tg at time g % flat_tg and is live while that is < len[item] * len_scale.
   int flat_tg = 0, flat_n = 0;
+  // conv2 A-stationary order: output-row tiles of one position are consecutive tiles of ONE CTA, and the converted
+  // activation window (all its channel chunks fit the operand ring) is loaded and converted once per position instead of
+  // once per output-row tile.  n_tiles = output-row tiles per position.
+  int astat = 0, n_tiles = 1;
   unsigned long long* prof = nullptr;   // optional: per-role stall cycle counters (tools/conv_diag.py)
 };
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);

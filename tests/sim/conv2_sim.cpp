@@ -66,7 +66,7 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
     const bool tm = (desc[25] & 4) != 0;                 // opts bit 2: tensor-map TMA for the activation window
     a.mma3 = (desc[25] & 8) ? 1 : 0;                     // opts bit 3: three instructions per k-step on matching accumulator regions
     TmapDesc td;
-    int grid = conv2::fill_args(a, p, launch_B, max_len, tm, &td);
+    int grid = conv2::fill_args(a, p, launch_B, max_len, tm, &td, (desc[25] & 32) != 0);   // opts bit 5: A-stationary order
     if (desc[23] > 0) grid = std::min(grid, desc[23]);
     if (info) {
       info[0] = p.n_tile; info[1] = p.n_tiles; info[2] = p.mt; info[3] = p.kc; info[4] = p.t_slots; info[5] = a.chains;

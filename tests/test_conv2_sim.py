@@ -357,7 +357,8 @@ def test_tensor_map_conv_transpose_tail(sim):
                                                           (2, 96, 192, 5, 1, "GATE", (131, 40, 259, 7)),   # halo across item boundaries, ragged
                                                           (1, 64, 128, 3, 1, "RELU", (100, 1, 128)),
                                                           (2, 192, 384, 1, 1, "WN", (70, 130))])
-def test_flat_mode_tiles_on_the_concatenated_time_axis(sim, prec, ci, rows, k, dil, epi, lens):
+@pytest.mark.parametrize("astat", [0, 32])
+def test_flat_mode_tiles_on_the_concatenated_time_axis(sim, prec, ci, rows, k, dil, epi, lens, astat):
     """opts bit 4: views laid out [channel][item][slot] and ONE launch item of length items x slot - a tile may cover the end
     of one utterance and the start of the next; rows in the gaps are neither read as data nor written."""
     B = len(lens)
@@ -382,7 +383,7 @@ def test_flat_mode_tiles_on_the_concatenated_time_axis(sim, prec, ci, rows, k, d
         y[...] = r                                           # in-place residual stream (y == r in the engine)
     lens_a = np.asarray(lens, np.int32)
     desc = (C.c_int32 * 26)(ci, rows, k, dil, pad, 0, 1 if epi == "RELU" else 0, EPI[epi], split, 0, 1, 0, 0, 3, prec, 1,
-                           B * Tg, B * Tg, B * Tg, B * Tg, C_y, y2.shape[0], C_y, 2, 0, 16 | 4)
+                           B * Tg, B * Tg, B * Tg, B * Tg, C_y, y2.shape[0], C_y, 2, 0, 16 | 4 | astat)
     info = (C.c_int32 * 8)()
     err = C.create_string_buffer(512)
     rc = sim.conv2_sim_run(_fp(x), _fp(np.ascontiguousarray(w)), _fp(bias), None, 0, _fp(y), _fp(y2), _fp(y if epi == "WN" else r),
@@ -406,3 +407,37 @@ def test_flat_mode_tiles_on_the_concatenated_time_axis(sim, prec, ci, rows, k, d
         assert e <= tol * max(1.0, float(want.abs().max())), (epi, b, e, list(info))
         gap = y[:, b, L:]
         assert np.all(gap == (r[:, b, L:] if epi == "WN" else 7e7)), "stored in the gap between utterances"
+
+
+@pytest.mark.parametrize("prec,ci,rows,k,dil,epi,lens,grid", [(2, 192, 576, 1, 1, "BIAS", (259, 130), 3),    # q|k|v: 5 output-row tiles per position, two chunks
+                                                               (2, 64, 256, 5, 1, "RES", (300, 37), 2),        # one chunk (both ring slots alternate between positions)
+                                                               (1, 96, 384, 3, 1, "RELU", (140,), 5),          # more CTAs than positions: groups split across CTAs
+                                                               (2, 192, 384, 5, 1, "GATE", (131, 259), 4)])
+def test_a_stationary_tile_order(sim, prec, ci, rows, k, dil, epi, lens, grid):
+    """opts bit 5: the output-row tiles of a position are consecutive tiles of one CTA; the activation window is loaded and
+    converted once per position and stays in the operand ring until the group's last tile - same numbers as the default
+    order (bit-identical: same operands, same accumulation order), with and without the flat layout / tensor-map loads."""
+    B = len(lens)
+    x, clean = _ragged(B, ci, lens, seed=ci + rows)
+    rng = np.random.default_rng(8)
+    w = (rng.standard_normal((rows, ci, k)) / np.sqrt(ci * k)).astype(np.float32)
+    bias = rng.standard_normal(rows).astype(np.float32)
+    C_y = rows // 2 if epi == "GATE" else rows
+    r = rng.standard_normal((B, C_y, x.shape[2])).astype(np.float32) if epi == "RES" else None
+    kw = dict(dil=dil, pre=1 if epi == "RELU" else 0, epi=epi, prec=prec, r=r, grid=grid, y_channels=C_y)
+    y_ref, _, _ = _run(sim, x, w, bias, lens, opts=0, **kw)
+    for opts in (32, 32 | 4):
+        y, _, info = _run(sim, x, w, bias, lens, opts=opts, **kw)
+        for b, L in enumerate(lens):
+            assert np.array_equal(y[b, :, :L], y_ref[b, :, :L]), (opts, b, info)
+            assert np.all(y[b, :, L:] == 7e7)
+    for b, L in enumerate(lens):                                  # and the default order is right in the first place
+        ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, kw["pre"], 0.1)
+        if epi == "RES":
+            ref = ref + torch.from_numpy(r[b, :, :L])
+        elif epi == "RELU":
+            ref = torch.relu(ref)
+        elif epi == "GATE":
+            ref = torch.tanh(ref[0::2]) * torch.sigmoid(ref[1::2])
+        e = float((torch.from_numpy(y_ref[b, :, :L]) - ref).abs().max())
+        assert e <= _tol(prec != 0) * max(1.0, float(ref.abs().max())), (b, e)
