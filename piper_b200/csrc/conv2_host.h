@@ -39,7 +39,7 @@ inline bool plan(int ci, int rows, int k, int dil, int prec, int chains, Plan& p
   for (int nt = 1; nt <= 64; ++nt) {
     if (rows % nt || (rows / nt) % 16 || rows / nt > 128) continue;
     const int n_tile = rows / nt;
-    if (chains > 1 && n_tile > 64 && !(ci * k >= 900 && rows >= 256)) continue;   // as conv_mma.cu: wide tiles only for long reductions
+    if (chains > 1 && n_tile > 64 && (!(ci * k >= 900 && rows >= 256) || (opts & 4))) continue;   // wide tiles only for long reductions (opts bit 2: never - keeps two TMEM sets)
     for (int mt : {256, 128}) {
       if (tf32 && mt != 128) continue;                     // no 256-row tf32 kernel instantiation
       if (chains > 1 && mt != 128 && !(opts & 1)) continue;
