@@ -148,9 +148,12 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     return t0 < Lq;
   };
   // flat mode: is concatenated position g inside an utterance, and whose?
+  // (g / flat_tg by multiplication with ceil(2^32 / flat_tg): exact while g * flat_tg < 2^32, which the host guarantees for
+  // a flat launch; a 32-bit integer division is ~25 dependent instructions, and this runs per row in three roles)
+  const uint32_t tg_magic = flat_tg > 1 ? 0xFFFFFFFFu / (uint32_t)flat_tg + 1u : 0u;
   auto flat_live = [&](int g, int& item) -> bool {
     if (g < 0) return false;
-    item = g / flat_tg;
+    item = (int)(((unsigned long long)(uint32_t)g * tg_magic) >> 32);
     return item < a.flat_n && g - item * flat_tg < a.len[item] * a.len_scale;
   };
 
@@ -222,10 +225,11 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       ok = P::bcast0(cx, (int)ok) != 0;
       if (!ok) continue;
       const uint8_t* wsrc = a.w + size_t(nt) * nt_bytes;
-      for (int u = 0; u < n_units; ++u, ++it) {
+      int kc = 0, j = 0;                                               // unit u = (chunk kc, tap j), tap fastest
+      for (int u = 0; u < n_units; ++u, ++it, ++j) {
         const int s = it % C2_W_SLOTS;
         if (it >= C2_W_SLOTS) P::mbar_wait(cx, &bar.w_empty[s], ((it / C2_W_SLOTS) - 1) & 1);
-        const int kc = u / a.k, j = u - kc * a.k;
+        if (j == a.k) { j = 0; ++kc; }
         const uint8_t* src = wsrc + (size_t(j) * (a.ci / E) + size_t(kc) * (KC / E)) * 2 * NT * 16;
         if (P::elect_one(cx)) {
           P::mbar_expect_tx(cx, &bar.w_full[s], unit_bytes);
@@ -242,6 +246,12 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const uint32_t idesc2 = make_idesc(PREC, 128, 2 * NT), idesc1 = make_idesc(PREC, 128, NT);
     const uint32_t a_step = 2u * (uint32_t)R, w_step = 4u * (uint32_t)NT;          // 16-byte units per k-step
     uint32_t a_it = 0, w_it = 0, t_it = 0;
+    // optional per-role wait counters (a.prof, developer diagnostic): cycles the MMA warp waits for [0] the TMEM set,
+    // [1] an operand chunk, [2] a weight unit, and [3] its whole loop; [4] epilogue waiting for an accumulator, [5] its loop;
+    // [6] converters waiting for raw data, [7] for a free operand slot, [8] their loop
+    const bool prof = a.prof != nullptr;
+    long long pw_t = 0, pw_a = 0, pw_w = 0;
+    const long long p_start = prof ? P::clock() : 0;
     for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
       bool ok = decode(tile, nt, b, t0, L, Lq);
@@ -250,7 +260,9 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       if (!ok) continue;
       const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
       const int ts = t_it % t_slots;
+      long long pc = prof ? P::clock() : 0;
       if (t_it >= (uint32_t)t_slots) P::mbar_wait(cx, &bar.t_empty[ts], ((t_it / t_slots) - 1) & 1);
+      if (prof) pw_t += P::clock() - pc;
       P::fence_tc_after();
       const uint32_t d_set = tmem_du + (uint32_t)(ts * set_cols);
       uint32_t started = 0;
@@ -260,15 +272,19 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       for (int kc = 0; kc < n_kc; ++kc) {
         const uint32_t a_idx = a_base + (uint32_t)kc;
         const int as = a_idx % C2_A_SLOTS;
+        pc = prof ? P::clock() : 0;
         if (g_first) P::mbar_wait(cx, &bar.a_full[as], (a_idx / C2_A_SLOTS) & 1);   // (a later tile of the group: still resident)
+        if (prof) pw_a += P::clock() - pc;
         P::fence_tc_after();
         const uint32_t a_hi = P::saddr(cx, A_ring + size_t(as) * 2 * a_part);
         const uint32_t ah_base = desc_lo(a_hi, a_lbo), al_base = desc_lo(a_hi + a_part, a_lbo);
         for (int j = 0; j < a.k; ++j, ++u, ++w_it) {
           const int ws = w_it % C2_W_SLOTS;
+          pc = prof ? P::clock() : 0;
           P::mbar_wait(cx, &bar.w_full[ws], (w_it / C2_W_SLOTS) & 1);
+          if (prof) pw_w += P::clock() - pc;
           P::fence_tc_after();
-          const int chain = (u * a.chains) / n_units;
+          const int chain = u * a.chains >= n_units ? 1 : 0;            // = (u * chains) / n_units for chains <= 2, without the division
           uint32_t acc = (started >> chain) & 1u;
           started |= 1u << chain;
           const uint32_t d_pair = d_set + (uint32_t)(chain * pair_cols);
@@ -335,10 +351,17 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       P::syncwarp();
       ++t_it;
     }
+    if (prof && lane == 0) {
+      P::prof_add(a.prof + 0, pw_t); P::prof_add(a.prof + 1, pw_a); P::prof_add(a.prof + 2, pw_w);
+      P::prof_add(a.prof + 3, P::clock() - p_start);
+    }
   } else if (warp < C2_EPI_WARP0) {
     // ---------------------------------------------------------------------- converters
     const int ctid = tid - C2_CONV_WARP0 * 32;
     uint32_t raw_it = 0, a_it = 0;
+    const bool prof = a.prof != nullptr && ctid == 0;
+    long long pw_r = 0, pw_e = 0;
+    const long long p_start = prof ? P::clock() : 0;
     for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       int nt, b, t0, L, Lq;
       if (!decode(tile, nt, b, t0, L, Lq) || !group_first(tile)) continue;   // one conversion per position
@@ -347,8 +370,11 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       const int Wb = TM ? RS / a.tm_boxes : RS;                         // TM: dense boxes [box][KC][Wb]
       for (int kc = 0; kc < n_kc; ++kc, ++raw_it, ++a_it) {
         const int rs = raw_it % C2_RAW_SLOTS, as = a_it % C2_A_SLOTS;
+        long long pc = prof ? P::clock() : 0;
         P::mbar_wait(cx, &bar.raw_full[rs], (raw_it / C2_RAW_SLOTS) & 1);
+        if (prof) { const long long n = P::clock(); pw_r += n - pc; pc = n; }
         if (a_it >= C2_A_SLOTS) P::mbar_wait(cx, &bar.a_empty[as], ((a_it / C2_A_SLOTS) - 1) & 1);
+        if (prof) pw_e += P::clock() - pc;
         const float* raw = reinterpret_cast<const float*>(RAW_ring + size_t(rs) * raw_bytes) + off;
         uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
         uint8_t* A_lo = A_hi + a_part;
@@ -360,8 +386,9 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         // work item = (row, share of the channel groups): with R = 136 rows and 128 threads a row-only split would leave
         // 120 threads idle in the second pass
         const int S = (G % 4 == 0 && G >= 16) ? 4 : (G % 2 == 0 && G >= 8) ? 2 : 1, GS = G / S;
-        for (int item = ctid; item < R * S; item += C2_CONV_THREADS) {
-          const int sg = item / R, r = item - sg * R;
+        int sg = 0, r = ctid;                                           // item = sg * R + r, advanced without a division
+        for (int item = ctid; item < R * S; item += C2_CONV_THREADS, r += C2_CONV_THREADS) {
+          while (r >= R) { r -= R; ++sg; }
           const int t = t_lo + r;
           int item_unused = 0;
           const bool live = flat_tg ? flat_live(t, item_unused) : (t >= 0 && t < L);   // outside the utterance: zeros, whatever the
@@ -412,6 +439,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         P::mbar_arrive(cx, &bar.raw_empty[rs]);
       }
     }
+    if (prof) { P::prof_add(a.prof + 6, pw_r); P::prof_add(a.prof + 7, pw_e); P::prof_add(a.prof + 8, P::clock() - p_start); }
   } else {
     // ---------------------------------------------------------------------- epilogue
     // The tensors an epilogue READS from global memory (the residual, the MRF / WaveNet-skip running sums) do not depend
@@ -426,6 +454,9 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const int n_acc = 2 * a.chains;                     // (main | correction) per chain, NT columns apart
     const int epi = a.epi;
     const bool bias_vec = a.bias != nullptr && (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0;
+    const bool prof = a.prof != nullptr && ew == 0 && lane == 0;
+    long long pw_f = 0;
+    const long long p_start = prof ? P::clock() : 0;
     const bool r_all = epi == EPI_RES || epi == EPI_MRF || epi == EPI_SUBFROM;     // residual for every row
     const bool o_all = epi == EPI_MRF && a.mrf != 0;                               // running MRF sum for every row
     for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
@@ -446,7 +477,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         return (r_all ? 1 : 0) | (o_all ? 2 : 0);
       };
       auto aux_issue = [&](int wi, float (&rv)[16], float (&ov)[16]) {
-        const int mh = wi / my_chunks, c = half + 2 * (wi - mh * my_chunks);
+        const int mh = wi >= my_chunks ? 1 : 0, c = half + 2 * (wi - mh * my_chunks);   // (work <= 2 * my_chunks)
         const int t = t0 + mh * 128 + q * 32 + lane;
         int item = b;
         if (flat_tg ? !flat_live(t, item) : t >= Lq) return;
@@ -463,11 +494,13 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       };
       float rv[16], ov[16];
       if (work > 0) aux_issue(0, rv, ov);
+      const long long pc = prof ? P::clock() : 0;
       P::mbar_wait(cx, &bar.t_full[ts], (t_it / t_slots) & 1);
+      if (prof) pw_f += P::clock() - pc;
       P::fence_tc_after();
       const uint32_t d_set = tmem_d + (uint32_t)(ts * set_cols);
       for (int wi = 0; wi < work; ++wi) {
-        const int mh = wi / my_chunks, c = half + 2 * (wi - mh * my_chunks);
+        const int mh = wi >= my_chunks ? 1 : 0, c = half + 2 * (wi - mh * my_chunks);   // (work <= 2 * my_chunks)
         const int t = t0 + mh * 128 + q * 32 + lane;
         float rn[16], on[16];
         if (wi + 1 < work) aux_issue(wi + 1, rn, on);    // the next item's reads fly while this one is finished
@@ -576,6 +609,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       }
       ++t_it;
     }
+    if (prof) { P::prof_add(a.prof + 4, pw_f); P::prof_add(a.prof + 5, P::clock() - p_start); }
   }
   P::fence_tc_before();
   P::syncthreads(cx);

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <stdexcept>
 #include <vector>
 
 #include "kernels.cuh"
@@ -172,6 +173,10 @@ inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm 
   a.n_tile = p.n_tile; a.acc_cols = p.n_tile; a.chains = p.chains; a.mh_stride = p.mh_stride; a.sep_corr = 0;
   a.kc = p.kc; a.stage_rows = p.stage_rows; a.raw_stride = p.raw_stride; a.t_slots = p.t_slots; a.tmem_cols = p.tmem_cols;
   a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);          // never more chains than weight units
+  if (p.chains > 2) throw std::runtime_error("conv2: at most two K-chains (the kernel picks the chain by comparison)");
+  // flat mode divides a concatenated position by the slot width with a 32-bit reciprocal multiplication (conv2_body.inl)
+  if (a.flat_tg > 0 && (a.flat_tg < 2 || ((long long)a.flat_n * a.flat_tg + 1024) * a.flat_tg >= (1LL << 32)))
+    throw std::runtime_error("conv2: flat launch outside the range of the reciprocal division");
   a.tiles_per_item = (max_len + p.mt - 1) / p.mt;
   a.total_tiles = a.tiles_per_item * B * p.n_tiles;
   a.batch = B;

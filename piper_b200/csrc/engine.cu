@@ -103,7 +103,7 @@ Engine::~Engine() {
   drop_graphs();
   DeviceBuf* dbs[] = {&weights_, &weights_mma_, &ids_d_, &len_d_, &ylen_d_, &cum_d_, &logw_d_, &override_d_, &epsdp_d_, &epsoff_d_,
                       &off_d_, &sid_d_, &cond_d_, &x_, &t1_, &qkv_, &att_, &ffn_, &stats_, &g_, &h_, &u_, &v_, &pr_, &z2_, &z_, &fh_,
-                      &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_, &mrf_w_, &params_d_};
+                      &facts_, &fout_, &epsz_d_, &ga_, &gp_, &gq_, &gs_, &audio_d_, &audio16_d_, &peak_d_, &mrf_w_, &params_d_, &prof_d_};
   for (auto* d : dbs) d->release();
   for (auto& kv : v2_layers_)
     if (kv.second.w_dev) cudaFree(kv.second.w_dev);
@@ -161,9 +161,12 @@ void Engine::conv(const char* tag, ConvArgs& a, int max_len, double len_sum) {
       if (l) {
         MmaConvArgs m2 = m;
         m2.w = static_cast<const uint8_t*>(l->w_dev);
+        if (profile_ && prof_d_.p && recs_.size() < kProfRecs)       // per-role wait counters of this launch (conv2_body.inl)
+          m2.prof = prof_d_.as<unsigned long long>() + 16 * recs_.size();
         // flat layout views (bs = slot < cs): one launch item of length items x slot, tiles on the concatenated time axis
         auto same_layout = [&](const View& v) { return v.p == nullptr || (v.bs == a.x.bs && v.cs == a.x.cs); };
         const bool flat = flat_ > 0 && a.len_scale == 1 && a.q_extra == 0 && a.x.bs < (long long)a.x.cs && a.x.bs * B_ == a.x.cs &&
+                          a.x.bs >= 2 && ((long long)a.x.cs + 1024) * a.x.bs < (1LL << 32) &&   // (range of the kernel's reciprocal division)
                           same_layout(a.y) && same_layout(a.y2) && same_layout(a.r);   // (conv_pre writes an item-major generator buffer)
         if (flat) {
           m2.flat_tg = int(a.x.bs);
@@ -248,6 +251,11 @@ const Conv2Layer* Engine::v2_layer(const ConvW& w, const ConvArgs& a, int varian
 void Engine::profile_begin() {
   recs_.clear();
   ev_used_ = 0;
+  static const bool roles = std::getenv("PIPER_B200_PROF_ROLES") != nullptr;   // developer diagnostic (tools/layer_report.py --roles)
+  if (roles) {
+    prof_d_.ensure(kProfRecs * 16 * sizeof(unsigned long long));
+    CUDA_CHECK(cudaMemsetAsync(prof_d_.p, 0, kProfRecs * 16 * sizeof(unsigned long long), stream_));
+  }
 }
 
 std::string Engine::profile_json() {
@@ -274,17 +282,28 @@ std::string Engine::profile_json() {
 
 std::string Engine::profile_launches_json() {
   CUDA_CHECK(cudaStreamSynchronize(stream_));
+  std::vector<unsigned long long> roles;
+  if (prof_d_.p) {
+    roles.resize(kProfRecs * 16);
+    CUDA_CHECK(cudaMemcpy(roles.data(), prof_d_.p, roles.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
   std::string out = "[";
   for (size_t i = 0; i < recs_.size(); ++i) {
     const ProfRec& r = recs_[i];
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
-    char buf[320];
+    char buf[640];
     snprintf(buf, sizeof buf,
              "%s{\"tag\":\"%s\",\"mma\":%d,\"us\":%.3f,\"ci\":%d,\"rows\":%d,\"k\":%d,\"dil\":%d,\"up\":%d,"
              "\"max_len\":%d,\"len_sum\":%.0f,\"bytes\":%.0f,\"flops\":%.0f}",
              i ? "," : "", r.tag, r.mma ? 1 : 0, ms * 1e3, r.ci, r.rows, r.k, r.dil, r.up, r.max_len, r.len_sum, r.bytes, r.flops);
     out += buf;
+    if (!roles.empty() && i < kProfRecs && roles[16 * i + 3]) {   // summed over CTAs, SM cycles: see conv2_body.inl for the slots
+      out.pop_back();
+      out += ",\"roles\":[";
+      for (int j = 0; j < 9; ++j) out += (j ? "," : "") + std::to_string(roles[16 * i + j]);
+      out += "]}";
+    }
   }
   return out + "]";
 }

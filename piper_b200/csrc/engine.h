@@ -203,6 +203,8 @@ class Engine {
 
   struct ProfRec { const char* tag; bool mma; cudaEvent_t e0, e1; double bytes, flops; int ci, rows, k, dil, up, max_len; double len_sum; };
   bool profile_ = false;
+  static constexpr size_t kProfRecs = 1024;
+  DeviceBuf prof_d_;                       // PIPER_B200_PROF_ROLES: 16 counters per profiled launch
   std::vector<cudaEvent_t> ev_pool_;
   size_t ev_used_ = 0;
   std::vector<ProfRec> recs_;

@@ -37,6 +37,8 @@ struct DevPrim {
         : "r"(0xFFFFFFFFu));
     return pred != 0;
   }
+  static __device__ __forceinline__ long long clock() { return clock64(); }
+  static __device__ __forceinline__ void prof_add(unsigned long long* p, long long v) { atomicAdd(p, (unsigned long long)v); }
   static __device__ __forceinline__ void pdl_launch() { pdl_launch_dependents(); }
   static __device__ __forceinline__ void pdl_sync() { pdl_wait(); }
   static __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }

@@ -227,7 +227,7 @@ class Voice:
 
     def profile_launches(self) -> list:
         """Every conv launch of the last profiled call, in order (tag, us, shape, algorithmic bytes / FLOP)."""
-        buf = C.create_string_buffer(1 << 17)
+        buf = C.create_string_buffer(1 << 19)
         check(self._lib.pb200_profile_read_launches(self._h, buf, len(buf)))
         return json.loads(buf.value.decode())
 

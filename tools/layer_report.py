@@ -2,6 +2,7 @@
 analytical bounds of tools/perf_model.py for the same shape (HBM, tcgen05 issue, weight streaming).
 
 usage: python tools/layer_report.py [--arch medium] [--batch 32] > gpurun_out/layer_report.txt   (JSON beside it)
+With PIPER_B200_PROF_ROLES=1 each tensor-core launch also reports where its warp roles waited.
 """
 import argparse, json, math, os, statistics, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -59,6 +60,11 @@ for i, r in enumerate(rows):
     if r["mma"] and "bound" in r:
         print(f"{i:3d} {r['tag']:8s} {r['ci']:4d} {r['rows']:5d} {r['k']:2d} {r['dil']:2d} {r['n_tile']:4d} {r['mt']:3d} {r['tiles']:6d} | {r['us']:7.1f} | "
               f"{r['t_hbm']:6.1f} {r['t_mma']:6.1f} {r['t_w']:6.1f} {r['t_tma']:6.1f} | {r['us'] / r['bound']:8.2f}")
+        if "roles" in r:   # PIPER_B200_PROF_ROLES=1: share of each role's loop spent waiting (conv2_body.inl, summed over CTAs)
+            q = r["roles"]
+            pc = lambda x, d: 100.0 * x / max(1, d)
+            print(f"      roles: MMA waits accumulator-free {pc(q[0], q[3]):4.0f}%  operands {pc(q[1], q[3]):4.0f}%  weights {pc(q[2], q[3]):4.0f}% | "
+                  f"epilogue waits accumulator {pc(q[4], q[5]):4.0f}% | converter waits raw {pc(q[6], q[8]):4.0f}%  free slot {pc(q[7], q[8]):4.0f}%")
         f = fam.setdefault(r["tag"], [0.0, 0.0, 0])
         f[0] += r["us"]; f[1] += r["bound"]; f[2] += 1
     else:
