@@ -443,10 +443,16 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   } else {
     // ---------------------------------------------------------------------- epilogue
     // The tensors an epilogue READS from global memory (the residual, the MRF / WaveNet-skip running sums) do not depend
-    // on the accumulator, so their loads are issued one work item ahead - the first item's before the accumulator is even
-    // waited for.  Measured on the B200 (profiles/r02_ncu_*): with the loads issued after tcgen05.ld, the 8 epilogue warps
-    // kept 16 KB in flight per SM and sat in `long scoreboard` for 45 % of all samples of the generator's 32-channel convs,
-    // holding the TMEM set (and through it the MMA warp and the converters) - 2.4 TB/s where HBM gives 6.5.
+    // on the accumulator, so their loads are issued ahead of their use - the first item's of a tile before the accumulator
+    // is even waited for (while the previous tile's last item is still being stored).  Measured on the B200
+    // (profiles/r02_ncu_*): with the loads issued after tcgen05.ld, the 8 epilogue warps kept 16 KB in flight per SM and
+    // sat in `long scoreboard` for 45 % of all samples of the generator's 32-channel convs, holding the TMEM set (and
+    // through it the MMA warp and the converters) - 2.4 TB/s where HBM gives 6.5.
+    // Order inside an item (second revision, from the per-instruction samples of the 64-channel ResBlock launches where
+    // this role paces the kernel): tcgen05.ld (both accumulators of a pair behind one wait) -> every use of the prefetched values -> the NEXT item's
+    // loads into the SAME registers -> stores.  The first revision prefetched into a second register set and copied it
+    // over at the end of the item: 32-48 moves per item, 32 more live registers, and the first item of every tile had
+    // nothing in flight while it waited.  Addresses are one 64-bit base per tensor and item plus i * (channel stride).
     const int ew = warp - C2_EPI_WARP0;                 // 0..7
     const int q = warp & 3, half = ew >> 2;             // TMEM lane quadrant is fixed by warp id % 4
     uint32_t t_it = 0;
@@ -459,41 +465,55 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const long long p_start = prof ? P::clock() : 0;
     const bool r_all = epi == EPI_RES || epi == EPI_MRF || epi == EPI_SUBFROM;     // residual for every row
     const bool o_all = epi == EPI_MRF && a.mrf != 0;                               // running MRF sum for every row
-    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
-      int nt, b, t0, L, Lq;
-      if (!decode(tile, nt, b, t0, L, Lq)) continue;
+    const bool any_aux = r_all || o_all || epi == EPI_WN;
+    const long long r_cs = a.r.cs, y_cs = a.y.cs, y2_cs = a.y2.cs;
+    const int my_chunks = (n_chunks - half + 1) / 2;    // this thread's chunks c = half, half + 2, ... of each live row half
+    // kind of auxiliary read of a 16-row chunk: bit 0 = residual rows (r), bit 1 = running-sum rows (y2)
+    auto aux_kind = [&](int row0) -> int {
+      if (epi == EPI_WN) return row0 + 16 <= a.split ? 1 : (row0 >= a.split && !a.first ? 2 : 0);
+      return (r_all ? 1 : 0) | (o_all ? 2 : 0);
+    };
+    // issue the auxiliary reads of work item wi of tile (nt, b, t0, Lq)
+    auto aux_issue = [&](int nt, int b, int t0, int Lq, int wi, float (&rv)[16], float (&ov)[16]) {
+      const int mh = wi >= my_chunks ? 1 : 0, c = half + 2 * (wi - mh * my_chunks);   // (work <= 2 * my_chunks)
+      const int t = t0 + mh * 128 + q * 32 + lane;
+      int item = b;
+      if (flat_tg ? !flat_live(t, item) : t >= Lq) return;
+      const int row0 = nt * NT + c * 16, kind = aux_kind(row0);
+      if (kind & 1) {
+        const float* pr = a.r.p + (long long)b * a.r.bs + (long long)row0 * r_cs + t;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rv[i] = pr[i * r_cs];
+      }
+      if (kind & 2) {
+        const int o0 = epi == EPI_WN ? row0 - a.split : row0;
+        const float* po = a.y2.p + (long long)b * a.y2.bs + (long long)o0 * y2_cs + t;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ov[i] = po[i * y2_cs];
+      }
+    };
+    // first live tile at or after `tile` (every role skips the same tiles); false: none left
+    auto next_live = [&](int& tile, int& nt, int& b, int& t0, int& L, int& Lq) -> bool {
+      for (; tile < tile_hi; tile += tile_step)
+        if (decode(tile, nt, b, t0, L, Lq)) return true;
+      return false;
+    };
+    float rv[16], ov[16];
+    int tile = tile_lo, nt, b, t0, L, Lq;
+    bool have = next_live(tile, nt, b, t0, L, Lq);
+    if (have && any_aux && ((Lq - t0 > 128 && MH > 1) ? 2 : 1) * my_chunks > 0) aux_issue(nt, b, t0, Lq, 0, rv, ov);
+    while (have) {
       const int mh_live = (Lq - t0 > 128 && MH > 1) ? 2 : 1;
       const int ts = t_it % t_slots;
       float* yb = a.y.p ? a.y.p + (long long)b * a.y.bs : nullptr;
       float* y2b = a.y2.p ? a.y2.p + (long long)b * a.y2.bs : nullptr;
       const float* rb = a.r.p ? a.r.p + (long long)b * a.r.bs : nullptr;
       const int n0 = nt * NT;
-      // this thread's share of the tile: chunks c = half, half+2, ... of each live row half
-      const int my_chunks = (n_chunks - half + 1) / 2;
       const int work = mh_live * my_chunks;
-      // kind of auxiliary read of a 16-row chunk: bit 0 = residual rows (r), bit 1 = running-sum rows (y2)
-      auto aux_kind = [&](int row0) -> int {
-        if (epi == EPI_WN) return row0 + 16 <= a.split ? 1 : (row0 >= a.split && !a.first ? 2 : 0);
-        return (r_all ? 1 : 0) | (o_all ? 2 : 0);
-      };
-      auto aux_issue = [&](int wi, float (&rv)[16], float (&ov)[16]) {
-        const int mh = wi >= my_chunks ? 1 : 0, c = half + 2 * (wi - mh * my_chunks);   // (work <= 2 * my_chunks)
-        const int t = t0 + mh * 128 + q * 32 + lane;
-        int item = b;
-        if (flat_tg ? !flat_live(t, item) : t >= Lq) return;
-        const int row0 = n0 + c * 16, kind = aux_kind(row0);
-        if (kind & 1) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) rv[i] = rb[(long long)(row0 + i) * a.r.cs + t];
-        }
-        if (kind & 2) {
-          const int o0 = epi == EPI_WN ? row0 - a.split : row0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) ov[i] = y2b[(long long)(o0 + i) * a.y2.cs + t];
-        }
-      };
-      float rv[16], ov[16];
-      if (work > 0) aux_issue(0, rv, ov);
+      // the tile after this one (its first auxiliary reads are issued from inside this tile's last item)
+      int tile_n = tile + tile_step, nt_n = 0, b_n = 0, t0_n = 0, L_n = 0, Lq_n = 0;
+      const bool have_n = next_live(tile_n, nt_n, b_n, t0_n, L_n, Lq_n);
+      const bool pre_n = have_n && any_aux && ((Lq_n - t0_n > 128 && MH > 1) ? 2 : 1) * my_chunks > 0;
       const long long pc = prof ? P::clock() : 0;
       P::mbar_wait(cx, &bar.t_full[ts], (t_it / t_slots) & 1);
       if (prof) pw_f += P::clock() - pc;
@@ -502,24 +522,32 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       for (int wi = 0; wi < work; ++wi) {
         const int mh = wi >= my_chunks ? 1 : 0, c = half + 2 * (wi - mh * my_chunks);   // (work <= 2 * my_chunks)
         const int t = t0 + mh * 128 + q * 32 + lane;
-        float rn[16], on[16];
-        if (wi + 1 < work) aux_issue(wi + 1, rn, on);    // the next item's reads fly while this one is finished
+        const int row0 = n0 + c * 16;
+        int item = b;
+        const bool live = flat_tg ? flat_live(t, item) : t < Lq;
         float v[16];
         const uint32_t tbase = d_set + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * a.mh_stride + c * 16);
-        P::tmem_ld16(cx, tbase, v);
-        for (int ai = 1; ai < n_acc; ++ai) {             // fp32 round-to-nearest combine of the partial sums
-          float p[16];
-          P::tmem_ld16(cx, tbase + (uint32_t)(ai * NT), p);
+        {                                                // fp32 round-to-nearest combine of the partial sums: (main | correction)
+          float p[16];                                   // pairs, both loads of a pair behind one wait
+          P::tmem_ld16x2(cx, tbase, tbase + (uint32_t)NT, v, p);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += p[i];
+          if (n_acc == 4) {
+            float p2[16];
+            P::tmem_ld16x2(cx, tbase + (uint32_t)(2 * NT), tbase + (uint32_t)(3 * NT), p, p2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += p[i];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += p2[i];
+          }
         }
         if (wi == work - 1) {                            // all of this thread's TMEM reads are done: release the set
           P::fence_tc_before();
           P::mbar_arrive(cx, &bar.t_empty[ts]);
         }
-        int item = b;
-        if (flat_tg ? flat_live(t, item) : t < Lq) {
-          const int row0 = n0 + c * 16;
+        // ---- everything that uses the prefetched values (v becomes what is stored); `dst` picks the destination
+        int dst = 0;                                     // 0: y rows row0.., 1: y2 rows row0.., 2: y2 rows row0 - split.., 3: special store
+        if (live) {
           if (a.bias) {
             if (bias_vec) {                                  // 16-byte aligned bias vector: four 128-bit loads
 #pragma unroll
@@ -536,23 +564,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += P::ldg(a.bias_item + (long long)item * a.bias_item_stride + row0 + i);
           }
-          if (epi == EPI_GATE) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 2)
-              yb[(long long)((row0 + i) >> 1) * a.y.cs + t] = wn_gate(v[i], v[i + 1]);
-          } else if (epi == EPI_UPSAMPLE) {
-            if (a.up == 8) store_upsampled<8>(v, yb, a.y.cs, row0, t, a.up_pad, L * 8);
-            else if (a.up == 4) store_upsampled<4>(v, yb, a.y.cs, row0, t, a.up_pad, L * 4);
-            else if (a.up == 2) store_upsampled<2>(v, yb, a.y.cs, row0, t, a.up_pad, L * 2);
-            else {
-              for (int i = 0; i < 16; ++i) {               // generic stride
-                const int row = row0 + i;
-                const int co = row / a.up, phi = row - co * a.up;
-                const int to = t * a.up + phi - a.up_pad;
-                if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = v[i];
-              }
-            }
-          } else if (epi == EPI_MRF) {
+          if (epi == EPI_MRF) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += rv[i];
             if (a.mrf == 1) {
@@ -565,49 +577,82 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = (ov[i] + v[i]) * inv_n;
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) y2b[(long long)(row0 + i) * a.y2.cs + t] = v[i];
+            dst = 1;
           } else if (epi == EPI_WN) {
             const int kind = aux_kind(row0);
             if (kind == 1) {                               // residual stream, in place
 #pragma unroll
-              for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = rv[i] + v[i];
+              for (int i = 0; i < 16; ++i) v[i] = rv[i] + v[i];
             } else if (row0 >= a.split) {                  // skip sum
+              if (kind == 2) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) y2b[(long long)(row0 - a.split + i) * a.y2.cs + t] = kind == 2 ? ov[i] + v[i] : v[i];
-            } else {                                       // a chunk that straddles the split (no real layer has one)
-              for (int i = 0; i < 16; ++i) {
-                const int row = row0 + i;
-                if (row < a.split) yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + v[i];
-                else {
-                  float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
-                  *o = a.first ? v[i] : *o + v[i];
-                }
+                for (int i = 0; i < 16; ++i) v[i] = ov[i] + v[i];
               }
+              dst = 2;
+            } else {
+              dst = 3;                                     // a chunk that straddles the split (no real layer has one)
             }
-          } else {
-            if (epi == EPI_RES) {
+          } else if (epi == EPI_RES) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += rv[i];
-            } else if (epi == EPI_SUBFROM) {
+            for (int i = 0; i < 16; ++i) v[i] += rv[i];
+          } else if (epi == EPI_SUBFROM) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = rv[i] - v[i];
-            } else if (epi == EPI_RELU) {
+            for (int i = 0; i < 16; ++i) v[i] = rv[i] - v[i];
+          } else if (epi == EPI_RELU) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) yb[(long long)(row0 + i) * a.y.cs + t] = v[i];
+            for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
           }
         }
+        // ---- the next item's reads, into the registers that were just consumed: they fly during the stores below and
+        // the next tcgen05.ld (the next item may be the first one of the next tile)
+        {
+          const bool more = wi + 1 < work;               // (one call site: the instruction footprint of this role matters)
+          if (more ? any_aux : pre_n) aux_issue(more ? nt : nt_n, more ? b : b_n, more ? t0 : t0_n, more ? Lq : Lq_n, more ? wi + 1 : 0, rv, ov);
+        }
+        // ---- stores
+        if (live) {
+          if (epi == EPI_GATE) {
+            float* py = yb + (long long)(row0 >> 1) * y_cs + t;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { rv[i] = rn[i]; ov[i] = on[i]; }
+            for (int i = 0; i < 16; i += 2) py[(i >> 1) * y_cs] = wn_gate(v[i], v[i + 1]);
+          } else if (epi == EPI_UPSAMPLE) {
+            if (a.up == 8) store_upsampled<8>(v, yb, a.y.cs, row0, t, a.up_pad, L * 8);
+            else if (a.up == 4) store_upsampled<4>(v, yb, a.y.cs, row0, t, a.up_pad, L * 4);
+            else if (a.up == 2) store_upsampled<2>(v, yb, a.y.cs, row0, t, a.up_pad, L * 2);
+            else {
+              for (int i = 0; i < 16; ++i) {               // generic stride
+                const int row = row0 + i;
+                const int co = row / a.up, phi = row - co * a.up;
+                const int to = t * a.up + phi - a.up_pad;
+                if (to >= 0 && to < L * a.up) yb[(long long)co * a.y.cs + to] = v[i];
+              }
+            }
+          } else if (dst == 3) {
+            for (int i = 0; i < 16; ++i) {
+              const int row = row0 + i;
+              if (row < a.split) yb[(long long)row * a.y.cs + t] = rb[(long long)row * a.r.cs + t] + v[i];
+              else {
+                float* o = y2b + (long long)(row - a.split) * a.y2.cs + t;
+                *o = a.first ? v[i] : *o + v[i];
+              }
+            }
+          } else if (dst == 0) {
+            float* py = yb + (long long)row0 * y_cs + t;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) py[i * y_cs] = v[i];
+          } else {
+            float* py = y2b + (long long)(dst == 2 ? row0 - a.split : row0) * y2_cs + t;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) py[i * y2_cs] = v[i];
+          }
+        }
       }
       if (work == 0) {                                   // a 16-row tile leaves the odd half of the warps without a chunk:
         P::fence_tc_before();                            // they still owe the accumulator set their arrival
         P::mbar_arrive(cx, &bar.t_empty[ts]);
       }
       ++t_it;
+      tile = tile_n; nt = nt_n; b = b_n; t0 = t0_n; L = L_n; Lq = Lq_n; have = have_n;
     }
     if (prof) { P::prof_add(a.prof + 4, pw_f); P::prof_add(a.prof + 5, P::clock() - p_start); }
   }

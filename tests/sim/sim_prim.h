@@ -326,6 +326,10 @@ struct SimPrim {
     ++c.cta->aligned_ops[c.tid_];
     for (int i = 0; i < 16; ++i) v[i] = c.cta->tmem[lane0 + (c.tid_ & 31)][col + i];
   }
+  static void tmem_ld16x2(Ctx& c, uint32_t taddr0, uint32_t taddr1, float (&v)[16], float (&w)[16]) {
+    tmem_ld16(c, taddr0, v);
+    tmem_ld16(c, taddr1, w);
+  }
   static void tmem_st16(Ctx& c, uint32_t taddr, const float* v) {
     const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFFu;
     check(c, lane0 == 32u * ((c.tid_ >> 5) & 3), "tcgen05.st outside the warp's TMEM lane quadrant (warp id % 4)");
