@@ -45,6 +45,7 @@ struct Args {
   int H = 0, dk = 0, n_heads = 0, q_tiles = 0;
   int tm = 0;                             // 1: q / k / v windows by tensor-map TMA (tmq: box [dk][136], tmk: box [dk][72])
   int flat = 0;                           // with tm: qkv is laid out [channel][item][slot] -> coordinates (t, item, channel)
+  int tail_thr = 0;                       // > 0: the LAST query tile of an utterance is left to the CUDA-core kernel when it holds <= tail_thr rows (encoder.cu)
 };
 
 // tensor-map descriptors of the qkv view for the two boxes (host side; shared with the CPU model)
@@ -120,7 +121,10 @@ MRF_FN void att_body(const Args& a, typename P::Ctx& cx, uint8_t* smem, Barriers
   float* Ev = reinterpret_cast<float*>(smem + off_ev(dk));
   const int q_part = G * A_QT * 16, p_part = (A_KB / 8) * A_QT * 16;
   const int n_blk = (T + A_KB - 1) / A_KB;
-  const bool active = q0 < T;                          // uniform per CTA: a tile past the utterance has nothing to do
+  // uniform per CTA: a tile past the utterance has nothing to do; neither has a short last tile that the launcher gave to
+  // the CUDA-core kernel (a 259-id utterance is two full tiles + 3 rows, and a 3-row tile costs a CTA as much as a full one:
+  // 32 utterances x 2 heads x 3 tiles = 192 CTAs on 148 SMs were two waves)
+  const bool active = q0 < T && !(a.tail_thr > 0 && q0 > 0 && T - q0 <= a.tail_thr);
 
   if (warp == 1) P::tmem_alloc(cx, tmem_base_s, 512u);
   if (tid == 0) {

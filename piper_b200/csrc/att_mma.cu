@@ -30,13 +30,22 @@ __global__ void __launch_bounds__(att::A_THREADS, 1) att_kernel(const __grid_con
 
 // false: shape outside what the kernel handles (caller keeps the CUDA-core kernel)
 bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
-                             const int* len, int B, int Tmax, cudaStream_t st) {
+                             const int* len, int B, int Tmax, cudaStream_t st, int* tail_thr) {
+  if (tail_thr) *tail_thr = 0;
   if (B <= 0 || Tmax <= 0) return true;
   const int dk = H / n_heads;
   if (window != 4 || dk % 16 != 0 || dk > att::A_MAXDK || dk * n_heads != H) return false;
   att::Args a;
   a.qkv = qkv; a.out = out; a.rel_k = rel_k; a.rel_v = rel_v; a.len = len;
   a.H = H; a.dk = dk; a.n_heads = n_heads; a.q_tiles = (Tmax + att::A_QT - 1) / att::A_QT;
+  // More tiles than SMs (one CTA per SM): short last tiles go to the CUDA-core kernel, which the caller launches behind
+  // this one (PIPER_B200_ATT_TAIL=0 keeps every tile here)
+  static int g_tail = -1;
+  if (g_tail < 0) {
+    const char* e = std::getenv("PIPER_B200_ATT_TAIL");
+    g_tail = e ? std::atoi(e) : 32;
+  }
+  if (tail_thr && g_tail > 0 && a.q_tiles >= 2 && (long long)a.q_tiles * n_heads * B > 148) a.tail_thr = *tail_thr = g_tail;
   const int smem = att::smem_bytes(dk) + 128;
   static int g_tm = -1;                                   // PIPER_B200_ATT_TM: tensor-map loads of the q / k / v windows (default on)
   if (g_tm < 0) {

@@ -20,11 +20,11 @@ namespace conv2 {
 constexpr int C2_CONV_WARP0 = 3, C2_CONV_THREADS = 128;
 constexpr int C2_EPI_WARP0 = 7, C2_EPI_THREADS = 256;
 constexpr int C2_THREADS = 32 * 15;
-constexpr int C2_RAW_SLOTS = 2, C2_A_SLOTS = 2, C2_W_SLOTS = 4, C2_T_SLOTS = 2;
+constexpr int C2_RAW_SLOTS = 2, C2_A_SLOTS_MAX = 12, C2_W_SLOTS = 4, C2_T_SLOTS = 2;   // (operand slots per launch: MmaConvArgs::a_slots, 2 .. 12)
 
 template <class Mbar>
 struct Barriers {
-  Mbar raw_full[C2_RAW_SLOTS], raw_empty[C2_RAW_SLOTS], a_full[C2_A_SLOTS], a_empty[C2_A_SLOTS], w_full[C2_W_SLOTS],
+  Mbar raw_full[C2_RAW_SLOTS], raw_empty[C2_RAW_SLOTS], a_full[C2_A_SLOTS_MAX], a_empty[C2_A_SLOTS_MAX], w_full[C2_W_SLOTS],
       w_empty[C2_W_SLOTS], t_full[C2_T_SLOTS], t_empty[C2_T_SLOTS];
 };
 
@@ -77,7 +77,9 @@ MRF_FN void store_upsampled(const float (&v)[16], float* yb, int cs, int row0, i
 
 // TM: the activation rows of a channel chunk arrive as one tensor-map TMA copy (cp.async.bulk.tensor.3d, box
 // [KC channels][R / boxes columns], any start column, out-of-bounds zero filled) instead of KC per-row bulk copies.
-template <class P, int PREC, int MT, bool TM = false>
+// ASLOTS: operand-ring slots, 2 = the streaming ring (compile-time), 0 = one slot per channel chunk of a position
+// (MmaConvArgs::a_slots, A-stationary launches)
+template <class P, int PREC, int MT, bool TM = false, int ASLOTS = 2>
 MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem, Barriers<typename P::Mbar>& bar,
                        uint32_t* tmem_base_s, const typename P::TensorMap* tmx = nullptr) {
   constexpr bool TF32 = PREC == PREC_TF32;
@@ -94,7 +96,8 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   const uint32_t unit_bytes = (uint32_t)(KC / E) * 2u * (uint32_t)NT * 16u;       // one (chunk, tap): stacked hi | lo rows
   uint8_t* RAW_ring = smem;
   uint8_t* A_ring = RAW_ring + size_t(C2_RAW_SLOTS) * raw_bytes;
-  uint8_t* W_ring = A_ring + size_t(C2_A_SLOTS) * 2 * a_part;
+  const int a_slots = ASLOTS > 0 ? ASLOTS : (a.a_slots < 2 ? 2 : (a.a_slots > C2_A_SLOTS_MAX ? C2_A_SLOTS_MAX : a.a_slots));   // operand ring: 2, or every chunk of a position (A-stationary)
+  uint8_t* W_ring = A_ring + size_t(a_slots) * 2 * a_part;
   const int n_kc = a.ci / KC;
   const int n_units = n_kc * a.k;
   const int tpi = a.tiles_per_item, total = a.total_tiles;
@@ -105,7 +108,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   if (warp == 2) P::tmem_alloc(cx, tmem_base_s, (uint32_t)a.tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < C2_RAW_SLOTS; ++i) { P::mbar_init(cx, &bar.raw_full[i], 1); P::mbar_init(cx, &bar.raw_empty[i], C2_CONV_THREADS); }
-    for (int i = 0; i < C2_A_SLOTS; ++i) { P::mbar_init(cx, &bar.a_full[i], C2_CONV_THREADS); P::mbar_init(cx, &bar.a_empty[i], 1); }
+    for (int i = 0; i < a_slots; ++i) { P::mbar_init(cx, &bar.a_full[i], C2_CONV_THREADS); P::mbar_init(cx, &bar.a_empty[i], 1); }
     for (int i = 0; i < C2_W_SLOTS; ++i) { P::mbar_init(cx, &bar.w_full[i], 1); P::mbar_init(cx, &bar.w_empty[i], 1); }
     for (int i = 0; i < C2_T_SLOTS; ++i) { P::mbar_init(cx, &bar.t_full[i], 1); P::mbar_init(cx, &bar.t_empty[i], C2_EPI_THREADS); }
     P::fence_mbar_init();
@@ -245,7 +248,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
     const uint32_t a_lbo = (uint32_t)R * 16, w_lbo = 2u * (uint32_t)NT * 16;
     const uint32_t idesc2 = make_idesc(PREC, 128, 2 * NT), idesc1 = make_idesc(PREC, 128, NT);
     const uint32_t a_step = 2u * (uint32_t)R, w_step = 4u * (uint32_t)NT;          // 16-byte units per k-step
-    uint32_t a_it = 0, w_it = 0, t_it = 0;
+    uint32_t a_slot = 0, a_round = 0, w_it = 0, t_it = 0;
     // optional per-role wait counters (a.prof, developer diagnostic): cycles the MMA warp waits for [0] the TMEM set,
     // [1] an operand chunk, [2] a weight unit, and [3] its whole loop; [4] epilogue waiting for an accumulator, [5] its loop;
     // [6] converters waiting for raw data, [7] for a free operand slot, [8] their loop
@@ -268,12 +271,10 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       uint32_t started = 0;
       int u = 0;
       const bool g_first = group_first(tile), g_last = group_last(tile);
-      const uint32_t a_base = a_it;                                    // operand-ring position of this group's first chunk
+      uint32_t as = a_slot, a_par = a_round;                           // operand-ring slot / round of this group's first chunk
       for (int kc = 0; kc < n_kc; ++kc) {
-        const uint32_t a_idx = a_base + (uint32_t)kc;
-        const int as = a_idx % C2_A_SLOTS;
         pc = prof ? P::clock() : 0;
-        if (g_first) P::mbar_wait(cx, &bar.a_full[as], (a_idx / C2_A_SLOTS) & 1);   // (a later tile of the group: still resident)
+        if (g_first) P::mbar_wait(cx, &bar.a_full[as], a_par & 1);     // (a later tile of the group: still resident)
         if (prof) pw_a += P::clock() - pc;
         P::fence_tc_after();
         const uint32_t a_hi = P::saddr(cx, A_ring + size_t(as) * 2 * a_part);
@@ -345,8 +346,9 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
           if (P::elect_one(cx)) P::mma_commit(cx, &bar.a_empty[as]);
           P::syncwarp();
         }
+        if (++as == (uint32_t)a_slots) { as = 0; ++a_par; }
       }
-      if (g_last) a_it += (uint32_t)n_kc;
+      if (g_last) { a_slot = as; a_round = a_par; }
       if (P::elect_one(cx)) P::mma_commit(cx, &bar.t_full[ts]);
       P::syncwarp();
       ++t_it;
@@ -358,7 +360,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
   } else if (warp < C2_EPI_WARP0) {
     // ---------------------------------------------------------------------- converters
     const int ctid = tid - C2_CONV_WARP0 * 32;
-    uint32_t raw_it = 0, a_it = 0;
+    uint32_t raw_it = 0, as = 0, a_round = 0;                           // next operand slot and how often the ring has wrapped
     const bool prof = a.prof != nullptr && ctid == 0;
     long long pw_r = 0, pw_e = 0;
     const long long p_start = prof ? P::clock() : 0;
@@ -368,12 +370,12 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
       const int t_lo = t0 - a.pad;
       const int off = t_lo - (t_lo & ~3);                               // smem column of stage row 0
       const int Wb = TM ? RS / a.tm_boxes : RS;                         // TM: dense boxes [box][KC][Wb]
-      for (int kc = 0; kc < n_kc; ++kc, ++raw_it, ++a_it) {
-        const int rs = raw_it % C2_RAW_SLOTS, as = a_it % C2_A_SLOTS;
+      for (int kc = 0; kc < n_kc; ++kc, ++raw_it) {
+        const int rs = raw_it % C2_RAW_SLOTS;
         long long pc = prof ? P::clock() : 0;
         P::mbar_wait(cx, &bar.raw_full[rs], (raw_it / C2_RAW_SLOTS) & 1);
         if (prof) { const long long n = P::clock(); pw_r += n - pc; pc = n; }
-        if (a_it >= C2_A_SLOTS) P::mbar_wait(cx, &bar.a_empty[as], ((a_it / C2_A_SLOTS) - 1) & 1);
+        if (a_round > 0) P::mbar_wait(cx, &bar.a_empty[as], (a_round - 1) & 1);
         if (prof) pw_e += P::clock() - pc;
         const float* raw = reinterpret_cast<const float*>(RAW_ring + size_t(rs) * raw_bytes) + off;
         uint8_t* A_hi = A_ring + size_t(as) * 2 * a_part;
@@ -437,6 +439,7 @@ MRF_FN void conv2_body(const MmaConvArgs& a, typename P::Ctx& cx, uint8_t* smem,
         P::fence_async_proxy();
         P::mbar_arrive(cx, &bar.a_full[as]);
         P::mbar_arrive(cx, &bar.raw_empty[rs]);
+        if (++as == (uint32_t)a_slots) { as = 0; ++a_round; }
       }
     }
     if (prof) { P::prof_add(a.prof + 6, pw_r); P::prof_add(a.prof + 7, pw_e); P::prof_add(a.prof + 8, P::clock() - p_start); }

@@ -169,7 +169,9 @@ inline void pack(const float* wsrc, int ci, int k, int rows_p, const Plan& p, ui
 // plan -> the tiling fields of the launch arguments; returns the grid size (0: nothing to do)
 // tm: stage the activation rows with one tensor-map TMA copy per channel chunk (two when the staged window is wider than
 // the 256-element box limit) instead of one bulk copy per channel row; `td` then describes the tensor and the box.
-inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm = false, TmapDesc* td = nullptr, bool astat_ok = false) {
+constexpr size_t kAstatSmem = size_t(212) << 10;
+inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm = false, TmapDesc* td = nullptr, bool astat_ok = false,
+                     size_t* smem_out = nullptr) {
   a.n_tile = p.n_tile; a.acc_cols = p.n_tile; a.chains = p.chains; a.mh_stride = p.mh_stride; a.sep_corr = 0;
   a.kc = p.kc; a.stage_rows = p.stage_rows; a.raw_stride = p.raw_stride; a.t_slots = p.t_slots; a.tmem_cols = p.tmem_cols;
   a.chains = std::min(p.chains, (a.ci / p.kc) * a.k);          // never more chains than weight units
@@ -200,9 +202,35 @@ inline int fill_args(MmaConvArgs& a, const Plan& p, int B, int max_len, bool tm 
     a.chains = std::min(p.chains, (a.ci / a.kc) * a.k);
   }
   // A-stationary order where it pays and is possible: several output-row tiles per position, and every channel chunk of a
-  // position resident in the two-slot operand ring at once
+  // position resident in the operand ring at once.  The ring then gets one slot per chunk (a_slots = C_in / kc <= 12) and
+  // the chunk size is re-chosen so that raw staging (2 slots) + the whole converted window + the weight ring (4 slots)
+  // fit kAstatSmem; the window is converted ONCE per position instead of once per output-row tile (9x for the q|k|v conv,
+  // 12x for the first FFN conv: the role waits showed the MMA warp waiting for operands 40 % of those launches).
   a.n_tiles = p.n_tiles;
-  a.astat = (astat_ok && p.n_tiles > 1 && a.ci / a.kc <= 2) ? 1 : 0;
+  a.a_slots = 2;
+  a.astat = 0;
+  if (smem_out) *smem_out = p.smem;
+  if (astat_ok && p.n_tiles > 1) {
+    const int es = p.tf32 ? 4 : 2, kstep = p.tf32 ? 8 : 16;
+    int pick = 0;
+    for (int c = a.ci; c >= kstep; c -= kstep) {
+      if (a.ci % c) continue;
+      const int n_kc = a.ci / c;
+      if (n_kc > 12) break;
+      const size_t bytes = size_t(2) * c * p.raw_stride * 4 + size_t(2) * a.ci * p.stage_rows * es + size_t(4) * c * 2 * p.n_tile * es;
+      if (bytes > kAstatSmem) continue;
+      pick = c;
+      if (n_kc >= 4) break;                                // enough chunks for load / convert / MMA to overlap inside a position
+    }
+    if (pick) {
+      a.kc = pick;
+      a.a_slots = std::max(2, a.ci / pick);
+      a.astat = 1;
+      a.chains = std::min(p.chains, (a.ci / a.kc) * a.k);
+      if (smem_out)
+        *smem_out = size_t(2) * pick * p.raw_stride * 4 + size_t(a.a_slots) * 2 * pick * p.stage_rows * es + size_t(4) * pick * 2 * p.n_tile * es;
+    }
+  }
   a.tm_boxes = 0;
   if (tm && td) {
     // the innermost start coordinate of a tiled tensor copy must be 16-byte aligned (an unaligned one is an illegal

@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(conv2::C2_THREADS, 1) conv2_kernel(const __gri
 
 // Tensor-map variant (PIPER_B200_V2_TM=1): the activation window of a channel chunk is one cp.async.bulk.tensor copy.
 // The dynamic shared memory is re-aligned to 128 bytes by hand (tensor copies require it; the launcher adds the slack).
-template <int PREC, int MT>
+// ASLOTS = 0: the A-stationary instantiation (operand ring with one slot per channel chunk, MmaConvArgs::a_slots)
+template <int PREC, int MT, int ASLOTS = 2>
 __global__ void __launch_bounds__(conv2::C2_THREADS, 1) conv2_tm_kernel(const __grid_constant__ MmaConvArgs a,
                                                                         const __grid_constant__ CUtensorMap tmx) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(conv2::C2_THREADS, 1) conv2_tm_kernel(const __
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u);
   DevPrim::Ctx cx;
-  conv2::conv2_body<DevPrim, PREC, MT, true>(a, cx, smem, bar, &tmem_base_s, &tmx);
+  conv2::conv2_body<DevPrim, PREC, MT, true, ASLOTS>(a, cx, smem, bar, &tmem_base_s, &tmx);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
@@ -118,17 +119,22 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   TmapDesc td;
   CUtensorMap tmx;
   bool tm = g_tm != 0;
-  // PIPER_B200_V2_ASTAT=1: A-stationary tile order (conv2_body.inl).  Measured on the B200: 447.9 vs 448.4 M samples/s -
-  // the layers with several output-row tiles per position are not bound by re-converting their activations - so off by default.
+  // PIPER_B200_V2_ASTAT (default 1): A-stationary tile order with the whole converted window of a position resident
+  // (conv2_body.inl, conv2_host.h).  The first version kept the two-slot ring and so applied to almost no layer (447.9 vs
+  // 448.4 M samples/s); with one slot per channel chunk: 512.0 vs 493.4 M samples/s on the same box (first FFN conv 59 ->
+  // 45 us, second upsampler 238 -> 168 us).
   static int g_astat = -1;
   if (g_astat < 0) {
     const char* e = std::getenv("PIPER_B200_V2_ASTAT");
-    g_astat = e ? (std::atoi(e) != 0) : 0;
+    g_astat = e ? (std::atoi(e) != 0) : 1;
   }
-  int grid = conv2::fill_args(a, p, B, max_len, tm, &td, g_astat != 0);
+  size_t smem = p.smem;                                 // (the A-stationary plan re-sizes the rings)
+  int grid = conv2::fill_args(a, p, B, max_len, tm, &td, g_astat != 0, &smem);
   if (tm && !encode_tmap(td, &tmx)) {                    // (a view the encoder refuses: fall back to per-row copies)
     tm = false;
-    grid = conv2::fill_args(a, p, B, max_len, false, nullptr, g_astat != 0);
+    grid = conv2::fill_args(a, p, B, max_len, false, nullptr, false, &smem);
+  } else if (!tm && a.astat) {
+    grid = conv2::fill_args(a, p, B, max_len, false, nullptr, false, &smem);   // (the A-stationary instantiations exist for the tensor-map kernel only)
   }
   static int g_small_too = -1;                          // PIPER_B200_V2=2: also take launches with fewer tiles than SMs
   if (g_small_too < 0) {
@@ -140,20 +146,35 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(conv2_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_tm_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_tm_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_tm_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_tm_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(conv2_tm_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<0, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<0, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<1, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<2, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    cudaFuncSetAttribute(conv2_tm_kernel<2, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
     attr_set[dev & 63] = true;
   }
+  if (tm && a.astat) {
+    const size_t sm = smem + 128;
+    if (p.prec == 1) launch_k(conv2_tm_kernel<1, 128, 0>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else if (p.prec == 2 && p.mt == 256) launch_k(conv2_tm_kernel<2, 256, 0>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else if (p.prec == 2) launch_k(conv2_tm_kernel<2, 128, 0>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else if (p.mt == 256) launch_k(conv2_tm_kernel<0, 256, 0>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    else launch_k(conv2_tm_kernel<0, 128, 0>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
+    count_launch();
+    return true;
+  }
   if (tm) {
-    const size_t sm = p.smem + 128;
+    const size_t sm = smem + 128;
     if (p.prec == 1) launch_k(conv2_tm_kernel<1, 128>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
     else if (p.prec == 2 && p.mt == 256) launch_k(conv2_tm_kernel<2, 256>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
     else if (p.prec == 2) launch_k(conv2_tm_kernel<2, 128>, dim3(grid), dim3(conv2::C2_THREADS), sm, st, a, tmx);
@@ -162,11 +183,11 @@ bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaSt
     count_launch();
     return true;
   }
-  if (p.prec == 1) launch_k(conv2_kernel<1, 128>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
-  else if (p.prec == 2 && p.mt == 256) launch_k(conv2_kernel<2, 256>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
-  else if (p.prec == 2) launch_k(conv2_kernel<2, 128>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
-  else if (p.mt == 256) launch_k(conv2_kernel<0, 256>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
-  else launch_k(conv2_kernel<0, 128>, dim3(grid), dim3(conv2::C2_THREADS), p.smem, st, a);
+  if (p.prec == 1) launch_k(conv2_kernel<1, 128>, dim3(grid), dim3(conv2::C2_THREADS), smem, st, a);
+  else if (p.prec == 2 && p.mt == 256) launch_k(conv2_kernel<2, 256>, dim3(grid), dim3(conv2::C2_THREADS), smem, st, a);
+  else if (p.prec == 2) launch_k(conv2_kernel<2, 128>, dim3(grid), dim3(conv2::C2_THREADS), smem, st, a);
+  else if (p.mt == 256) launch_k(conv2_kernel<0, 256>, dim3(grid), dim3(conv2::C2_THREADS), smem, st, a);
+  else launch_k(conv2_kernel<0, 128>, dim3(grid), dim3(conv2::C2_THREADS), smem, st, a);
   count_launch();
   return true;
 }

@@ -184,13 +184,19 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, 
 static_assert(ATT_QPW == 4, "rel_attention_kernel2 packs the four queries of a warp into one float4");
 __global__ void __launch_bounds__(256) rel_attention_kernel2(View qkv, View out, const float* __restrict__ rel_k,
                                                             const float* __restrict__ rel_v, int H, int dk, int window,
-                                                            const int* __restrict__ len) {
+                                                            const int* __restrict__ len, int tail_thr) {
   pdl_launch_dependents();   // programmatic dependent launch (launch.cuh): the next grid may be scheduled now;
   pdl_wait();                // nothing below runs before the previous grid has completed
   extern __shared__ float sm[];
   const int b = blockIdx.z, h = blockIdx.y;
   const int T = len[b];
-  const int i0 = blockIdx.x * ATT_Q;
+  int i0 = blockIdx.x * ATT_Q;
+  if (tail_thr > 0) {
+    // tail mode: only the rows of a short last 128-query tile, which the tensor-core kernel (att_body.inl) skipped
+    const int q0 = ((T - 1) / 128) * 128;
+    if (T <= 0 || q0 == 0 || T - q0 > tail_thr) return;
+    i0 += q0;
+  }
   if (i0 >= T) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nrel = 2 * window + 1;
@@ -544,14 +550,27 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
     const char* e = std::getenv("PIPER_B200_ATT3");
     g_att3 = e ? std::atoi(e) : 1;                       // default since round 2: tcgen05 attention (0 = CUDA-core kernel)
   }
-  if (g_att3 && launch_rel_attention_tc(qkv, out, rel_k, rel_v, H, n_heads, window, len, B, Tmax, st)) return;
+  int tail_thr = 0;
+  if (g_att3 && launch_rel_attention_tc(qkv, out, rel_k, rel_v, H, n_heads, window, len, B, Tmax, st, &tail_thr)) {
+    if (tail_thr > 0) {                                  // short last tiles: the CUDA-core kernel, one CTA per ATT_Q rows
+      static bool attr2[64] = {};
+      if (!attr2[dev & 63]) {
+        cudaFuncSetAttribute(rel_attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr2[dev & 63] = true;
+      }
+      launch_k(rel_attention_kernel2, dim3((tail_thr + ATT_Q - 1) / ATT_Q, n_heads, B), dim3(256), smem, st, qkv, out, rel_k, rel_v, H,
+               dk, window, len, tail_thr);
+      count_launch();
+    }
+    return;
+  }
   static int g_att2 = -1;
   if (g_att2 < 0) {
     const char* e = std::getenv("PIPER_B200_ATT2");
     g_att2 = e ? std::atoi(e) : 1;                       // default since round 2 (measured +; 0 = first version)
     if (g_att2) cudaFuncSetAttribute(rel_attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
-  if (g_att2) launch_k(rel_attention_kernel2, dim3(grid), dim3(256), smem, st, qkv, out, rel_k, rel_v, H, dk, window, len);
+  if (g_att2) launch_k(rel_attention_kernel2, dim3(grid), dim3(256), smem, st, qkv, out, rel_k, rel_v, H, dk, window, len, 0);
   else launch_k(rel_attention_kernel, dim3(grid), dim3(256), smem, st, qkv, out, rel_k, rel_v, H, dk, window, len);
   count_launch();
 }

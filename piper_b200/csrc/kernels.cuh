@@ -170,7 +170,7 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
 
 // EXPERIMENTAL, off by default (PIPER_B200_ATT3=1): the same attention on the tensor cores (att_mma.cu); false = shape not handled
 bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
-                             const int* len, int B, int Tmax, cudaStream_t st);
+                             const int* len, int B, int Tmax, cudaStream_t st, int* tail_thr = nullptr);
 
 enum LnMode {
   LN_ADD = 0,          // y = LN(a + b)

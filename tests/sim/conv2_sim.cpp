@@ -66,20 +66,28 @@ extern "C" int conv2_sim_run(const float* x, const float* w, const float* bias, 
     const bool tm = (desc[25] & 4) != 0;                 // opts bit 2: tensor-map TMA for the activation window
     a.mma3 = (desc[25] & 8) ? 1 : 0;                     // opts bit 3: three instructions per k-step on matching accumulator regions
     TmapDesc td;
-    int grid = conv2::fill_args(a, p, launch_B, max_len, tm, &td, (desc[25] & 32) != 0);   // opts bit 5: A-stationary order
+    size_t smem_bytes = p.smem;
+    int grid = conv2::fill_args(a, p, launch_B, max_len, tm, &td, (desc[25] & 32) != 0, &smem_bytes);   // opts bit 5: A-stationary order
+    if (!tm && a.astat) grid = conv2::fill_args(a, p, launch_B, max_len, false, nullptr, false, &smem_bytes);   // as the launcher: A-stationary needs the tensor-map kernel
     if (desc[23] > 0) grid = std::min(grid, desc[23]);
     if (info) {
       info[0] = p.n_tile; info[1] = p.n_tiles; info[2] = p.mt; info[3] = p.kc; info[4] = p.t_slots; info[5] = a.chains;
-      info[6] = a.total_tiles; info[7] = (int)p.smem;
+      info[6] = a.total_tiles; info[7] = (int)smem_bytes;
     }
     for (int block = 0; block < grid; ++block) {
       std::unique_ptr<SimCta> cta(new SimCta);
-      SmemBuf smem(p.smem);
-      cta->smem = smem.p; cta->smem_bytes = (int)p.smem; cta->control_warps = conv2::C2_CONV_WARP0;
+      SmemBuf smem(smem_bytes);
+      cta->smem = smem.p; cta->smem_bytes = (int)smem_bytes; cta->control_warps = conv2::C2_CONV_WARP0;
       for (auto& row : cta->tmem) for (float& v : row) v = std::numeric_limits<float>::quiet_NaN();
       std::unique_ptr<conv2::Barriers<SimMbar>> bar(new conv2::Barriers<SimMbar>);
       const std::string e = run_cta(*cta, conv2::C2_THREADS, block, grid, [&](SimPrim::Ctx& cx) {
-        if (tm) {
+        if (tm && a.astat) {                             // the A-stationary instantiation: operand ring sized at run time
+          if (tf32) conv2::conv2_body<SimPrim, 1, 128, true, 0>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else if (prec == 2 && p.mt == 256) conv2::conv2_body<SimPrim, 2, 256, true, 0>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else if (prec == 2) conv2::conv2_body<SimPrim, 2, 128, true, 0>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else if (p.mt == 256) conv2::conv2_body<SimPrim, 0, 256, true, 0>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+          else conv2::conv2_body<SimPrim, 0, 128, true, 0>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
+        } else if (tm) {
           if (tf32) conv2::conv2_body<SimPrim, 1, 128, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
           else if (prec == 2 && p.mt == 256) conv2::conv2_body<SimPrim, 2, 256, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);
           else if (prec == 2) conv2::conv2_body<SimPrim, 2, 128, true>(a, cx, cta->smem, *bar, &cta->tmem_base, &td);

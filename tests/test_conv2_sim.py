@@ -412,11 +412,14 @@ def test_flat_mode_tiles_on_the_concatenated_time_axis(sim, prec, ci, rows, k, d
 @pytest.mark.parametrize("prec,ci,rows,k,dil,epi,lens,grid", [(2, 192, 576, 1, 1, "BIAS", (259, 130), 3),    # q|k|v: 5 output-row tiles per position, two chunks
                                                                (2, 64, 256, 5, 1, "RES", (300, 37), 2),        # one chunk (both ring slots alternate between positions)
                                                                (1, 96, 384, 3, 1, "RELU", (140,), 5),          # more CTAs than positions: groups split across CTAs
-                                                               (2, 192, 384, 5, 1, "GATE", (131, 259), 4)])
+                                                               (2, 192, 384, 5, 1, "GATE", (131, 259), 4),
+                                                               (2, 192, 768, 3, 1, "RELU", (259, 130, 40), 2),  # first FFN conv: 12 output-row tiles, 4 resident chunks, several groups per CTA
+                                                               (2, 256, 512, 3, 1, "BIAS", (150,), 1)])         # 256 channels: the window does not fit, the default order runs
 def test_a_stationary_tile_order(sim, prec, ci, rows, k, dil, epi, lens, grid):
     """opts bit 5: the output-row tiles of a position are consecutive tiles of one CTA; the activation window is loaded and
-    converted once per position and stays in the operand ring until the group's last tile - same numbers as the default
-    order (bit-identical: same operands, same accumulation order), with and without the flat layout / tensor-map loads."""
+    converted once per position and stays in the operand ring (one slot per channel chunk) until the group's last tile -
+    same numbers as the default order up to the summation order inside the tensor core (the chunk size is re-chosen so that
+    the whole window fits), with and without the flat layout / tensor-map loads."""
     B = len(lens)
     x, clean = _ragged(B, ci, lens, seed=ci + rows)
     rng = np.random.default_rng(8)
@@ -429,7 +432,8 @@ def test_a_stationary_tile_order(sim, prec, ci, rows, k, dil, epi, lens, grid):
     for opts in (32, 32 | 4):
         y, _, info = _run(sim, x, w, bias, lens, opts=opts, **kw)
         for b, L in enumerate(lens):
-            assert np.array_equal(y[b, :, :L], y_ref[b, :, :L]), (opts, b, info)
+            scale = max(1.0, float(np.abs(y_ref[b, :, :L]).max()))
+            assert float(np.abs(y[b, :, :L] - y_ref[b, :, :L]).max()) <= 2e-6 * scale, (opts, b, info)
             assert np.all(y[b, :, L:] == 7e7)
     for b, L in enumerate(lens):                                  # and the default order is right in the first place
         ref = _ref_conv(clean[b], w, bias, dil, (k - 1) // 2 * dil, kw["pre"], 0.1)

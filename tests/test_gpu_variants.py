@@ -118,7 +118,7 @@ print("RESULT " + json.dumps(out))
                                  {"PIPER_B200_V2_MMA3": "1"},                             # three instructions per k-step
                                  {"PIPER_B200_GRAPH": "0"},
                                  {"PIPER_B200_FLAT": "0"},                                # [item][channel][pitch] activations, per-item tiles
-                                 {"PIPER_B200_V2_ASTAT": "1"},                            # A-stationary tile order
+                                 {"PIPER_B200_V2_ASTAT": "0", "PIPER_B200_ATT_TAIL": "0"},   # streaming operand ring for every layer; every query tile on the tensor cores
                                  {"PIPER_B200_ATT_TM": "0", "PIPER_B200_V2_CHAIN_K": "0"},   # per-row TMA in attention; two K-chains everywhere
                                  {"PIPER_B200_LN2": "0", "PIPER_B200_POST2": "0", "PIPER_B200_ATT2": "0"},
                                  {"PIPER_B200_MMA": "15"},                                # layer-wise MRF stage

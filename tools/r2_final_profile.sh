@@ -7,8 +7,11 @@ cd "$(dirname "$0")/.."
 timeout -k 10 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/f_gpu_suite.log 2>&1; tail -3 gpurun_out/f_gpu_suite.log | cut -c1-200
 timeout 900 python bench.py > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err; cut -c1-220 gpurun_out/f_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/f_launches_bench.csv python bench.py --steps 2 --warmup 1 --quick > gpurun_out/f_ncu_bench.log 2>&1; wc -l gpurun_out/f_launches_bench.csv
-# DRAM traffic of the layer-wise generator ResBlock launches (indices 136..141 and 143..148 of a 151-launch step)
-PIPER_B200_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip $((151 + 136)) --launch-count 13 --csv --log-file gpurun_out/f_traffic.csv python tools/ncu_step.py 2 > gpurun_out/f_ncu_traffic.log 2>&1
+# launches per step (the fused MRF stage is the last one; before it: up3, 6 ResBlock convs, up2, 6 ResBlock convs, up1, conv_pre)
+NL=$(PIPER_B200_GRAPH=0 timeout 300 python tools/ncu_step.py 1 | sed -n 's/.*launches so far \([0-9]*\).*/\1/p' | tail -1)
+echo "launches per step: $NL"
+# DRAM traffic of the layer-wise generator ResBlock launches (the 13 launches NL-15 .. NL-3 of a step, the second upsampler in the middle)
+PIPER_B200_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --launch-skip $((NL + NL - 15)) --launch-count 13 --csv --log-file gpurun_out/f_traffic.csv python tools/ncu_step.py 2 > gpurun_out/f_ncu_traffic.log 2>&1
 python - <<'PY'
 import csv, hashlib, json
 rows = list(csv.reader(open("gpurun_out/f_traffic.csv")))
@@ -31,7 +34,7 @@ out = {"lib_sha16": sha, "source": "ncu dram__bytes_read.sum + dram__bytes_write
 json.dump(out, open("gpurun_out/r02_traffic.json", "w"), indent=1)
 print("traffic per launch", tot / max(len(rb), 1) / 1e6, "MB over", len(rb), "launches; lib", sha)
 PY
-PIPER_B200_GRAPH=0 timeout 600 ncu --set full --import-source on --clock-control none --launch-skip $((151 + 148)) --launch-count 1 -f -o gpurun_out/f_full_rb2k7 python tools/ncu_step.py 2 > gpurun_out/f_ncu_full.log 2>&1
+PIPER_B200_GRAPH=0 timeout 600 ncu --set full --import-source on --clock-control none --launch-skip $((NL + NL - 3)) --launch-count 1 -f -o gpurun_out/f_full_rb2k7 python tools/ncu_step.py 2 > gpurun_out/f_ncu_full.log 2>&1
 ncu -i gpurun_out/f_full_rb2k7.ncu-rep --page raw --csv > gpurun_out/f_full_rb2k7.raw.csv 2>/dev/null
 ncu -i gpurun_out/f_full_rb2k7.ncu-rep --page details --csv > gpurun_out/f_full_rb2k7.details.csv 2>/dev/null
 ls -la gpurun_out/f_full_rb2k7.ncu-rep | awk '{print $5}'
