@@ -43,7 +43,7 @@ bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float
   static int g_tail = -1;
   if (g_tail < 0) {
     const char* e = std::getenv("PIPER_B200_ATT_TAIL");
-    g_tail = e ? std::atoi(e) : 32;
+    g_tail = e ? std::atoi(e) : 16;                      // rows; at most 128
   }
   if (tail_thr && g_tail > 0 && a.q_tiles >= 2 && (long long)a.q_tiles * n_heads * B > 148) a.tail_thr = *tail_thr = g_tail;
   const int smem = att::smem_bytes(dk) + 128;

@@ -7,6 +7,7 @@
 //     O_i     = sum_j P[i,j] v_j      +  sum_{|j-i|<=w} P[i,j] emb_rel_v[j-i+w]
 // and modules.LayerNorm (modules.py:23-26): LayerNorm over the CHANNEL axis, eps 1e-5.
 #include "kernels.cuh"
+#include <algorithm>
 #include "launch.cuh"
 
 #include <cstdlib>
@@ -331,6 +332,164 @@ __global__ void __launch_bounds__(256) rel_attention_kernel2(View qkv, View out,
   }
 }
 
+// The rows of a SHORT last 128-query tile (launch_rel_attention: tail mode), key-parallel: one CTA per (utterance, head,
+// ATT_QPW rows); every warp walks its own share of the 32-key chunks (chunk c for warp c % n_w) with a private K / V
+// stage and its own online-softmax state, the states are merged at the end (m = max, l and the accumulators rescaled).
+// Same arithmetic per key as rel_attention_kernel2; only the order in which the chunks meet differs.  With the generic
+// kernel in tail mode one warp per CTA walked all nine chunks of a 259-id utterance behind block-wide barriers (~60 us
+// per launch, as long as the tensor-core CTAs it was meant to relieve).
+__global__ void __launch_bounds__(256) rel_attention_tail_kernel(View qkv, View out, const float* __restrict__ rel_k,
+                                                                 const float* __restrict__ rel_v, int H, int dk, int window,
+                                                                 const int* __restrict__ len, int tail_thr, int n_w) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sm[];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int T = len[b];
+  const int q0 = T > 0 ? ((T - 1) / 128) * 128 : 0;
+  if (T <= 0 || q0 == 0 || T - q0 > tail_thr) return;
+  const int i0 = q0 + blockIdx.x * ATT_QPW;
+  if (i0 >= T) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nrel = 2 * window + 1;
+  float* Qs = sm;                               // [dk][ATT_QPW]
+  float* Rl = Qs + dk * ATT_QPW;                // [ATT_QPW][nrel]
+  float* Ev = Rl + ATT_QPW * nrel + (4 - (ATT_QPW * nrel) % 4) % 4;   // [nrel][dk]
+  float* stage = Ev + nrel * dk;                // per warp: K [dk][33] | V [dk][33]; afterwards the partial states
+  const float* base = qkv.p + (long long)b * qkv.bs;
+  const float* qg = base + (long long)(h * dk) * qkv.cs;
+  const float* kg = base + (long long)(H + h * dk) * qkv.cs;
+  const float* vg = base + (long long)(2 * H + h * dk) * qkv.cs;
+  for (int idx = threadIdx.x; idx < ATT_QPW * dk; idx += 256) {
+    const int d = idx / ATT_QPW, qq = idx - d * ATT_QPW;
+    const int i = i0 + qq;
+    Qs[d * ATT_QPW + qq] = i < T ? qg[(long long)d * qkv.cs + i] / sqrtf((float)dk) : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < nrel * dk; idx += 256) Ev[idx] = rel_v[idx];
+  __syncthreads();
+  for (int pr = warp; pr < ATT_QPW * nrel; pr += 8) {      // relative-key logits Rl[qq][r] = q . emb_rel_k[r]
+    const int qq = pr / nrel, r = pr - qq * nrel;
+    float p = 0.f;
+    for (int d = lane; d < dk; d += 32) p += Qs[d * ATT_QPW + qq] * __ldg(rel_k + r * dk + d);
+    for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if (lane == 0) Rl[pr] = p;
+  }
+  __syncthreads();
+
+  float m_run[ATT_QPW], l_run[ATT_QPW], acc[ATT_QPW][ATT_MAXR];
+#pragma unroll
+  for (int qq = 0; qq < ATT_QPW; ++qq) {
+    m_run[qq] = -INFINITY;
+    l_run[qq] = 0.f;
+#pragma unroll
+    for (int r = 0; r < ATT_MAXR; ++r) acc[qq][r] = 0.f;
+  }
+  if (warp < n_w) {
+    float* Ks = stage + (size_t)warp * 2 * dk * 33;
+    float* Vs = Ks + dk * 33;
+    for (int j0 = warp * 32; j0 < T; j0 += n_w * 32) {
+      __syncwarp();
+      const int j = j0 + lane;
+      for (int d = 0; d < dk; ++d) {
+        Ks[d * 33 + lane] = j < T ? kg[(long long)d * qkv.cs + j] : 0.f;
+        Vs[d * 33 + lane] = j < T ? vg[(long long)d * qkv.cs + j] : 0.f;
+      }
+      __syncwarp();
+      const int jn = min(32, T - j0);
+      float s[ATT_QPW];
+#pragma unroll
+      for (int qq = 0; qq < ATT_QPW; ++qq) s[qq] = 0.f;
+      const float4* qw = reinterpret_cast<const float4*>(Qs);
+      for (int d = 0; d < dk; ++d) {
+        const float kd = Ks[d * 33 + lane];
+        const float4 q4 = qw[d];
+        s[0] = fmaf(q4.x, kd, s[0]);
+        s[1] = fmaf(q4.y, kd, s[1]);
+        s[2] = fmaf(q4.z, kd, s[2]);
+        s[3] = fmaf(q4.w, kd, s[3]);
+      }
+      float p[ATT_QPW];
+#pragma unroll
+      for (int qq = 0; qq < ATT_QPW; ++qq) {
+        const int i = i0 + qq;
+        float sc = s[qq];
+        const int rel = j - i + window;
+        if (rel >= 0 && rel < nrel) sc += Rl[qq * nrel + rel];
+        if (j >= T || i >= T) sc = -INFINITY;
+        float cmax = sc;
+        for (int o = 16; o; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        const float m_new = fmaxf(m_run[qq], cmax);
+        const float corr = (m_new == -INFINITY) ? 1.f : expf(m_run[qq] - m_new);
+        p[qq] = (m_new == -INFINITY) ? 0.f : expf(sc - m_new);
+        float psum = p[qq];
+        for (int o = 16; o; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        l_run[qq] = l_run[qq] * corr + psum;
+#pragma unroll
+        for (int r = 0; r < ATT_MAXR; ++r) acc[qq][r] *= corr;
+        m_run[qq] = m_new;
+        const int jlo = max(j0, i - window), jhi = min(j0 + jn - 1, i + window);   // banded relative values
+        for (int jb = jlo; jb <= jhi; ++jb) {
+          const float pj = __shfl_sync(0xffffffffu, p[qq], jb - j0);
+          const int relj = jb - i + window;
+#pragma unroll
+          for (int r = 0; r < ATT_MAXR; ++r) {
+            const int d = lane + 32 * r;
+            if (d < dk) acc[qq][r] = fmaf(pj, Ev[relj * dk + d], acc[qq][r]);
+          }
+        }
+      }
+      for (int jj = 0; jj < jn; ++jj) {
+        float pj[ATT_QPW];
+#pragma unroll
+        for (int qq = 0; qq < ATT_QPW; ++qq) pj[qq] = __shfl_sync(0xffffffffu, p[qq], jj);
+#pragma unroll
+        for (int r = 0; r < ATT_MAXR; ++r) {
+          const int d = lane + 32 * r;
+          if (d < dk) {
+            const float v = Vs[d * 33 + jj];
+#pragma unroll
+            for (int qq = 0; qq < ATT_QPW; ++qq) acc[qq][r] = fmaf(pj[qq], v, acc[qq][r]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();                                   // every warp is done with its stage: reuse it for the partial states
+  float* Pm = stage;                                 // [n_w][ATT_QPW]
+  float* Pl = Pm + 8 * ATT_QPW;                      // [n_w][ATT_QPW]
+  float* Pa = Pl + 8 * ATT_QPW;                      // [n_w][ATT_QPW][128]
+  if (warp < n_w) {
+#pragma unroll
+    for (int qq = 0; qq < ATT_QPW; ++qq) {
+      if (lane == 0) { Pm[warp * ATT_QPW + qq] = m_run[qq]; Pl[warp * ATT_QPW + qq] = l_run[qq]; }
+#pragma unroll
+      for (int r = 0; r < ATT_MAXR; ++r) Pa[(warp * ATT_QPW + qq) * 128 + lane + 32 * r] = acc[qq][r];
+    }
+  }
+  __syncthreads();
+  if (warp < ATT_QPW) {
+    const int qq = warp, i = i0 + qq;
+    if (i < T) {
+      float M = -INFINITY;
+      for (int w = 0; w < n_w; ++w) M = fmaxf(M, Pm[w * ATT_QPW + qq]);
+      float Lsum = 0.f, o[ATT_MAXR] = {0.f, 0.f, 0.f, 0.f};
+      for (int w = 0; w < n_w; ++w) {
+        const float mw = Pm[w * ATT_QPW + qq];
+        const float f = mw == -INFINITY ? 0.f : expf(mw - M);
+        Lsum = fmaf(Pl[w * ATT_QPW + qq], f, Lsum);
+#pragma unroll
+        for (int r = 0; r < ATT_MAXR; ++r) o[r] = fmaf(Pa[(w * ATT_QPW + qq) * 128 + lane + 32 * r], f, o[r]);
+      }
+      float* ob = out.p + (long long)b * out.bs + (long long)(h * dk) * out.cs;
+#pragma unroll
+      for (int r = 0; r < ATT_MAXR; ++r) {
+        const int d = lane + 32 * r;
+        if (d < dk) ob[(long long)d * out.cs + i] = o[r] / Lsum;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // LayerNorm over channels for a tile of 32 time steps; 8 warps split the channel axis.
@@ -555,11 +714,23 @@ void launch_rel_attention(View qkv, View out, const float* rel_k, const float* r
     if (tail_thr > 0) {                                  // short last tiles: the CUDA-core kernel, one CTA per ATT_Q rows
       static bool attr2[64] = {};
       if (!attr2[dev & 63]) {
-        cudaFuncSetAttribute(rel_attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(rel_attention_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
         attr2[dev & 63] = true;
       }
-      launch_k(rel_attention_kernel2, dim3((tail_thr + ATT_Q - 1) / ATT_Q, n_heads, B), dim3(256), smem, st, qkv, out, rel_k, rel_v, H,
-               dk, window, len, tail_thr);
+      // warps that walk key chunks: as many private K | V stages as fit (8 for dk = 96, 5 for dk = 128); the same region
+      // later holds the 8 x ATT_QPW x (128 + 2) partial states
+      const size_t fixed = size_t(dk * ATT_QPW + ATT_QPW * nrel + 4 + nrel * dk) * sizeof(float);
+      const size_t per_warp = size_t(2) * dk * 33 * sizeof(float), part = size_t(8) * ATT_QPW * 130 * sizeof(float);
+      int n_w = int(std::min<size_t>(8, (size_t(212) * 1024 - fixed) / per_warp));
+      if (n_w >= 1) {
+        const size_t smem_t = fixed + std::max(per_warp * n_w, part);
+        launch_k(rel_attention_tail_kernel, dim3((tail_thr + ATT_QPW - 1) / ATT_QPW, n_heads, B), dim3(256), smem_t, st, qkv, out,
+                 rel_k, rel_v, H, dk, window, len, tail_thr, n_w);
+      } else {
+        cudaFuncSetAttribute(rel_attention_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        launch_k(rel_attention_kernel2, dim3((tail_thr + ATT_Q - 1) / ATT_Q, n_heads, B), dim3(256), smem, st, qkv, out, rel_k, rel_v, H,
+                 dk, window, len, tail_thr);
+      }
       count_launch();
     }
     return;
