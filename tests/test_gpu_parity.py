@@ -225,6 +225,23 @@ def test_full_size_properties_medium_batch32():
     assert np.abs(out - outs3[0]).max() <= 2e-4
 
 
+def test_attention_short_last_tiles_on_the_tail_kernel():
+    """40 utterances of 131 .. 147 ids: one full 128-query tile + 3 .. 19 rows, and 40 x 2 heads x 2 tiles = 160 tiles > 148
+    SMs, so last tiles of <= 16 rows go to the key-parallel CUDA-core kernel (encoder.cu: rel_attention_tail_kernel) and the
+    longer ones stay on the tensor cores (attentions.py:225-272 either way); items of both kinds against the oracle, and the
+    encoder output tap of the whole batch is finite."""
+    voice, orc = _pair("synthetic:medium:1234")
+    ids_list = [voicegen.benchmark_ids(64 + (i % 9), seed=50 + i) for i in range(40)]
+    assert {len(i) for i in ids_list} == set(range(131, 148, 2))
+    rng = np.random.default_rng(3)
+    eps_dp = [rng.standard_normal((2, len(i))).astype(np.float32) for i in ids_list]
+    eps_z = rng.standard_normal((40, orc.s.inter, 6 * 147)).astype(np.float32)
+    outs, _ = voice.synthesize_batch(ids_list, (0.667, 1.0, 0.8), eps_dp, eps_z)
+    for b in (0, 5, 8, 26, 39):                          # 131, 141, 147, 147, 137 ids: tails of 3, 13, 19, 19, 9 rows
+        ref = orc.infer(ids_list[b], (0.667, 1.0, 0.8), eps_dp[b], eps_z[b])
+        assert outs[b].shape == ref.shape and np.abs(outs[b] - ref).max() <= TOL, (b, len(ids_list[b]))
+
+
 def test_high_ragged_batch8_matches_per_item_oracle():
     """BASELINE.json configs[3]'s per-GPU share: the "high" preset (ResBlock1, 512-channel generator,
     piper_train/__main__.py:72-82), 8 ragged utterances of up to 128 phonemes in ONE batch launch, every item against its own

@@ -4,7 +4,11 @@
 set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-timeout -k 10 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/f_gpu_suite.log 2>&1; tail -3 gpurun_out/f_gpu_suite.log | cut -c1-200
+if [ "${SUITE:-1}" = "1" ]; then
+  timeout -k 10 1500 python -m pytest tests -m gpu -q -n 4 --timeout 900 > gpurun_out/f_gpu_suite.log 2>&1; tail -3 gpurun_out/f_gpu_suite.log | cut -c1-200
+else
+  timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "tail_kernel or batch32" > gpurun_out/f_gpu_suite.log 2>&1; tail -3 gpurun_out/f_gpu_suite.log | cut -c1-200
+fi
 timeout 900 python bench.py > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err; cut -c1-220 gpurun_out/f_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/f_launches_bench.csv python bench.py --steps 2 --warmup 1 --quick > gpurun_out/f_ncu_bench.log 2>&1; wc -l gpurun_out/f_launches_bench.csv
 # launches per step (the fused MRF stage is the last one; before it: up3, 6 ResBlock convs, up2, 6 ResBlock convs, up1, conv_pre)
