@@ -307,6 +307,18 @@ def lib_sha16() -> str:
     return hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
 
 
+def kernel_src_sha16() -> str:
+    """Hash of the sources that are compiled into libpiper_b200.so (piper_b200/csrc/*.{cu,cuh,inl,h,cc}, Makefile; not shim/)."""
+    d = os.path.join(ROOT, "piper_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".inl", ".h", ".cc")) or name == "Makefile":
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "piper_b200.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def conv_rooflines(voice, run, prof_steps, peaks, pipe_peaks, prec):
     """CUDA events around every conv launch (engine profile mode), aggregated per family; for each family the HBM
     fraction (algorithmic bytes) and the tensor/FMA-pipe fraction (algorithmic FLOP), and which one binds."""
@@ -357,7 +369,9 @@ def conv_rooflines(voice, run, prof_steps, peaks, pipe_peaks, prec):
     tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
-        if t.get("lib_sha16") == lib_sha16():
+        # (the library file's hash, or - a rebuild of the same sources need not be byte-identical - the hash of the sources
+        # that go into it)
+        if t.get("lib_sha16") == lib_sha16() or (t.get("src_sha16") and t.get("src_sha16") == kernel_src_sha16()):
             roofline["traffic"] = t.get("families", {}).get(dom, {}).get("dram_bytes_per_launch")
             roofline["traffic_source"] = t.get("source")
     return roofline

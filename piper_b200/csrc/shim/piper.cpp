@@ -59,6 +59,15 @@ void parsePhonemizeConfig(const json& root, PhonemizeConfig& pc) {
       const Phoneme p = getCodepoint(kv.first);
       for (const json& id : kv.second.arr) pc.phonemeIdMap[p].push_back(PhonemeId(id.number()));
     }
+    // pad / bos / eos are phonemes of the voice's own map ('_', '^', '$': piper-phonemize's PhonemeIdConfig defaults, which
+    // is what piper.cpp:540-560 hands to phonemes_to_ids); the struct defaults 0 / 1 / 2 only stand in when a map lacks them
+    auto first_id = [&](Phoneme p, PhonemeId& out) {
+      auto it = pc.phonemeIdMap.find(p);
+      if (it != pc.phonemeIdMap.end() && !it->second.empty()) out = it->second.front();
+    };
+    first_id(U'_', pc.idPad);
+    first_id(U'^', pc.idBos);
+    first_id(U'$', pc.idEos);
   }
   if (const json* m = root.find("phoneme_map")) {
     if (!pc.phonemeMap) pc.phonemeMap.emplace();
