@@ -319,7 +319,7 @@ def kernel_src_sha16() -> str:
     return h.hexdigest()[:16]
 
 
-def conv_rooflines(voice, run, prof_steps, peaks, pipe_peaks, prec):
+def conv_rooflines(voice, run, prof_steps, peaks, pipe_peaks, prec, config_id=3):
     """CUDA events around every conv launch (engine profile mode), aggregated per family; for each family the HBM
     fraction (algorithmic bytes) and the tensor/FMA-pipe fraction (algorithmic FLOP), and which one binds."""
     voice.set_profile(True)
@@ -371,7 +371,8 @@ def conv_rooflines(voice, run, prof_steps, peaks, pipe_peaks, prec):
         t = json.load(open(tpath))
         # (the library file's hash, or - a rebuild of the same sources need not be byte-identical - the hash of the sources
         # that go into it)
-        if t.get("lib_sha16") == lib_sha16() or (t.get("src_sha16") and t.get("src_sha16") == kernel_src_sha16()):
+        same_build = t.get("lib_sha16") == lib_sha16() or (t.get("src_sha16") and t.get("src_sha16") == kernel_src_sha16())
+        if same_build and t.get("config", 3) == config_id:      # (the capture is of one configuration's launches)
             roofline["traffic"] = t.get("families", {}).get(dom, {}).get("dram_bytes_per_launch")
             roofline["traffic_source"] = t.get("source")
     return roofline
@@ -490,7 +491,7 @@ def run_engine(args):
     peaks = measured_peaks()
     pipe_peaks = measure_pipe_peaks(torch) if (rank == 0 and not args.quick) else {"tf32_tflops": 1.0, "fp32_fma_tflops": 1.0}
     prec = engine_precision()
-    roofline = conv_rooflines(voice, voice.run_staged, 2, peaks, pipe_peaks, prec)
+    roofline = conv_rooflines(voice, voice.run_staged, 2, peaks, pipe_peaks, prec, args.config)
 
     # ---------------- batch = 1 latency / real-time factor / time to first streamed chunk (BASELINE.json configs[1])
     b1 = batch1_latency(voice, ids_list[0])
