@@ -240,9 +240,16 @@ void textToAudio(PiperConfig& config, Voice& voice, std::string text, std::vecto
                  SynthesisResult& result, const std::function<void()>& audioCallback) {
   std::vector<std::vector<Phoneme>> sentences;
   if (voice.phonemizeConfig.phonemeType == TextPhonemes) {
-    // phonemize_codepoints: one "sentence" of raw codepoints
+    // phonemize_codepoints: one "sentence" of codepoints.  piper-phonemize (a dependency that is not in the reference tree;
+    // CodepointsPhonemeConfig, casing = CASING_FOLD by default) case-folds and NFD-normalises the text first.  Folding is
+    // done here for ASCII and the Latin-1 letters (one-to-one lower-casing); full Unicode case folding and decomposition
+    // need the Unicode tables and stay with the host: pass text that is already case-folded / NFD if the voice needs it.
     sentences.emplace_back();
-    for (size_t i = 0; i < text.size();) sentences.back().push_back(decode_utf8(text, i));
+    for (size_t i = 0; i < text.size();) {
+      Phoneme c = decode_utf8(text, i);
+      if ((c >= U'A' && c <= U'Z') || (c >= 0xC0 && c <= 0xDE && c != 0xD7)) c += 32;
+      sentences.back().push_back(c);
+    }
   } else {
     if (!config.phonemizer)
       throw std::runtime_error(
