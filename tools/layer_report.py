@@ -16,25 +16,33 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--arch", default="medium")
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--from-json", default=None, help="re-print a saved gpurun_out/layer_report.json with the current model (no GPU)")
 a = ap.parse_args()
 
-v = engine.Voice(voicegen.cached_voice(a.arch), 0)
-ids = [voicegen.benchmark_ids(128, seed=1234 + b) for b in range(a.batch)]
-v.stage(ids, (0.667, 1.0, 0.8), seed=4242)
-for _ in range(3):
-    v.run_staged()
-v.set_profile(True)
-runs = []
-for _ in range(a.steps):
-    n, ms = v.run_staged()
-    runs.append(v.profile_launches())
-v.set_profile(False)
+if a.from_json:
+    saved = json.load(open(a.from_json))
+    runs = [[{k: r[k] for k in r if k not in ("n_tile", "n_tiles", "mt", "tiles", "t_hbm", "t_mma", "t_w", "t_tma", "bound")} for r in saved]]
+    n, ms = 0, float("nan")
+else:
+  v = engine.Voice(voicegen.cached_voice(a.arch), 0)
+  ids = [voicegen.benchmark_ids(128, seed=1234 + b) for b in range(a.batch)]
+  v.stage(ids, (0.667, 1.0, 0.8), seed=4242)
+  for _ in range(3):
+      v.run_staged()
+  v.set_profile(True)
+  runs = []
+  for _ in range(a.steps):
+      n, ms = v.run_staged()
+      runs.append(v.profile_launches())
+  v.set_profile(False)
 n_l = len(runs[0])
 assert all(len(r) == n_l for r in runs)
 pm.B = a.batch
-# model the kernel that is actually running (opt-in variants are selected by environment variables)
-if os.environ.get("PIPER_B200_V2"):
-    pm.V2, pm.F16, pm.TMA_CYC = True, os.environ.get("PIPER_B200_V2_PREC") == "f16", 20.0
+# model the kernel that is actually running (the defaults since round 2: second-generation kernel, fp16x3, tensor-map TMA;
+# the first-generation kernels are selected by PIPER_B200_V2=0)
+if os.environ.get("PIPER_B200_V2", "2") != "0":
+    pm.V2, pm.F16 = True, os.environ.get("PIPER_B200_V2_PREC", "f16") == "f16"
+    pm.TMA_CYC = 0.0 if os.environ.get("PIPER_B200_V2_TM", "1") != "0" else 20.0
 elif os.environ.get("PIPER_B200_UNI"):
     pm.TMA_CYC = 20.0
 rows = []
@@ -53,7 +61,8 @@ for i in range(n_l):
                  t_mma=m["t_mma"] * scale * 1e6, t_w=m["t_w"] * scale * 1e6, t_tma=m["t_tma"] * scale * 1e6)
         r["bound"] = max(r["t_hbm"], r["t_mma"], r["t_w"], r["t_tma"])
     rows.append(r)
-print(f"{a.arch}, {a.batch} utterances: {n} samples in {ms:.3f} ms (profiled step), {n_l} conv launches")
+print(f"{a.arch}, {a.batch} utterances: " + (f"saved launch records of {a.from_json} re-modelled" if a.from_json else f"{n} samples in {ms:.3f} ms (profiled step)") + f", {n_l} conv launches")
+print("bounds: t_hbm = algorithmic bytes / copy peak; t_mma = tcgen05 instructions x max(N/2, 32 + N/4) cycles (measured pacing, tools/perf_model.py); t_w = weight stream L2 -> SM; us/bound against the largest")
 print(f"{'#':>3s} {'tag':8s} {'ci':>4s} {'rows':>5s} {'k':>2s} {'d':>2s} {'N':>4s} {'mt':>3s} {'tiles':>6s} | {'us':>7s} | {'t_hbm':>6s} {'t_mma':>6s} {'t_w':>6s} {'t_tma':>6s} | {'us/bound':>8s}")
 fam = {}
 for i, r in enumerate(rows):
@@ -74,4 +83,5 @@ print("\nfamily    launches   measured ms   bound ms   ratio")
 for k, (us, b, c) in fam.items():
     print(f"{k:9s} {c:8d} {us / 1e3:13.3f} {b / 1e3:10.3f} {us / b:7.2f}")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "layer_report.json"), "w"))
+if not a.from_json:
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "layer_report.json"), "w"))

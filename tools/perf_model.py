@@ -30,13 +30,17 @@ L2_B_PER_CLK_SM = 6300.0 / SMS
 STACK = "--stack" in sys.argv
 V2 = "--v2" in sys.argv
 F16 = "--f16" in sys.argv
-TMA_CYC = 20.0 if V2 else 150.0
+TMA_CYC = 20.0 if V2 else 150.0   # (tools/layer_report.py sets 0 for the tensor-map kernel: one copy per channel chunk)
 
 B, T, TP = 32, 259, 509          # utterances, ids, frames per utterance (bench: 4 071 680 samples / 256 / 32 = 497..520)
 
 
 def mma_cost(n):                  # cycles per tcgen05.mma, M = 128, K = 32 bytes
-    return (4096 + 32 * n) / 128 + 8
+    # round 2, measured with the kernel's exact instruction stream (tools/probe/mma_probe.cu, profiles/r02_mma_probe_*.txt):
+    # 64 / 49 / ~40 cycles at N = 128 / 64 / 32 = the larger of the tensor-pipe floor 128 N / 256 and the time its A
+    # (128 x 32 B) and B (N x 32 B) operands take to leave shared memory at 128 B/clk.  (Round 1 fitted (4096 + 32 N) / 128 + 8
+    # to tools/mma_bench.py, which included the issue loop.)
+    return max(n / 2.0, 32.0 + n / 4.0)
 
 
 def plan(ci, rows, k, dil, tf32):
