@@ -12,10 +12,12 @@ using namespace pb200;
 using namespace simtc;
 
 // qkv [B][3H][cs], out [B][H][cs], rel_k / rel_v [9][dk], len [B]
-extern "C" int att_sim_run(const float* qkv, float* out, const float* rel_k, const float* rel_v, const int* len, int B, int H,
-                           int n_heads, int cs, int Tmax, char* err, int errcap, int tm, int flat) {
+// tail_thr > 0: the launcher's tail mode - a last query tile of at most tail_thr rows is left to the CUDA-core kernel
+extern "C" int att_sim_run2(const float* qkv, float* out, const float* rel_k, const float* rel_v, const int* len, int B, int H,
+                            int n_heads, int cs, int Tmax, char* err, int errcap, int tm, int flat, int tail_thr) {
   try {
     att::Args a;
+    a.tail_thr = tail_thr;
     // flat: the caller passes [channel][item][cs] tensors
     a.qkv = flat ? View{const_cast<float*>(qkv), (long long)cs, B * cs} : View{const_cast<float*>(qkv), (long long)3 * H * cs, cs};
     a.out = flat ? View{out, (long long)cs, B * cs} : View{out, (long long)H * cs, cs};
@@ -42,4 +44,9 @@ extern "C" int att_sim_run(const float* qkv, float* out, const float* rel_k, con
     if (err && errcap > 0) std::snprintf(err, size_t(errcap), "%s", e.what());
     return 1;
   }
+}
+
+extern "C" int att_sim_run(const float* qkv, float* out, const float* rel_k, const float* rel_v, const int* len, int B, int H,
+                           int n_heads, int cs, int Tmax, char* err, int errcap, int tm, int flat) {
+  return att_sim_run2(qkv, out, rel_k, rel_v, len, B, H, n_heads, cs, Tmax, err, errcap, tm, flat, 0);
 }

@@ -78,3 +78,38 @@ def test_tensor_core_attention_on_cpu_model(sim, H, n_heads, lens, mode):
             e = float((got - ref).abs().max())
             assert e <= 2e-5 * max(1.0, float(ref.abs().max())), (b, h, e)
         assert np.all(out[b, :, T:] == 7e7), "stored outside the utterance"
+
+
+def test_short_last_tiles_are_left_to_the_tail_kernel(sim):
+    """Tail mode of the launcher (att_mma.cu: more query tiles than SMs): a LAST tile of at most tail_thr rows is skipped -
+    its rows stay untouched for encoder.cu's rel_attention_tail_kernel - every other tile is computed as before."""
+    H, n_heads, lens, thr = 32, 2, (259, 131, 200, 16, 144), 16
+    B, dk = len(lens), H // n_heads
+    Tmax = max(lens)
+    cs = (Tmax + 3) & ~3
+    rng = np.random.default_rng(5)
+    qkv = rng.standard_normal((B, 3 * H, cs)).astype(np.float32) * 30.0
+    for b, T in enumerate(lens):
+        qkv[b, :, :T] = rng.standard_normal((3 * H, T)).astype(np.float32) * np.float32(1.5)
+    rel_k = (rng.standard_normal((9, dk)) * 0.3).astype(np.float32)
+    rel_v = (rng.standard_normal((9, dk)) * 0.3).astype(np.float32)
+    out = np.full((B, H, cs), 7e7, np.float32)
+    lens_a = np.asarray(lens, np.int32)
+    err = C.create_string_buffer(512)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    rc = sim.att_sim_run2(fp(qkv), fp(out), fp(rel_k), fp(rel_v), lens_a.ctypes.data_as(C.POINTER(C.c_int32)), B, H, n_heads, cs, Tmax,
+                          err, len(err), 1, 0, thr)
+    assert rc == 0, err.value.decode()
+    for b, T in enumerate(lens):
+        q0 = (T - 1) // 128 * 128
+        skipped = q0 > 0 and T - q0 <= thr                               # 259 -> rows 256.., 131 -> rows 128.., 144 -> rows 128..; 200 and 16 are computed
+        done = q0 if skipped else T
+        assert np.all(out[b, :, done:] == 7e7), (b, "rows of a skipped tile / past the utterance were written")
+        for h in range(n_heads):
+            q = torch.from_numpy(qkv[b, h * dk:(h + 1) * dk, :T])
+            k = torch.from_numpy(qkv[b, H + h * dk:H + (h + 1) * dk, :T])
+            v = torch.from_numpy(qkv[b, 2 * H + h * dk:2 * H + (h + 1) * dk, :T])
+            ref = _reference(q, k, v, torch.from_numpy(rel_k), torch.from_numpy(rel_v))
+            got = torch.from_numpy(np.ascontiguousarray(out[b, h * dk:(h + 1) * dk, :done]))
+            assert float((got - ref[:, :done]).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), (b, h)
+    assert any((T - 1) // 128 * 128 > 0 and T - (T - 1) // 128 * 128 <= thr for T in lens)
