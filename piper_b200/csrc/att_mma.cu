@@ -1,6 +1,6 @@
-// EXPERIMENTAL - OFF BY DEFAULT (PIPER_B200_ATT3=1).  CUDA instantiation of the tensor-core relative-position attention;
+// DEFAULT since round 2 (PIPER_B200_ATT3=0 selects the CUDA-core kernel).  CUDA instantiation of the tensor-core relative-position attention;
 // the body is att_body.inl (design notes there), the primitives tc_policy_dev.cuh.  The same body runs on the CPU model of
-// the primitives in tests/test_att_sim.py; it has NOT yet run on a GPU.
+// the primitives in tests/test_att_sim.py; on the B200 it is covered by the whole -m gpu suite.
 #include "kernels.cuh"
 #include "launch.cuh"
 

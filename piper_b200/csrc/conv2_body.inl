@@ -1,6 +1,6 @@
-// EXPERIMENTAL - OFF BY DEFAULT (PIPER_B200_V2=1).  Second-generation persistent tensor-core convolution, written against
+// Second-generation persistent tensor-core convolution (the default conv kernel since round 2), written against
 // the primitive policy P (tc_policy_dev.cuh on the GPU, tests/sim/sim_prim.h on the CPU) so that its logic is checked by
-// tests/test_conv2_sim.py without a GPU.  NOT yet run on hardware.  Same GEMM view, data layout, ragged-batch rules and
+// tests/test_conv2_sim.py without a GPU.  Same GEMM view, data layout, ragged-batch rules and
 // fused epilogues as conv_mma_persist_kernel (conv_mma.cu); what changes, from the round-1 measurements:
 //
 //   * both TMA warps run converged and issue from an elected lane, so copy operands live in uniform registers (the

@@ -1,7 +1,7 @@
-// EXPERIMENTAL - OFF BY DEFAULT (PIPER_B200_V2=1).  CUDA instantiation of the second-generation persistent tensor-core
+// DEFAULT since round 2 (PIPER_B200_V2=0 selects conv_mma.cu).  CUDA instantiation of the second-generation persistent tensor-core
 // convolution: the body lives in conv2_body.inl (what changes against conv_mma.cu is described there), the primitives
 // in tc_policy_dev.cuh, plan / pack / argument fill in conv2_host.h.  The same body runs on a CPU model of the primitives
-// in tests/test_conv2_sim.py (every epilogue, both split precisions, ragged batches); it has NOT yet run on a GPU.
+// in tests/test_conv2_sim.py (every epilogue, both split precisions, ragged batches); on the B200: tests/test_gpu_conv_kernels.py and the whole -m gpu suite.
 #include "kernels.cuh"
 #include "launch.cuh"
 

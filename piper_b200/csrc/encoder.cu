@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) rel_attention_kernel(View qkv, View out, 
   }
 }
 
-// EXPERIMENTAL (PIPER_B200_ATT2=1, off by default, not yet run on a GPU): the same kernel with the staged queries kept
+// Second version of the CUDA-core kernel (PIPER_B200_ATT2, default 1; used when PIPER_B200_ATT3=0): the same kernel with the staged queries kept
 // per warp as [d][4 queries], so the score loop issues one K load and ONE 16-byte broadcast load per 4 FMAs instead of one
 // K load and four scalar broadcast loads - the loop is bound by the shared-memory pipe.  Same
 // arithmetic in the same order as rel_attention_kernel.
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   }
 }
 
-// EXPERIMENTAL (PIPER_B200_LN2=1, off by default, not yet run on a GPU): same arithmetic as layernorm_kernel in the same
+// DEFAULT since round 2 (PIPER_B200_LN2=0 selects layernorm_kernel): same arithmetic as layernorm_kernel in the same
 // order, but every warp issues its global loads eight channel rows at a time before using any of them.  The shipped kernel
 // walks its 24 rows (C = 192) one dependent load -> store at a time in both passes, which is what its ~28 us per launch
 // (36 launches per step) looks like: ~2 x 24 exposed L2 / DRAM latencies with only 16 warps per SM to hide them.

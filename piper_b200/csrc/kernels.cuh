@@ -103,7 +103,7 @@ struct MmaConvArgs {
 void launch_conv_mma(MmaConvArgs a, const MmaPlan& p, int B, int max_len, cudaStream_t st);
 void run_mma_bench(int N, int tf32, int n_acc, int iters, int shift, unsigned long long out[2]);
 
-// ---- EXPERIMENTAL, off by default (PIPER_B200_V2=1): second-generation persistent tensor-core conv (conv_mma2.cu) ----
+// ---- second-generation persistent tensor-core conv (conv_mma2.cu; default since round 2, PIPER_B200_V2=0 = first generation) ----
 struct Conv2Layer {          // tiling of one layer + where its stacked weights live (filled lazily by the engine)
   bool tf32 = false;
   int prec = 0;              // 0 bf16x3, 1 tf32x3, 2 fp16x3 (conv2_body.inl)
@@ -116,7 +116,7 @@ void conv2_pack(const float* wsrc, int ci, int k, int rows_p, const Conv2Layer& 
 // false: the launch is too small for the persistent kernel (caller falls back to launch_conv_mma)
 bool launch_conv2(MmaConvArgs a, const Conv2Layer& l, int B, int max_len, cudaStream_t st);
 
-// ---- EXPERIMENTAL, off by default: one whole MRF stage (three resblocks) of the generator per launch (mrf_fused.cu) ----
+// ---- one whole MRF stage (three resblocks) of the generator per launch (mrf_fused.cu; default for 32-channel stages) ----
 constexpr int MRF_MAX_CHAINS = 3, MRF_MAX_STEPS = 6;
 struct MrfFusedPlan {
   bool ok = false;
@@ -168,7 +168,7 @@ void launch_embed(const int* ids, int ids_pitch, const float* emb, int H, float 
 void launch_rel_attention(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
                           const int* len, int B, int Tmax, cudaStream_t st);
 
-// EXPERIMENTAL, off by default (PIPER_B200_ATT3=1): the same attention on the tensor cores (att_mma.cu); false = shape not handled
+// the same attention on the tensor cores (att_mma.cu; default, PIPER_B200_ATT3=0 = CUDA cores); false = shape not handled
 bool launch_rel_attention_tc(View qkv, View out, const float* rel_k, const float* rel_v, int H, int n_heads, int window,
                              const int* len, int B, int Tmax, cudaStream_t st, int* tail_thr = nullptr);
 

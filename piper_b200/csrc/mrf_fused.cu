@@ -1,6 +1,6 @@
-// EXPERIMENTAL - OFF BY DEFAULT (engine mask bit 16 / PIPER_B200_MMA=31).  Written at the end of round 1 from the
-// per-launch measurements in profiles/r01_layer_report.txt; compiled and checked with ptxas here, NOT yet run on a GPU.
-// The shipped path is the layer-wise one in conv_mma.cu.  tools/fused_mrf_proto.py is the CPU statement of the same
+// DEFAULT since round 2 (engine mask bit 16; PIPER_B200_MMA=15 runs the stage layer-wise).  Written at the end of round 1 from the
+// per-launch measurements in profiles/r01_layer_report.txt; first run on a B200 in round 2 (profiles/r02_summary.md).
+// (The layer-wise path in conv_mma2.cu remains for the other stages.)  tools/fused_mrf_proto.py is the CPU statement of the same
 // tile algorithm and tests/test_fused_mrf_proto.py pins it against the oracle.
 //
 // One multi-receptive-field stage of the HiFi-GAN generator in a single persistent kernel, for the C = 32 stage (the last

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) conv_post_kernel(View x, const float* __r
   out[out_off[b] + t] = tanhf(acc);
 }
 
-// EXPERIMENTAL (PIPER_B200_POST2=1, off by default, not yet run on a GPU): the same computation in the same order, with the
+// DEFAULT since round 2 where the fused MRF stage does not apply (PIPER_B200_POST2=0 selects conv_post_kernel): the same computation in the same order, with the
 // staging loads of eight channels in flight at once.  The shipped kernel stages its C = 32 rows one exposed load latency
 // after the other (~0.58 ms per step for 0.5 GB, 7x the HBM time).
 __global__ void __launch_bounds__(256) conv_post_kernel2(View x, const float* __restrict__ w, int C, int k, float slope,
